@@ -1,0 +1,340 @@
+// GroupNorm(32, C) (+ residual add) (+ ReLU) forward / backward on NHWC bf16 activations.
+// Replaces the 53 ATen native_group_norm calls the reference makes after its BN->GN swap
+// (reference: src/networks/mask_rcnn.py:523-534).
+//
+// HBM-bound.  Forward = statistics (sum, sumsq per (n, group); skipped when the producing conv's
+// epilogue already emitted them) + one normalise/affine/add/ReLU pass (1 read [+1 residual read]
+// + 1 write).  Backward = one reduction pass + one apply pass.
+#include "common.h"
+#include "../../include/eosvos_b200.h"
+#include <cuda_bf16.h>
+
+namespace eosvos {
+
+constexpr int GN_GROUPS = 32;
+constexpr int GN_THREADS = 256;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics: sums[n][g] = (sum x, sum x^2).  grid = (chunks, N); C/8 must divide GN_THREADS.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums,
+                                                             int HW, int C, int chunk_pixels) {
+  __shared__ float sm[GN_GROUPS * 2];
+  const int n = blockIdx.y;
+  const int cv = C >> 3;                       // channel vectors per pixel
+  const int my_cv = threadIdx.x % cv;
+  const int pix_per_pass = GN_THREADS / cv;
+  const int p0 = blockIdx.x * chunk_pixels;
+  const int p1 = min(HW, p0 + chunk_pixels);
+  if (threadIdx.x < GN_GROUPS * 2) sm[threadIdx.x] = 0.f;
+  __syncthreads();
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+  const __nv_bfloat16* base = x + (size_t)n * HW * C + (size_t)my_cv * 8;
+  for (int p = p0 + threadIdx.x / cv; p < p1; p += pix_per_pass) {
+    float f[8];
+    load8(base + (size_t)p * C, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += f[k];
+      s2[k] += f[k] * f[k];
+    }
+  }
+  const int cpg = C / GN_GROUPS;
+  if (cpg >= 8) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a += s1[k];
+      b += s2[k];
+    }
+    const int g = (my_cv * 8) / cpg;
+    atomicAdd(&sm[g * 2], a);
+    atomicAdd(&sm[g * 2 + 1], b);
+  } else {
+    for (int k0 = 0; k0 < 8; k0 += cpg) {
+      float a = 0.f, b = 0.f;
+      for (int k = k0; k < k0 + cpg; ++k) {
+        a += s1[k];
+        b += s2[k];
+      }
+      const int g = (my_cv * 8 + k0) / cpg;
+      atomicAdd(&sm[g * 2], a);
+      atomicAdd(&sm[g * 2 + 1], b);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS * 2) atomicAdd(&sums[(size_t)n * GN_GROUPS * 2 + threadIdx.x], sm[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// apply: y = relu?( (x - mean) * rstd * gamma + beta  (+ res) )
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y,
+                int HW, int C, int chunk_pixels, float eps, int relu) {
+  const int n = blockIdx.y;
+  const int cv = C >> 3;
+  const int my_cv = threadIdx.x % cv;
+  const int pix_per_pass = GN_THREADS / cv;
+  const int cpg = C / GN_GROUPS;
+  const float inv_m = 1.f / ((float)cpg * (float)HW);
+  float a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = my_cv * 8 + k;
+    const int g = c / cpg;
+    const float mean = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
+    const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    a[k] = rstd * gamma[c];
+    b[k] = beta[c] - mean * a[k];
+  }
+  const int p0 = blockIdx.x * chunk_pixels;
+  const int p1 = min(HW, p0 + chunk_pixels);
+  const size_t base = (size_t)n * HW * C + (size_t)my_cv * 8;
+  for (int p = p0 + threadIdx.x / cv; p < p1; p += pix_per_pass) {
+    float f[8];
+    load8(x + base + (size_t)p * C, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = f[k] * a[k] + b[k];
+    if (res) {
+      float r[8];
+      load8(res + base + (size_t)p * C, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += r[k];
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    }
+    store8(y + base + (size_t)p * C, f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward pass 1: per (n, c): S1 = sum dy_eff, S2 = sum dy_eff * xhat  ->  part[n][c][2]
+//   mask_mode 0: dy_eff = dy;  1: dy_eff = dy * (xhat*gamma+beta > 0);  2: dy_eff = dy * (yout > 0)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sums,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yout,
+                     float* __restrict__ part, int HW, int C, int chunk_pixels, float eps, int mask_mode) {
+  extern __shared__ float smp[];  // [C][2]
+  const int n = blockIdx.y;
+  const int cv = C >> 3;
+  const int my_cv = threadIdx.x % cv;
+  const int pix_per_pass = GN_THREADS / cv;
+  const int cpg = C / GN_GROUPS;
+  const float inv_m = 1.f / ((float)cpg * (float)HW);
+  for (int i = threadIdx.x; i < C * 2; i += GN_THREADS) smp[i] = 0.f;
+  float mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = my_cv * 8 + k;
+    const int g = c / cpg;
+    mean[k] = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
+    const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean[k] * mean[k], 0.f);
+    rstd[k] = rsqrtf(var + eps);
+    ga[k] = gamma[c];
+    be[k] = beta[c];
+  }
+  __syncthreads();
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+  const int p0 = blockIdx.x * chunk_pixels;
+  const int p1 = min(HW, p0 + chunk_pixels);
+  const size_t base = (size_t)n * HW * C + (size_t)my_cv * 8;
+  for (int p = p0 + threadIdx.x / cv; p < p1; p += pix_per_pass) {
+    float f[8], d[8];
+    load8(x + base + (size_t)p * C, f);
+    load8(dy + base + (size_t)p * C, d);
+    float yo[8];
+    if (mask_mode == 2) load8(yout + base + (size_t)p * C, yo);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (f[k] - mean[k]) * rstd[k];
+      float de = d[k];
+      if (mask_mode == 1) de = (xh * ga[k] + be[k] > 0.f) ? de : 0.f;
+      if (mask_mode == 2) de = (yo[k] > 0.f) ? de : 0.f;
+      s1[k] += de;
+      s2[k] += de * xh;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    atomicAdd(&smp[(my_cv * 8 + k) * 2], s1[k]);
+    atomicAdd(&smp[(my_cv * 8 + k) * 2 + 1], s2[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += GN_THREADS) atomicAdd(&part[(size_t)n * C * 2 + i], smp[i]);
+}
+
+// backward pass 2: dx = rstd * (gamma*dy_eff - (A_g + xhat*B_g)/m);  optional d_res = dy_eff
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sums,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yout,
+                    const float* __restrict__ part, __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
+                    int HW, int C, int chunk_pixels, float eps, int mask_mode) {
+  __shared__ float gA[GN_GROUPS], gB[GN_GROUPS];
+  const int n = blockIdx.y;
+  const int cv = C >> 3;
+  const int my_cv = threadIdx.x % cv;
+  const int pix_per_pass = GN_THREADS / cv;
+  const int cpg = C / GN_GROUPS;
+  const float inv_m = 1.f / ((float)cpg * (float)HW);
+  if (threadIdx.x < GN_GROUPS) {
+    float A = 0.f, B = 0.f;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+      A += gamma[c] * part[((size_t)n * C + c) * 2];
+      B += gamma[c] * part[((size_t)n * C + c) * 2 + 1];
+    }
+    gA[threadIdx.x] = A * inv_m;
+    gB[threadIdx.x] = B * inv_m;
+  }
+  __syncthreads();
+  float mean[8], rstd[8], ga[8], be[8], cA[8], cB[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = my_cv * 8 + k;
+    const int g = c / cpg;
+    mean[k] = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
+    const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean[k] * mean[k], 0.f);
+    rstd[k] = rsqrtf(var + eps);
+    ga[k] = gamma[c];
+    be[k] = beta[c];
+    cA[k] = gA[g];
+    cB[k] = gB[g];
+  }
+  const int p0 = blockIdx.x * chunk_pixels;
+  const int p1 = min(HW, p0 + chunk_pixels);
+  const size_t base = (size_t)n * HW * C + (size_t)my_cv * 8;
+  for (int p = p0 + threadIdx.x / cv; p < p1; p += pix_per_pass) {
+    float f[8], d[8], yo[8];
+    load8(x + base + (size_t)p * C, f);
+    load8(dy + base + (size_t)p * C, d);
+    if (mask_mode == 2) load8(yout + base + (size_t)p * C, yo);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (f[k] - mean[k]) * rstd[k];
+      float de = d[k];
+      if (mask_mode == 1) de = (xh * ga[k] + be[k] > 0.f) ? de : 0.f;
+      if (mask_mode == 2) de = (yo[k] > 0.f) ? de : 0.f;
+      d[k] = de;
+      o[k] = rstd[k] * (ga[k] * de - cA[k] - xh * cB[k]);
+    }
+    store8(dx + base + (size_t)p * C, o);
+    if (dres) store8(dres + base + (size_t)p * C, d);
+  }
+}
+
+// dgamma[c] = sum_n part[n][c][1], dbeta[c] = sum_n part[n][c][0]
+__global__ void gn_bwd_param_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int N, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < N; ++n) {
+    b += part[((size_t)n * C + c) * 2];
+    a += part[((size_t)n * C + c) * 2 + 1];
+  }
+  dgamma[c] = a;
+  dbeta[c] = b;
+}
+
+static int gn_chunk(int HW, int N, int C, int* chunks) {
+  // ~4 CTAs per SM overall; each CTA covers >= one pass of pixels
+  const int pix_per_pass = GN_THREADS / (C >> 3);
+  int want = (4 * num_sms() + N - 1) / N;
+  int chunk = (HW + want - 1) / want;
+  chunk = ((chunk + pix_per_pass - 1) / pix_per_pass) * pix_per_pass;
+  if (chunk < pix_per_pass) chunk = pix_per_pass;
+  *chunks = (HW + chunk - 1) / chunk;
+  return chunk;
+}
+
+}  // namespace eosvos
+
+using namespace eosvos;
+
+static int gn_check(int N, int HW, int C) {
+  EOSVOS_REQUIRE(N > 0 && HW > 0, "groupnorm: empty tensor");
+  EOSVOS_REQUIRE(C % 32 == 0 && C >= 64 && C <= 2048 && (GN_THREADS % (C >> 3)) == 0,
+                 "groupnorm: C must be 64..2048 with C/8 dividing 256");
+  return 0;
+}
+
+extern "C" int eosvos_gn_stats(const void* x, float* sums, int N, int HW, int C, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_TRY(gn_check(N, HW, C));
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)N * GN_GROUPS * 2 * sizeof(float), stream);
+  if (e != cudaSuccess) return set_cuda_error(e, "gn_stats memset");
+  int chunks;
+  const int chunk = gn_chunk(HW, N, C, &chunks);
+  gn_stats_kernel<<<dim3(chunks, N), GN_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), sums, HW, C,
+                                                              chunk);
+  return check_launch("gn_stats_kernel");
+}
+
+extern "C" int eosvos_gn_apply(const void* x, const float* sums, const float* gamma, const float* beta, const void* res,
+                               void* y, int N, int HW, int C, float eps, int relu, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_TRY(gn_check(N, HW, C));
+  int chunks;
+  const int chunk = gn_chunk(HW, N, C, &chunks);
+  gn_apply_kernel<<<dim3(chunks, N), GN_THREADS, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), sums, gamma, beta, reinterpret_cast<const __nv_bfloat16*>(res),
+      reinterpret_cast<__nv_bfloat16*>(y), HW, C, chunk, eps, relu);
+  return check_launch("gn_apply_kernel");
+}
+
+// part: scratch [N][C][2] fp32 (zeroed here).  mask_mode: 0 none, 1 recompute ReLU mask, 2 mask from yout.
+extern "C" int eosvos_gn_backward(const void* x, const float* sums, const float* gamma, const float* beta,
+                                  const void* dy, const void* yout, float* part, void* dx, void* dres, float* dgamma,
+                                  float* dbeta, int N, int HW, int C, float eps, int mask_mode,
+                                  eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_TRY(gn_check(N, HW, C));
+  EOSVOS_REQUIRE(mask_mode != 2 || yout, "groupnorm backward: mask_mode 2 needs yout");
+  cudaError_t e = cudaMemsetAsync(part, 0, (size_t)N * C * 2 * sizeof(float), stream);
+  if (e != cudaSuccess) return set_cuda_error(e, "gn_backward memset");
+  int chunks;
+  const int chunk = gn_chunk(HW, N, C, &chunks);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(yout);
+  gn_bwd_reduce_kernel<<<dim3(chunks, N), GN_THREADS, (size_t)C * 2 * sizeof(float), stream>>>(
+      xb, sums, gamma, beta, dyb, yb, part, HW, C, chunk, eps, mask_mode);
+  EOSVOS_TRY(check_launch("gn_bwd_reduce_kernel"));
+  gn_bwd_apply_kernel<<<dim3(chunks, N), GN_THREADS, 0, stream>>>(xb, sums, gamma, beta, dyb, yb, part,
+                                                                  reinterpret_cast<__nv_bfloat16*>(dx),
+                                                                  reinterpret_cast<__nv_bfloat16*>(dres), HW, C, chunk,
+                                                                  eps, mask_mode);
+  EOSVOS_TRY(check_launch("gn_bwd_apply_kernel"));
+  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, dgamma, dbeta, N, C);
+  return check_launch("gn_bwd_param_kernel");
+}

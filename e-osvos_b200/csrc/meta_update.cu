@@ -1,0 +1,122 @@
+// MetaOptimizer parameter update, fused over all parameter tensors in one launch:
+//     p'[i] = p[i] - lr[row(i)] * g[i]        (lr = exp(log_lr) in log mode)
+// Reference: src/meta_optim/meta_optim.py:177-214 (step: exp, grad * lr per tensor) and
+// src/meta_optim/meta_model.py:78-80 (p - step per tensor) -- >= 402 elementwise launches there,
+// one here.  HBM-bound: 12 B / parameter (+ 4 B per learning-rate scalar).
+//
+// Also: the outer RAdam step of meta-training (src/util/radam.py:28-94 as used from
+// src/train_meta.py:361-373: grad / meta_batch, clamp, RAdam, lr clamp) as one flat kernel.
+#include "common.h"
+#include "../../include/eosvos_b200.h"
+
+namespace eosvos {
+
+constexpr int MU_THREADS = 256;
+constexpr int MU_CHUNK = 8192;  // elements per CTA
+
+// table: int64 [T][6] = (p, g, lr, out, numel, row_len) ; chunks: int32 [n][2] = (tensor, start / 4... in elements)
+__global__ void __launch_bounds__(MU_THREADS)
+meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ chunks, int use_log) {
+  const int t = chunks[blockIdx.x * 2];
+  const long long start = (long long)chunks[blockIdx.x * 2 + 1] * (long long)MU_CHUNK;
+  const long long* e = table + (size_t)t * 6;
+  const float* __restrict__ p = reinterpret_cast<const float*>(e[0]);
+  const float* __restrict__ g = reinterpret_cast<const float*>(e[1]);
+  const float* __restrict__ lr = reinterpret_cast<const float*>(e[2]);
+  float* __restrict__ out = reinterpret_cast<float*>(e[3]);
+  const long long numel = e[4];
+  const long long row_len = e[5];
+  long long n = numel - start;
+  if (n > MU_CHUNK) n = MU_CHUNK;
+  const bool aligned = (((e[0] | e[1] | e[3]) & 15) == 0);
+  if (aligned) {
+    const long long nv = n >> 2;
+    for (long long v = threadIdx.x; v < nv; v += MU_THREADS) {
+      const long long i = start + (v << 2);
+      const float4 pv = *reinterpret_cast<const float4*>(p + i);
+      const float4 gv = __ldcs(reinterpret_cast<const float4*>(g + i));
+      long long row = i / row_len;
+      long long col = i - row * row_len;
+      float l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float lv = __ldg(lr + row);
+        l[k] = use_log ? expf(lv) : lv;
+        if (++col == row_len) {
+          col = 0;
+          ++row;
+        }
+      }
+      float4 o;
+      o.x = pv.x - gv.x * l[0];
+      o.y = pv.y - gv.y * l[1];
+      o.z = pv.z - gv.z * l[2];
+      o.w = pv.w - gv.w * l[3];
+      *reinterpret_cast<float4*>(out + i) = o;
+    }
+    for (long long i = start + (nv << 2) + threadIdx.x; i < start + n; i += MU_THREADS) {
+      float lv = __ldg(lr + i / row_len);
+      if (use_log) lv = expf(lv);
+      out[i] = p[i] - g[i] * lv;
+    }
+  } else {
+    for (long long i = start + threadIdx.x; i < start + n; i += MU_THREADS) {
+      float lv = __ldg(lr + i / row_len);
+      if (use_log) lv = expf(lv);
+      out[i] = p[i] - g[i] * lv;
+    }
+  }
+}
+
+// Flat RAdam (radam.py:28-94).  Per-element group id selects (lr, weight_decay); the
+// rectification terms depend only on the step count and are computed on the host.
+//   g' = clamp(g * gscale, -clip, clip) ; m = b1 m + (1-b1) g' ; v = b2 v + (1-b2) g'^2
+//   p -= wd*lr*p ; p -= step_size * m / (sqrt(v) + eps)   [n_sma >= 5]   or   p -= step_size * m
+__global__ void __launch_bounds__(256)
+radam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             long long n, float gscale, float clip, float beta1, float beta2, float eps, float lr, float wd,
+             float step_size, int rectified, float clamp_lo, float clamp_hi, int do_clamp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gg = g[i] * gscale;
+  if (clip > 0.f) gg = fminf(fmaxf(gg, -clip), clip);
+  const float mm = beta1 * m[i] + (1.f - beta1) * gg;
+  const float vv = beta2 * v[i] + (1.f - beta2) * gg * gg;
+  m[i] = mm;
+  v[i] = vv;
+  float pp = p[i];
+  if (wd != 0.f) pp += -wd * lr * pp;
+  if (rectified)
+    pp += -step_size * mm / (sqrtf(vv) + eps);
+  else
+    pp += -step_size * mm;
+  if (do_clamp) pp = fminf(fmaxf(pp, clamp_lo), clamp_hi);
+  p[i] = pp;
+}
+
+}  // namespace eosvos
+
+using namespace eosvos;
+
+extern "C" int eosvos_meta_update_chunk_elems(void) { return MU_CHUNK; }
+
+extern "C" int eosvos_meta_update(const long long* table_dev, const int* chunks_dev, int num_chunks, int use_log,
+                                  eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (num_chunks == 0) return 0;
+  EOSVOS_REQUIRE(table_dev && chunks_dev && num_chunks > 0, "meta_update: null table");
+  meta_update_kernel<<<num_chunks, MU_THREADS, 0, stream>>>(table_dev, chunks_dev, use_log);
+  return check_launch("meta_update_kernel");
+}
+
+extern "C" int eosvos_radam_step(float* p, const float* g, float* m, float* v, long long n, float gscale, float clip,
+                                 float beta1, float beta2, float eps, float lr, float wd, float step_size,
+                                 int rectified, float clamp_lo, float clamp_hi, int do_clamp,
+                                 eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (n == 0) return 0;
+  EOSVOS_REQUIRE(p && g && m && v, "radam_step: null pointer");
+  radam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, g, m, v, n, gscale, clip, beta1, beta2, eps, lr, wd,
+                                                               step_size, rectified, clamp_lo, clamp_hi, do_clamp);
+  return check_launch("radam_kernel");
+}

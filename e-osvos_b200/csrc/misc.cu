@@ -1,0 +1,449 @@
+// Small HBM-bound helpers around the tensor-core kernels: layout/precision conversion, the
+// GeneralizedRCNNTransform (normalise + bilinear resize + pad), stem im2col, max-pool, FPN
+// sub-sampling, ReLU backward and bias gradients.  All NHWC, 128-bit accesses where shapes allow.
+//   transform : tv transform.py:119-160, 25-84, 237-255 as invoked from src/networks/mask_rcnn.py:716
+//   max-pool  : torchvision ResNet stem (3x3 / s2 / p1) and FPN LastLevelMaxPool (1x1 / s2)
+#include "common.h"
+#include "../../include/eosvos_b200.h"
+#include <cuda_bf16.h>
+
+namespace eosvos {
+
+__device__ __forceinline__ void ld8f(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void st8f(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic 4-D strided gather with conversion: dst[i0][i1][i2][i3] (given dst strides) = src[...]
+// ---------------------------------------------------------------------------------------------
+struct Permute4 {
+  long long dims[4];
+  long long sstride[4];
+  long long dstride[4];
+};
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) permute_cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Permute4 pm,
+                                                          long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long i3 = i % pm.dims[3];
+  i /= pm.dims[3];
+  const long long i2 = i % pm.dims[2];
+  i /= pm.dims[2];
+  const long long i1 = i % pm.dims[1];
+  const long long i0 = i / pm.dims[1];
+  const float v = (float)src[i0 * pm.sstride[0] + i1 * pm.sstride[1] + i2 * pm.sstride[2] + i3 * pm.sstride[3]];
+  dst[i0 * pm.dstride[0] + i1 * pm.dstride[1] + i2 * pm.dstride[2] + i3 * pm.dstride[3]] = (TD)v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// transform: NCHW fp32 image in [0,1] -> normalised, bilinearly resized (align_corners=False,
+// scale = in/out), zero-padded NHWC bf16 with Cs stored channels (3 used).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transform_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int h, int w, int oh, int ow,
+                 int Hp, int Wp, int Cs, float m0, float m1, float m2, float is0, float is1, float is2) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * Hp * Wp;
+  if (idx >= total) return;
+  const int x = (int)(idx % Wp);
+  const int y = (int)((idx / Wp) % Hp);
+  const int b = (int)(idx / ((long long)Wp * Hp));
+  float v[3] = {0.f, 0.f, 0.f};
+  if (y < oh && x < ow) {
+    const float sh = (float)h / (float)oh, sw = (float)w / (float)ow;
+    float sy = sh * ((float)y + 0.5f) - 0.5f;
+    float sx = sw * ((float)x + 0.5f) - 0.5f;
+    if (sy < 0.f) sy = 0.f;
+    if (sx < 0.f) sx = 0.f;
+    int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = fminf(fmaxf(sy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(sx - (float)x0, 0.f), 1.f);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float mean[3] = {m0, m1, m2}, istd[3] = {is0, is1, is2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* pl = img + ((size_t)b * 3 + c) * h * w;
+      const float v00 = (pl[(size_t)y0 * w + x0] - mean[c]) * istd[c], v01 = (pl[(size_t)y0 * w + x1] - mean[c]) * istd[c];
+      const float v10 = (pl[(size_t)y1 * w + x0] - mean[c]) * istd[c], v11 = (pl[(size_t)y1 * w + x1] - mean[c]) * istd[c];
+      v[c] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+    }
+  }
+  __nv_bfloat16* o = out + (size_t)idx * Cs;
+  for (int c = 0; c < Cs; ++c) o[c] = __float2bfloat16(c < 3 ? v[c] : 0.f);
+}
+
+// nearest resize of id masks (legacy 'nearest': src = floor(dst * in/out)), fp32 -> uint8, padded
+__global__ void __launch_bounds__(256)
+mask_resize_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int G, int h, int w, int oh, int ow) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)G * oh * ow) return;
+  const int x = (int)(idx % ow);
+  const int y = (int)((idx / ow) % oh);
+  const int g = (int)(idx / ((long long)ow * oh));
+  const float sh = (float)h / (float)oh, sw = (float)w / (float)ow;
+  const int sy = min((int)floorf((float)y * sh), h - 1), sx = min((int)floorf((float)x * sw), w - 1);
+  dst[idx] = src[((size_t)g * h + sy) * w + sx];
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem im2col: x [N,H,W,Cs] bf16 (3 used) -> col [N*Ho*Wo][Kp] bf16, k = (kh*KW + kw)*3 + c
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col_stem_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W, int Cs,
+                   int Ho, int Wo, int KH, int KW, int stride, int pad, int Kp) {
+  const int kv = Kp >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * Ho * Wo * kv;
+  if (idx >= total) return;
+  const int k8 = (int)(idx % kv);
+  long long row = idx / kv;
+  const int wo = (int)(row % Wo);
+  const int ho = (int)((row / Wo) % Ho);
+  const int n = (int)(row / ((long long)Wo * Ho));
+  __align__(16) __nv_bfloat16 vals[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = k8 * 8 + j;
+    __nv_bfloat16 v = __float2bfloat16(0.f);
+    if (k < KH * KW * 3) {
+      const int c = k % 3;
+      const int t = k / 3;
+      const int kw = t % KW, kh = t / KW;
+      const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((size_t)n * H + hi) * W + wi) * Cs + c];
+    }
+    vals[j] = v;
+  }
+  *reinterpret_cast<uint4*>(col + (size_t)row * Kp + (size_t)k8 * 8) = *reinterpret_cast<const uint4*>(vals);
+}
+
+// ---------------------------------------------------------------------------------------------
+// max-pool k x k / stride s / pad p, NHWC bf16.  Backward re-derives the arg-max (first maximum
+// in window scan order, as ATen) so no index tensor is stored.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, int C,
+                   int Ho, int Wo, int ksz, int stride, int pad) {
+  const int cv = C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * Ho * Wo * cv) return;
+  const int c8 = (int)(idx % cv);
+  long long t = idx / cv;
+  const int wo = (int)(t % Wo);
+  const int ho = (int)((t / Wo) % Ho);
+  const int n = (int)(t / ((long long)Wo * Ho));
+  float m[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = -3.0e38f;
+  for (int kh = 0; kh < ksz; ++kh) {
+    const int hi = ho * stride - pad + kh;
+    if (hi < 0 || hi >= H) continue;
+    for (int kw = 0; kw < ksz; ++kw) {
+      const int wi = wo * stride - pad + kw;
+      if (wi < 0 || wi >= W) continue;
+      float f[8];
+      ld8f(x + (((size_t)n * H + hi) * W + wi) * C + (size_t)c8 * 8, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+    }
+  }
+  st8f(y + (size_t)idx * 8, m);
+}
+
+// dx[hi,wi] = sum over windows containing (hi,wi) whose first arg-max is (hi,wi) of dy[window]
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                   const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C,
+                   int Ho, int Wo, int ksz, int stride, int pad) {
+  const int cv = C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * H * W * cv) return;
+  const int c8 = (int)(idx % cv);
+  long long t = idx / cv;
+  const int wi = (int)(t % W);
+  const int hi = (int)((t / W) % H);
+  const int n = (int)(t / ((long long)W * H));
+  float xv[8], acc[8];
+  ld8f(x + (size_t)idx * 8, xv);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  // windows (ho, wo) with ho*stride - pad <= hi < ho*stride - pad + ksz
+  const int ho_lo = max(0, (hi + pad - ksz + stride) / stride), ho_hi = min(Ho - 1, (hi + pad) / stride);
+  const int wo_lo = max(0, (wi + pad - ksz + stride) / stride), wo_hi = min(Wo - 1, (wi + pad) / stride);
+  for (int ho = ho_lo; ho <= ho_hi; ++ho)
+    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+      float yv[8], dv[8];
+      const size_t o = (((size_t)n * Ho + ho) * Wo + wo) * C + (size_t)c8 * 8;
+      ld8f(y + o, yv);
+      ld8f(dy + o, dv);
+      // is (hi,wi) the FIRST position in this window holding the max?
+      bool first[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) first[k] = (xv[k] == yv[k]);
+      for (int kh = 0; kh < ksz; ++kh) {
+        const int h2 = ho * stride - pad + kh;
+        if (h2 < 0 || h2 >= H) continue;
+        for (int kw = 0; kw < ksz; ++kw) {
+          const int w2 = wo * stride - pad + kw;
+          if (w2 < 0 || w2 >= W) continue;
+          if (h2 > hi || (h2 == hi && w2 >= wi)) continue;  // only earlier positions
+          float f[8];
+          ld8f(x + (((size_t)n * H + h2) * W + w2) * C + (size_t)c8 * 8, f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) first[k] = first[k] && !(f[k] == yv[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += first[k] ? dv[k] : 0.f;
+    }
+  st8f(dx + (size_t)idx * 8, acc);
+}
+
+// FPN LastLevelMaxPool (kernel 1, stride 2) forward and backward
+__global__ void __launch_bounds__(256)
+subsample2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, int Ho,
+                  int Wo, int backward) {
+  const int cv = C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (backward) {  // x = dy [N,Ho,Wo,C] -> y = dx [N,H,W,C]
+    if (idx >= (long long)N * H * W * cv) return;
+    const int c8 = (int)(idx % cv);
+    long long t = idx / cv;
+    const int wi = (int)(t % W), hi = (int)((t / W) % H), n = (int)(t / ((long long)W * H));
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(hi & 1) && !(wi & 1) && (hi >> 1) < Ho && (wi >> 1) < Wo)
+      v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * Ho + (hi >> 1)) * Wo + (wi >> 1)) * C + (size_t)c8 * 8));
+    *reinterpret_cast<uint4*>(y + (size_t)idx * 8) = v;
+  } else {
+    if (idx >= (long long)N * Ho * Wo * cv) return;
+    const int c8 = (int)(idx % cv);
+    long long t = idx / cv;
+    const int wo = (int)(t % Wo), ho = (int)((t / Wo) % Ho), n = (int)(t / ((long long)Wo * Ho));
+    *reinterpret_cast<uint4*>(y + (size_t)idx * 8) =
+        __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + (size_t)c8 * 8));
+  }
+}
+
+// backward of nearest 2x upsampling: dcoarse[h,w] = sum of the 2x2 fine gradients
+__global__ void __launch_bounds__(256)
+sum2x2_kernel(const __nv_bfloat16* __restrict__ dfine, __nv_bfloat16* __restrict__ dcoarse, int N, int Hc, int Wc, int C) {
+  const int cv = C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * Hc * Wc * cv) return;
+  const int c8 = (int)(idx % cv);
+  long long t = idx / cv;
+  const int w = (int)(t % Wc), h = (int)((t / Wc) % Hc), n = (int)(t / ((long long)Wc * Hc));
+  const int Hf = 2 * Hc, Wf = 2 * Wc;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float f[8];
+      ld8f(dfine + (((size_t)n * Hf + 2 * h + dy) * Wf + 2 * w + dx) * C + (size_t)c8 * 8, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += f[k];
+    }
+  st8f(dcoarse + (size_t)idx * 8, acc);
+}
+
+// dy_eff = dy * (y > 0)   (fused conv+bias+ReLU backward entry)
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out,
+                long long nvec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  float d[8], yy[8];
+  ld8f(dy + i * 8, d);
+  ld8f(y + i * 8, yy);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) d[k] = yy[k] > 0.f ? d[k] : 0.f;
+  st8f(out + i * 8, d);
+}
+
+// bias gradient: out[c] += sum_rows dy[row][c]; dy bf16 [M][C]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ out, long long M, int C, int rows_per_block) {
+  extern __shared__ float sm[];  // [C]
+  const int cv = C >> 3;
+  const int my_cv = threadIdx.x % cv;
+  const int rpp = 256 / cv;
+  for (int i = threadIdx.x; i < C; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (long long r = r0 + threadIdx.x / cv; r < r1; r += rpp) {
+    float f[8];
+    ld8f(dy + r * C + (size_t)my_cv * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += f[k];
+  }
+  if (threadIdx.x / cv < rpp) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&sm[my_cv * 8 + k], acc[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(&out[i], sm[i]);
+}
+
+static inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
+
+}  // namespace eosvos
+
+using namespace eosvos;
+
+// dtype codes: 0 = fp32, 1 = bf16
+extern "C" int eosvos_permute_cast(const void* src, void* dst, const long long* dims, const long long* sstride,
+                                   const long long* dstride, int src_dtype, int dst_dtype, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(src && dst && dims && sstride && dstride, "permute_cast: null pointer");
+  Permute4 pm;
+  long long total = 1;
+  for (int i = 0; i < 4; ++i) {
+    pm.dims[i] = dims[i];
+    pm.sstride[i] = sstride[i];
+    pm.dstride[i] = dstride[i];
+    total *= dims[i];
+  }
+  if (total == 0) return 0;
+  const unsigned nb = blocks_for(total);
+  if (src_dtype == 0 && dst_dtype == 1)
+    permute_cast_kernel<float, __nv_bfloat16><<<nb, 256, 0, stream>>>(reinterpret_cast<const float*>(src),
+                                                                     reinterpret_cast<__nv_bfloat16*>(dst), pm, total);
+  else if (src_dtype == 1 && dst_dtype == 0)
+    permute_cast_kernel<__nv_bfloat16, float><<<nb, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src),
+                                                                     reinterpret_cast<float*>(dst), pm, total);
+  else if (src_dtype == 0 && dst_dtype == 0)
+    permute_cast_kernel<float, float><<<nb, 256, 0, stream>>>(reinterpret_cast<const float*>(src),
+                                                             reinterpret_cast<float*>(dst), pm, total);
+  else if (src_dtype == 1 && dst_dtype == 1)
+    permute_cast_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), pm, total);
+  else
+    return set_error(EOSVOS_ERR_ARG, "permute_cast: unknown dtype code");
+  return check_launch("permute_cast_kernel");
+}
+
+extern "C" int eosvos_transform(const float* img, void* out, int B, int h, int w, int oh, int ow, int Hp, int Wp, int Cs,
+                                const float* mean3, const float* std3, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(img && out && mean3 && std3, "transform: null pointer");
+  EOSVOS_REQUIRE(Cs >= 3 && oh <= Hp && ow <= Wp, "transform: bad geometry");
+  const long long total = (long long)B * Hp * Wp;
+  transform_kernel<<<blocks_for(total), 256, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, h, w, oh, ow, Hp,
+                                                        Wp, Cs, mean3[0], mean3[1], mean3[2], 1.f / std3[0],
+                                                        1.f / std3[1], 1.f / std3[2]);
+  return check_launch("transform_kernel");
+}
+
+extern "C" int eosvos_mask_resize_nearest(const uint8_t* src, uint8_t* dst, int G, int h, int w, int oh, int ow,
+                                          eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (G == 0) return 0;
+  EOSVOS_REQUIRE(src && dst, "mask_resize_nearest: null pointer");
+  mask_resize_kernel<<<blocks_for((long long)G * oh * ow), 256, 0, stream>>>(src, dst, G, h, w, oh, ow);
+  return check_launch("mask_resize_kernel");
+}
+
+extern "C" int eosvos_im2col_stem(const void* x, void* col, int N, int H, int W, int Cs, int KH, int KW, int stride,
+                                  int pad, int Kp, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(x && col, "im2col_stem: null pointer");
+  EOSVOS_REQUIRE(Kp % 64 == 0 && Kp >= KH * KW * 3, "im2col_stem: Kp must be a multiple of 64 covering KH*KW*3");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * (Kp >> 3);
+  im2col_stem_kernel<<<blocks_for(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                          reinterpret_cast<__nv_bfloat16*>(col), N, H, W, Cs, Ho, Wo, KH,
+                                                          KW, stride, pad, Kp);
+  return check_launch("im2col_stem_kernel");
+}
+
+extern "C" int eosvos_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int ksz, int stride, int pad,
+                                  eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(x && y && C % 8 == 0, "maxpool_fwd: bad arguments");
+  const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
+  maxpool_fwd_kernel<<<blocks_for((long long)N * Ho * Wo * (C >> 3)), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), N, H, W, C, Ho, Wo, ksz, stride,
+      pad);
+  return check_launch("maxpool_fwd_kernel");
+}
+
+extern "C" int eosvos_maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, int N, int H, int W, int C,
+                                  int ksz, int stride, int pad, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(x && y && dy && dx && C % 8 == 0, "maxpool_bwd: bad arguments");
+  const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
+  maxpool_bwd_kernel<<<blocks_for((long long)N * H * W * (C >> 3)), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(y),
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<__nv_bfloat16*>(dx), N, H, W, C, Ho, Wo, ksz, stride,
+      pad);
+  return check_launch("maxpool_bwd_kernel");
+}
+
+extern "C" int eosvos_subsample2(const void* x, void* y, int N, int H, int W, int C, int backward,
+                                 eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(x && y && C % 8 == 0, "subsample2: bad arguments");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = backward ? (long long)N * H * W * (C >> 3) : (long long)N * Ho * Wo * (C >> 3);
+  subsample2_kernel<<<blocks_for(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                         reinterpret_cast<__nv_bfloat16*>(y), N, H, W, C, Ho, Wo,
+                                                         backward);
+  return check_launch("subsample2_kernel");
+}
+
+extern "C" int eosvos_sum2x2(const void* dfine, void* dcoarse, int N, int Hc, int Wc, int C, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(dfine && dcoarse && C % 8 == 0, "sum2x2: bad arguments");
+  sum2x2_kernel<<<blocks_for((long long)N * Hc * Wc * (C >> 3)), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dfine), reinterpret_cast<__nv_bfloat16*>(dcoarse), N, Hc, Wc, C);
+  return check_launch("sum2x2_kernel");
+}
+
+extern "C" int eosvos_relu_bwd(const void* dy, const void* y, void* out, long long numel, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (numel == 0) return 0;
+  EOSVOS_REQUIRE(dy && y && out && numel % 8 == 0, "relu_bwd: numel must be a multiple of 8");
+  relu_bwd_kernel<<<blocks_for(numel / 8), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                           reinterpret_cast<const __nv_bfloat16*>(y),
+                                                           reinterpret_cast<__nv_bfloat16*>(out), numel / 8);
+  return check_launch("relu_bwd_kernel");
+}
+
+// out[c] (fp32, ACCUMULATED: caller zeroes) += column sums of dy [M][C] bf16
+extern "C" int eosvos_colsum(const void* dy, float* out, long long M, int C, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (M == 0) return 0;
+  EOSVOS_REQUIRE(dy && out, "colsum: null pointer");
+  EOSVOS_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C >> 3) == 0, "colsum: C/8 must divide 256");
+  const int rpp = 256 / (C >> 3);
+  long long want_blocks = 4LL * num_sms();
+  long long rows_per_block = (M + want_blocks - 1) / want_blocks;
+  rows_per_block = ((rows_per_block + rpp - 1) / rpp) * rpp;
+  const unsigned nb = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+  colsum_kernel<<<nb, 256, C * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), out, M, C,
+                                                        (int)rows_per_block);
+  return check_launch("colsum_kernel");
+}

@@ -1,0 +1,426 @@
+"""Tensor-level wrappers over the C ABI (no autograd here; see ops.py).
+
+PyTorch supplies device memory and streams only.  Activations are [N, H, W, C] bf16 contiguous,
+parameters fp32 in the reference's (torch) layouts.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import FLAG_OUT_FP32, FLAG_RELU, FLAG_RES_HALF, call
+
+GN_EPS = 1e-5
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.EosvosError(f"{name} must live on a CUDA device (no CPU path exists)")
+    if not t.is_contiguous():
+        raise _lib.EosvosError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.EosvosError(f"{name} must be {dtype}, got {t.dtype}")
+    _lib.require_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    return t
+
+
+# ------------------------------------------------------------------------------------------- K1
+def conv2d_fprop(x, w, bias=None, res=None, *, stride=1, pad=0, relu=False, out_fp32=False, res_half=False,
+                 gn_sum=None, bn_hint=0, out=None):
+    """x [N,H,W,Cin] bf16, w [Cout,KH,KW,Cin] bf16 -> y [N,Ho,Wo,Cout]."""
+    _chk(x, torch.bfloat16, "x")
+    _chk(w, torch.bfloat16, "w")
+    N, H, W, Cin = x.shape
+    Cout, KH, KW, Cin2 = w.shape
+    assert Cin == Cin2, (x.shape, w.shape)
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    flags = (FLAG_RELU if relu else 0) | (FLAG_OUT_FP32 if out_fp32 else 0) | (FLAG_RES_HALF if res_half else 0)
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    if res is not None:
+        _chk(res, torch.bfloat16, "res")
+    if gn_sum is not None:
+        _chk(gn_sum, torch.float32, "gn_sum")
+    call("eosvos_conv2d_fprop", _ptr(x), _ptr(w), _ptr(bias), _ptr(res), _ptr(out), _ptr(gn_sum), N, H, W, Cin, Cout,
+         KH, KW, stride, pad, flags, bn_hint, _stream())
+    return out
+
+
+def conv2d_dgrad(dy, wt, in_hw, *, stride=1, pad=0, out_fp32=False, bn_hint=0):
+    """dy [N,Ho,Wo,Cout] bf16, wt [Cin,KH,KW,Cout] bf16 -> dx [N,H,W,Cin]."""
+    _chk(dy, torch.bfloat16, "dy")
+    _chk(wt, torch.bfloat16, "wt")
+    N, Ho, Wo, Cout = dy.shape
+    Cin, KH, KW, Cout2 = wt.shape
+    assert Cout == Cout2
+    H, W = in_hw
+    assert (H + 2 * pad - KH) // stride + 1 == Ho and (W + 2 * pad - KW) // stride + 1 == Wo
+    dx = torch.empty((N, H, W, Cin), device=dy.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    call("eosvos_conv2d_dgrad", _ptr(dy), _ptr(wt), _ptr(dx), N, H, W, Cin, Cout, KH, KW, stride, pad,
+         FLAG_OUT_FP32 if out_fp32 else 0, bn_hint, _stream())
+    return dx
+
+
+def conv2d_wgrad(x, dy, ksize, *, stride=1, pad=0, bn_hint=0, split_hint=0, out=None):
+    """x [N,H,W,Cin], dy [N,Ho,Wo,Cout] bf16 -> dw fp32 [Cout,Cin,KH,KW] (torch layout)."""
+    _chk(x, torch.bfloat16, "x")
+    _chk(dy, torch.bfloat16, "dy")
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    KH, KW = ksize
+    if out is None:
+        out = torch.zeros((Cout, Cin, KH, KW), device=x.device, dtype=torch.float32)
+    call("eosvos_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(out), N, H, W, Cin, Cout, KH, KW, stride, pad, bn_hint,
+         split_hint, _stream())
+    return out
+
+
+def gemm_wgrad(x, dy, out, *, s_m, n_inner=0, s_n_inner=1, s_n_outer=0, bn_hint=0, split_hint=0):
+    """out[m*s_m + (n//n_inner)*s_n_outer + (n%n_inner)*s_n_inner] += sum_r dy[r,m] * x[r,n]."""
+    _chk(x, torch.bfloat16, "x")
+    _chk(dy, torch.bfloat16, "dy")
+    _chk(out, torch.float32, "out")
+    rows, n_cols = x.shape
+    rows2, m_cols = dy.shape
+    assert rows == rows2
+    call("eosvos_gemm_wgrad", _ptr(x), _ptr(dy), _ptr(out), rows, n_cols, m_cols, s_m, n_inner, s_n_inner, s_n_outer,
+         bn_hint, split_hint, _stream())
+    return out
+
+
+def deconv2x2_fprop(x, wd, bias4=None, *, relu=False, bn_hint=0):
+    """x [N,h,w,Cin] bf16, wd [4*Cout, Cin] bf16 ((dy,dx,co) rows) -> y [N,2h,2w,Cout] bf16."""
+    _chk(x, torch.bfloat16, "x")
+    _chk(wd, torch.bfloat16, "wd")
+    N, h, w, Cin = x.shape
+    Cout = wd.shape[0] // 4
+    y = torch.empty((N, 2 * h, 2 * w, Cout), device=x.device, dtype=torch.bfloat16)
+    call("eosvos_deconv2x2_fprop", _ptr(x), _ptr(wd), _ptr(bias4), _ptr(y), N, h, w, Cin, Cout,
+         FLAG_RELU if relu else 0, bn_hint, _stream())
+    return y
+
+
+def deconv2x2_dgrad(dy, wdt, *, bn_hint=0):
+    """dy [N,2h,2w,Cout] bf16, wdt [Cin, 4*Cout] bf16 -> dx [N,h,w,Cin] bf16."""
+    _chk(dy, torch.bfloat16, "dy")
+    _chk(wdt, torch.bfloat16, "wdt")
+    N, H2, W2, Cout = dy.shape
+    Cin = wdt.shape[0]
+    dx = torch.empty((N, H2 // 2, W2 // 2, Cin), device=dy.device, dtype=torch.bfloat16)
+    call("eosvos_deconv2x2_dgrad", _ptr(dy), _ptr(wdt), _ptr(dx), N, H2 // 2, W2 // 2, Cin, Cout, 0, bn_hint,
+         _stream())
+    return dx
+
+
+def deconv2x2_wgrad(x, dy, *, bn_hint=0, split_hint=0):
+    """-> dw fp32 [Cin, Cout, 2, 2] (torch ConvTranspose2d layout)."""
+    _chk(x, torch.bfloat16, "x")
+    _chk(dy, torch.bfloat16, "dy")
+    N, h, w, Cin = x.shape
+    Cout = dy.shape[-1]
+    dw = torch.zeros((Cin, Cout, 2, 2), device=x.device, dtype=torch.float32)
+    call("eosvos_deconv2x2_wgrad", _ptr(x), _ptr(dy), _ptr(dw), N, h, w, Cin, Cout, bn_hint, split_hint, _stream())
+    return dw
+
+
+# ------------------------------------------------------------------------------------------- K2
+def gn_stats(x):
+    _chk(x, torch.bfloat16, "x")
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    sums = torch.empty((N, 32, 2), device=x.device, dtype=torch.float32)
+    call("eosvos_gn_stats", _ptr(x), _ptr(sums), N, HW, C, _stream())
+    return sums
+
+
+def gn_apply(x, sums, gamma, beta, res=None, relu=False, eps=GN_EPS):
+    _chk(x, torch.bfloat16, "x")
+    _chk(sums, torch.float32, "sums")
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    y = torch.empty_like(x)
+    call("eosvos_gn_apply", _ptr(x), _ptr(sums), _ptr(_chk(gamma, torch.float32)), _ptr(_chk(beta, torch.float32)),
+         _ptr(res), _ptr(y), N, HW, C, eps, 1 if relu else 0, _stream())
+    return y
+
+
+def gn_backward(x, sums, gamma, beta, dy, yout=None, mask_mode=0, want_dres=False, eps=GN_EPS):
+    _chk(x, torch.bfloat16, "x")
+    _chk(dy, torch.bfloat16, "dy")
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    part = torch.empty((N, C, 2), device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    dgamma = torch.empty((C,), device=x.device, dtype=torch.float32)
+    dbeta = torch.empty((C,), device=x.device, dtype=torch.float32)
+    call("eosvos_gn_backward", _ptr(x), _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(yout), _ptr(part),
+         _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), N, HW, C, eps, mask_mode, _stream())
+    return dx, dres, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------- K4
+def _level_args(feats_or_shapes):
+    ptrs = (ctypes.c_void_p * 4)()
+    Hs = (ctypes.c_int * 4)()
+    Ws = (ctypes.c_int * 4)()
+    return ptrs, Hs, Ws
+
+
+def roi_align_fwd(feats, scales, rois, P, sampling=2):
+    """feats: 4 NHWC bf16 levels; rois [R,5] fp32 (batch, x1, y1, x2, y2) -> [R,P,P,C] bf16."""
+    ptrs, Hs, Ws = _level_args(feats)
+    sc = (ctypes.c_float * 4)(*[float(s) for s in scales])
+    for i, f in enumerate(feats):
+        _chk(f, torch.bfloat16, "feature level")
+        ptrs[i] = f.data_ptr()
+        Hs[i], Ws[i] = f.shape[1], f.shape[2]
+    C = feats[0].shape[-1]
+    _chk(rois, torch.float32, "rois")
+    R = rois.shape[0]
+    out = torch.empty((R, P, P, C), device=rois.device, dtype=torch.bfloat16)
+    call("eosvos_roi_align_fwd", ptrs, Hs, Ws, sc, _ptr(rois), _ptr(out), R, P, C, sampling, _stream())
+    return out
+
+
+def roi_align_bwd(dout, level_shapes, scales, rois, P, sampling=2):
+    """-> list of 4 fp32 NHWC gradient maps (zero-initialised here, atomically accumulated)."""
+    _chk(dout, torch.bfloat16, "dout")
+    _chk(rois, torch.float32, "rois")
+    ptrs, Hs, Ws = _level_args(level_shapes)
+    sc = (ctypes.c_float * 4)(*[float(s) for s in scales])
+    outs = []
+    for i, shp in enumerate(level_shapes):
+        g = torch.zeros(shp, device=dout.device, dtype=torch.float32)
+        outs.append(g)
+        ptrs[i] = g.data_ptr()
+        Hs[i], Ws[i] = shp[1], shp[2]
+    R, C = rois.shape[0], dout.shape[-1]
+    call("eosvos_roi_align_bwd", ptrs, Hs, Ws, sc, _ptr(rois), _ptr(dout), R, P, C, sampling, _stream())
+    return outs
+
+
+def mask_targets(masks_u8, rois, M):
+    """masks uint8 [G,H,W]; rois [R,5] (mask idx, box) -> fp32 [R,M,M]."""
+    _chk(masks_u8, torch.uint8, "masks")
+    _chk(rois, torch.float32, "rois")
+    G, H, W = masks_u8.shape
+    R = rois.shape[0]
+    out = torch.empty((R, M, M), device=rois.device, dtype=torch.float32)
+    call("eosvos_mask_targets", _ptr(masks_u8), _ptr(rois), _ptr(out), R, M, H, W, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------- K7
+def mask_loss(logits, labels, targets, kind="LOVASZ"):
+    """logits [R,Cc,M,M] fp32, labels [R] int64, targets [R,M,M] fp32 -> (loss scalar, dlogits)."""
+    _chk(logits, torch.float32, "logits")
+    _chk(labels, torch.int64, "labels")
+    _chk(targets, torch.float32, "targets")
+    R, Cc = logits.shape[0], logits.shape[1]
+    P = logits.shape[2] * logits.shape[3]
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    dlogits = torch.empty_like(logits)
+    if kind == "LOVASZ":
+        call("eosvos_mask_loss_lovasz", _ptr(logits), _ptr(labels), _ptr(targets), _ptr(loss), None, _ptr(dlogits), R,
+             Cc, P, _stream())
+    elif kind == "BCE":
+        call("eosvos_mask_loss_bce", _ptr(logits), _ptr(labels), _ptr(targets), _ptr(loss), _ptr(dlogits), R, Cc, P,
+             _stream())
+    else:
+        raise NotImplementedError(kind)
+    return loss, dlogits
+
+
+# ------------------------------------------------------------------------------------------- K8
+def mask_paste_threshold(logits, det_of_chan, det_label, det_box, B, K, H, W, thresh=0.5, want_target=True):
+    """-> probs [B,K,H,W] fp32, target [B,1,H,W] fp32 ids, stats [B,K,5] int32 (xmin,ymin,xmax,ymax,count)."""
+    dev = det_of_chan.device
+    _chk(det_of_chan, torch.int32, "det_of_chan")
+    D = logits.shape[0]
+    if D > 0:
+        _chk(logits, torch.float32, "logits")
+        _chk(det_label, torch.int64, "det_label")
+        _chk(det_box, torch.float32, "det_box")
+    M = logits.shape[-1]
+    Cc = logits.shape[1]
+    probs = torch.empty((B, K, H, W), device=dev, dtype=torch.float32)
+    target = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32) if want_target else None
+    stats = torch.empty((B, K, 5), device=dev, dtype=torch.int32) if want_target else None
+    call("eosvos_mask_paste_threshold", _ptr(logits) if D else None, _ptr(det_of_chan), _ptr(det_label) if D else None,
+         _ptr(det_box) if D else None, _ptr(probs), _ptr(target), _ptr(stats), B, K, H, W, M, Cc, thresh, _stream())
+    return probs, target, stats
+
+
+def mask_to_bbox(target, K):
+    """target [B,1,H,W] (or [B,H,W]) fp32 ids -> stats [B,K,5] int32."""
+    _chk(target, torch.float32, "target")
+    B = target.shape[0]
+    H, W = target.shape[-2:]
+    stats = torch.empty((B, K, 5), device=target.device, dtype=torch.int32)
+    call("eosvos_mask_to_bbox", _ptr(target), _ptr(stats), B, K, H, W, _stream())
+    return stats
+
+
+# ------------------------------------------------------------------------------------------- K9
+class MetaUpdatePlan:
+    """Pointer/chunk tables of one (params, grads, lrs, outs) binding, cached on the device."""
+
+    def __init__(self, params, grads, lrs, outs):
+        chunk = _lib.load().eosvos_meta_update_chunk_elems()
+        rows, chunks = [], []
+        for t, (p, g, lr, o) in enumerate(zip(params, grads, lrs, outs)):
+            n = p.numel()
+            assert g.numel() == n and o.numel() == n, "meta_update: size mismatch"
+            assert n % lr.numel() == 0, "meta_update: learning-rate shape must divide the parameter"
+            for tt in (p, g, lr, o):
+                _chk(tt, torch.float32, "meta_update operand")
+            rows.append([p.data_ptr(), g.data_ptr(), lr.data_ptr(), o.data_ptr(), n, n // lr.numel()])
+            for c in range((n + chunk - 1) // chunk):
+                chunks.append([t, c])
+        dev = params[0].device
+        self.table = torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
+        self.chunks = torch.tensor(chunks, dtype=torch.int32).to(dev, non_blocking=True)
+        self.num_chunks = len(chunks)
+        self.key = tuple(r[0] for r in rows) + tuple(r[1] for r in rows) + tuple(r[3] for r in rows)
+
+
+def meta_update(plan, use_log=False):
+    call("eosvos_meta_update", _ptr(plan.table), _ptr(plan.chunks), plan.num_chunks, 1 if use_log else 0, _stream())
+
+
+def radam_step(p, g, m, v, *, gscale, clip, beta1, beta2, eps, lr, wd, step_size, rectified, clamp=None):
+    for t in (p, g, m, v):
+        _chk(t, torch.float32, "radam operand")
+    lo, hi, do = (clamp[0], clamp[1], 1) if clamp is not None else (0.0, 0.0, 0)
+    call("eosvos_radam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), gscale, clip if clip else 0.0, beta1,
+         beta2, eps, lr, wd, step_size, 1 if rectified else 0, lo, hi, do, _stream())
+
+
+# ------------------------------------------------------------------------------------------- misc
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def permute_cast(src, dst, dims, sstride, dstride):
+    """dst[i0,i1,i2,i3 . dstride] = src[i0,i1,i2,i3 . sstride] with dtype conversion (fp32/bf16)."""
+    d = (ctypes.c_longlong * 4)(*dims)
+    s = (ctypes.c_longlong * 4)(*sstride)
+    t = (ctypes.c_longlong * 4)(*dstride)
+    call("eosvos_permute_cast", _ptr(src), _ptr(dst), d, s, t, _DT[src.dtype], _DT[dst.dtype], _stream())
+    return dst
+
+
+def nchw_to_nhwc_bf16(x):
+    """fp32/bf16 [N,C,H,W] -> bf16 [N,H,W,C]."""
+    N, C, H, W = x.shape
+    x = x.contiguous()
+    out = torch.empty((N, H, W, C), device=x.device, dtype=torch.bfloat16)
+    return permute_cast(x, out, (N, H, W, C), (C * H * W, W, 1, H * W), (H * W * C, W * C, C, 1))
+
+
+def nhwc_to_nchw_fp32(x):
+    """bf16/fp32 [N,H,W,C] -> fp32 [N,C,H,W]."""
+    N, H, W, C = x.shape
+    x = x.contiguous()
+    out = torch.empty((N, C, H, W), device=x.device, dtype=torch.float32)
+    return permute_cast(x, out, (N, C, H, W), (H * W * C, 1, W * C, C), (C * H * W, H * W, W, 1))
+
+
+def transform(img, oh, ow, Hp, Wp, mean, std, Cs=8):
+    _chk(img, torch.float32, "image")
+    B, _, h, w = img.shape
+    out = torch.empty((B, Hp, Wp, Cs), device=img.device, dtype=torch.bfloat16)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    call("eosvos_transform", _ptr(img), _ptr(out), B, h, w, oh, ow, Hp, Wp, Cs, m, s, _stream())
+    return out
+
+
+def mask_resize_nearest(masks_u8, oh, ow):
+    _chk(masks_u8, torch.uint8, "masks")
+    G, h, w = masks_u8.shape
+    out = torch.empty((G, oh, ow), device=masks_u8.device, dtype=torch.uint8)
+    call("eosvos_mask_resize_nearest", _ptr(masks_u8), _ptr(out), G, h, w, oh, ow, _stream())
+    return out
+
+
+def im2col_stem(x, KH=7, KW=7, stride=2, pad=3, Kp=192):
+    _chk(x, torch.bfloat16, "x")
+    N, H, W, Cs = x.shape
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    col = torch.empty((N * Ho * Wo, Kp), device=x.device, dtype=torch.bfloat16)
+    call("eosvos_im2col_stem", _ptr(x), _ptr(col), N, H, W, Cs, KH, KW, stride, pad, Kp, _stream())
+    return col, Ho, Wo
+
+
+def maxpool_fwd(x, ksz=3, stride=2, pad=1):
+    _chk(x, torch.bfloat16, "x")
+    N, H, W, C = x.shape
+    Ho = (H + 2 * pad - ksz) // stride + 1
+    Wo = (W + 2 * pad - ksz) // stride + 1
+    y = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.bfloat16)
+    call("eosvos_maxpool_fwd", _ptr(x), _ptr(y), N, H, W, C, ksz, stride, pad, _stream())
+    return y
+
+
+def maxpool_bwd(x, y, dy, ksz=3, stride=2, pad=1):
+    N, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    call("eosvos_maxpool_bwd", _ptr(x), _ptr(y), _ptr(_chk(dy, torch.bfloat16)), _ptr(dx), N, H, W, C, ksz, stride,
+         pad, _stream())
+    return dx
+
+
+def subsample2(x):
+    _chk(x, torch.bfloat16, "x")
+    N, H, W, C = x.shape
+    y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), device=x.device, dtype=torch.bfloat16)
+    call("eosvos_subsample2", _ptr(x), _ptr(y), N, H, W, C, 0, _stream())
+    return y
+
+
+def subsample2_bwd(dy, in_shape):
+    _chk(dy, torch.bfloat16, "dy")
+    N, H, W, C = in_shape
+    dx = torch.empty(in_shape, device=dy.device, dtype=torch.bfloat16)
+    call("eosvos_subsample2", _ptr(dy), _ptr(dx), N, H, W, C, 1, _stream())
+    return dx
+
+
+def sum2x2(dfine):
+    _chk(dfine, torch.bfloat16, "dfine")
+    N, Hf, Wf, C = dfine.shape
+    out = torch.empty((N, Hf // 2, Wf // 2, C), device=dfine.device, dtype=torch.bfloat16)
+    call("eosvos_sum2x2", _ptr(dfine), _ptr(out), N, Hf // 2, Wf // 2, C, _stream())
+    return out
+
+
+def relu_bwd(dy, y):
+    _chk(dy, torch.bfloat16, "dy")
+    _chk(y, torch.bfloat16, "y")
+    out = torch.empty_like(dy)
+    call("eosvos_relu_bwd", _ptr(dy), _ptr(y), _ptr(out), dy.numel(), _stream())
+    return out
+
+
+def colsum(dy2d, out=None):
+    _chk(dy2d, torch.bfloat16, "dy")
+    M, C = dy2d.shape
+    if out is None:
+        out = torch.zeros((C,), device=dy2d.device, dtype=torch.float32)
+    call("eosvos_colsum", _ptr(dy2d), _ptr(out), M, C, _stream())
+    return out

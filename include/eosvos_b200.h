@@ -1,0 +1,123 @@
+/* libeosvos_b200.so -- C ABI of the B200-native e-OSVOS hot path.
+ *
+ * The reference (dvl-tum/e-osvos) has no FFI/plugin layer of its own: its arithmetic lives in
+ * PyTorch 1.2 / torchvision 0.4 / cuDNN.  Each entry point below
+ * therefore cites the reference *call site* whose library call it replaces.  Conventions:
+ *   - the caller owns every buffer; pointers are device pointers unless stated otherwise;
+ *   - the CUDA stream is passed explicitly (eosvos_stream_t == cudaStream_t);
+ *   - return 0 on success, a negative code on failure; eosvos_last_error() gives the message;
+ *   - no hidden allocation, no hidden synchronisation, nothing throws across the boundary;
+ *   - sm_100a only: there is no CPU or other-architecture fallback.
+ * Activations are NHWC bf16 ("bf16*" below means __nv_bfloat16), parameters and losses fp32.
+ */
+#ifndef EOSVOS_B200_H
+#define EOSVOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EOSVOS_B200_VERSION 100
+
+typedef void* eosvos_stream_t;
+
+/* epilogue flags for the contraction entry points */
+#define EOSVOS_FLAG_RELU 1      /* y = max(y, 0)                                             */
+#define EOSVOS_FLAG_OUT_FP32 2  /* write fp32 instead of bf16                                */
+#define EOSVOS_FLAG_RES_HALF 4  /* residual operand lives on the 2x coarser grid (FPN)       */
+
+const char* eosvos_last_error(void);
+int eosvos_version(void);
+int eosvos_device_check(int device);
+
+/* ---- K1: dense contractions on tcgen05 (reference: cuDNN conv / ATen addmm reached from
+ *      src/networks/mask_rcnn.py:716 forward and src/meta_optim/meta_optim.py:202-204 backward) */
+
+/* y[N,Ho,Wo,Cout] = act(conv(x[N,H,W,Cin], w[Cout,KH,KW,Cin]) + bias + res).
+ * gn_sum (optional, fp32 [N][32][2], caller-zeroed): per-(image, group) sum / sum of squares of
+ * the fp32 outputs, for the GroupNorm that follows (mask_rcnn.py:523-534). */
+int eosvos_conv2d_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, float* gn_sum,
+                        int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int flags,
+                        int bn_hint, eosvos_stream_t stream);
+/* dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], wt[Cin,KH,KW,Cout]) */
+int eosvos_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout, int KH,
+                        int KW, int stride, int pad, int flags, int bn_hint, eosvos_stream_t stream);
+/* dw[Cout,Cin,KH,KW] (fp32, torch layout) += x (*) dy ; the caller zeroes dw */
+int eosvos_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int KH,
+                        int KW, int stride, int pad, int bn_hint, int split_hint, eosvos_stream_t stream);
+/* dw[m * s_m + (n / n_inner) * s_n_outer + (n % n_inner) * s_n_inner] += sum_r dy[r][m] * x[r][n]
+ * (Linear / stem-im2col weight gradients with an arbitrary destination layout) */
+int eosvos_gemm_wgrad(const void* x, const void* dy, float* dw, long long rows, int n_cols, int m_cols,
+                      long long s_m, int n_inner, long long s_n_inner, long long s_n_outer, int bn_hint,
+                      int split_hint, eosvos_stream_t stream);
+/* 2x2 / stride-2 transposed convolution of the mask head (tv MaskRCNNPredictor.conv5_mask) */
+int eosvos_deconv2x2_fprop(const void* x, const void* wd, const float* bias4, void* y, int N, int h, int w, int Cin,
+                           int Cout, int flags, int bn_hint, eosvos_stream_t stream);
+int eosvos_deconv2x2_dgrad(const void* dy, const void* wdt, void* dx, int N, int h, int w, int Cin, int Cout,
+                           int flags, int bn_hint, eosvos_stream_t stream);
+int eosvos_deconv2x2_wgrad(const void* x, const void* dy, float* dw, int N, int h, int w, int Cin, int Cout,
+                           int bn_hint, int split_hint, eosvos_stream_t stream);
+
+/* ---- K2/K3: GroupNorm(32) (+residual) (+ReLU)  (reference: mask_rcnn.py:523-534 -> ATen native_group_norm) */
+int eosvos_gn_stats(const void* x, float* sums, int N, int HW, int C, eosvos_stream_t stream);
+int eosvos_gn_apply(const void* x, const float* sums, const float* gamma, const float* beta, const void* res, void* y,
+                    int N, int HW, int C, float eps, int relu, eosvos_stream_t stream);
+int eosvos_gn_backward(const void* x, const float* sums, const float* gamma, const float* beta, const void* dy,
+                       const void* yout, float* part, void* dx, void* dres, float* dgamma, float* dbeta, int N, int HW,
+                       int C, float eps, int mask_mode, eosvos_stream_t stream);
+
+/* ---- K4: multi-scale RoIAlign (reference: mask_rcnn.py:113,147 -> torchvision::roi_align) */
+int eosvos_roi_align_fwd(const void* const* feats, const int* Hs, const int* Ws, const float* scales, const float* rois,
+                         void* out, int R, int P, int C, int sampling, eosvos_stream_t stream);
+int eosvos_roi_align_bwd(float* const* dfeats, const int* Hs, const int* Ws, const float* scales, const float* rois,
+                         const void* dout, int R, int P, int C, int sampling, eosvos_stream_t stream);
+/* mask targets (reference: mask_rcnn.py:38,70 -> tv project_masks_on_boxes) */
+int eosvos_mask_targets(const uint8_t* masks, const float* rois, float* out, int R, int M, int H, int W,
+                        eosvos_stream_t stream);
+
+/* ---- K7: fused mask losses, forward + gradient (reference: mask_rcnn.py:24-92, loss_lovasz.py:18-126) */
+int eosvos_mask_loss_lovasz(const float* logits, const long long* labels, const float* targets, float* loss_out,
+                            float* loss_per_roi, float* dlogits, int R, int Cc, int P, eosvos_stream_t stream);
+int eosvos_mask_loss_bce(const float* logits, const long long* labels, const float* targets, float* loss_out,
+                         float* dlogits, int R, int Cc, int P, eosvos_stream_t stream);
+
+/* ---- K8: inference tail (reference: tv roi_heads.py:56-82,378-502; helper_func.py:113-121;
+ *      mask_rcnn.py:626-632) */
+int eosvos_mask_paste_threshold(const float* logits, const int* det_of_chan, const long long* det_label,
+                                const float* det_box, float* probs, float* target, int* stats, int B, int K, int H,
+                                int W, int M, int Cc, float thresh, eosvos_stream_t stream);
+int eosvos_mask_to_bbox(const float* target, int* stats, int B, int K, int H, int W, eosvos_stream_t stream);
+
+/* ---- K9: MetaOptimizer update (reference: meta_optim.py:177-214, meta_model.py:78-80) */
+int eosvos_meta_update_chunk_elems(void);
+int eosvos_meta_update(const long long* table_dev, const int* chunks_dev, int num_chunks, int use_log,
+                       eosvos_stream_t stream);
+/* ---- K10: outer RAdam step of meta-training (reference: radam.py:28-94, train_meta.py:361-373) */
+int eosvos_radam_step(float* p, const float* g, float* m, float* v, long long n, float gscale, float clip, float beta1,
+                      float beta2, float eps, float lr, float wd, float step_size, int rectified, float clamp_lo,
+                      float clamp_hi, int do_clamp, eosvos_stream_t stream);
+
+/* ---- helpers around the kernels (reference: tv transform.py:119-160 etc., see csrc/misc.cu) */
+int eosvos_permute_cast(const void* src, void* dst, const long long* dims, const long long* sstride,
+                        const long long* dstride, int src_dtype, int dst_dtype, eosvos_stream_t stream);
+int eosvos_transform(const float* img, void* out, int B, int h, int w, int oh, int ow, int Hp, int Wp, int Cs,
+                     const float* mean3, const float* std3, eosvos_stream_t stream);
+int eosvos_mask_resize_nearest(const uint8_t* src, uint8_t* dst, int G, int h, int w, int oh, int ow,
+                               eosvos_stream_t stream);
+int eosvos_im2col_stem(const void* x, void* col, int N, int H, int W, int Cs, int KH, int KW, int stride, int pad,
+                       int Kp, eosvos_stream_t stream);
+int eosvos_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int ksz, int stride, int pad,
+                       eosvos_stream_t stream);
+int eosvos_maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, int N, int H, int W, int C, int ksz,
+                       int stride, int pad, eosvos_stream_t stream);
+int eosvos_subsample2(const void* x, void* y, int N, int H, int W, int C, int backward, eosvos_stream_t stream);
+int eosvos_sum2x2(const void* dfine, void* dcoarse, int N, int Hc, int Wc, int C, eosvos_stream_t stream);
+int eosvos_relu_bwd(const void* dy, const void* y, void* out, long long numel, eosvos_stream_t stream);
+int eosvos_colsum(const void* dy, float* out, long long M, int C, eosvos_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EOSVOS_B200_H */

@@ -1,0 +1,367 @@
+"""Parity of every CUDA kernel (called through the C ABI) against the CPU oracle (oracle/ops_oracle.py).
+
+Tolerances (stated per test): operands are bf16 (8-bit mantissa), accumulation fp32.  The oracle is
+evaluated in fp32 on the SAME bf16-rounded operands, so the remaining error is accumulation order plus
+one bf16 rounding of the stored result: rel. Frobenius error <= 4e-3 for bf16 outputs, <= 2e-5 for
+fp32 outputs.  Integer / index results (boxes, counts, targets) must match exactly.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ops_oracle as O  # noqa: E402
+
+
+def K():
+    from eosvos_b200 import kernels
+    return kernels
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+def make_conv(N, H, W, Cin, Cout, k, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = bf(torch.randn(N, Cin, H, W, generator=g)).float()
+    w = bf(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).float()
+    return x, w
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, bn_hint
+    (1, 16, 16, 64, 64, 1, 1, 0, 0),
+    (2, 12, 21, 64, 128, 1, 1, 0, 0),
+    (1, 24, 42, 256, 256, 3, 1, 1, 0),
+    (2, 12, 21, 128, 64, 3, 1, 1, 0),
+    (1, 48, 84, 64, 256, 3, 1, 1, 256),
+    (1, 48, 84, 64, 256, 3, 1, 1, 128),
+    (1, 48, 84, 64, 256, 3, 1, 1, 64),
+    (1, 24, 42, 128, 128, 3, 2, 1, 0),
+    (2, 24, 42, 256, 512, 1, 2, 0, 0),
+    (1, 28, 28, 256, 256, 3, 1, 1, 0),
+    (1, 7, 9, 64, 16, 1, 1, 0, 0),
+    (1, 17, 23, 64, 64, 3, 2, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_fprop(case):
+    N, H, W, Cin, Cout, k, s, p, bn = case
+    x, w = make_conv(N, H, W, Cin, Cout, k)
+    ref = O.conv2d(x, w, None, s, p)
+    y = K().conv2d_fprop(bf(nhwc(x)).to(dev()), bf(w.permute(0, 2, 3, 1).contiguous()).to(dev()), stride=s, pad=p,
+                         bn_hint=bn)
+    torch.cuda.synchronize()
+    got = nchw(y.float().cpu())
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 4e-3, (case, rel_err(got, ref))
+
+
+def test_conv2d_fprop_epilogue_variants():
+    N, H, W, Cin, Cout = 2, 24, 42, 64, 128
+    x, w = make_conv(N, H, W, Cin, Cout, 3, seed=1)
+    g = torch.Generator().manual_seed(5)
+    bias = torch.randn(Cout, generator=g)
+    res = bf(torch.randn(N, Cout, H, W, generator=g)).float()
+    res_half = bf(torch.randn(N, Cout, H // 2, W // 2, generator=g)).float()
+    xd, wd = bf(nhwc(x)).to(dev()), bf(w.permute(0, 2, 3, 1).contiguous()).to(dev())
+    base = O.conv2d(x, w, bias, 1, 1)
+    # bias + relu, fp32 out
+    y = K().conv2d_fprop(xd, wd, bias.to(dev()), stride=1, pad=1, relu=True, out_fp32=True)
+    assert rel_err(nchw(y.cpu()), F.relu(base)) < 2e-5
+    # bias + residual (same grid)
+    y = K().conv2d_fprop(xd, wd, bias.to(dev()), bf(nhwc(res)).to(dev()), stride=1, pad=1, out_fp32=True)
+    assert rel_err(nchw(y.cpu()), base + res) < 2e-5
+    # bias + residual on the 2x coarser grid (FPN top-down: nearest upsample + add)
+    y = K().conv2d_fprop(xd, wd, bias.to(dev()), bf(nhwc(res_half)).to(dev()), stride=1, pad=1, out_fp32=True,
+                         res_half=True)
+    up = F.interpolate(res_half, size=(H, W), mode="nearest")
+    assert rel_err(nchw(y.cpu()), base + up) < 2e-5
+    # GroupNorm statistics from the epilogue
+    gn = torch.zeros(N, 32, 2, device=dev())
+    y = K().conv2d_fprop(xd, wd, stride=1, pad=1, gn_sum=gn)
+    ref = O.conv2d(x, w, None, 1, 1).reshape(N, 32, -1)
+    torch.cuda.synchronize()
+    assert rel_err(gn[..., 0].cpu(), ref.sum(-1)) < 1e-3
+    assert rel_err(gn[..., 1].cpu(), (ref * ref).sum(-1)) < 1e-3
+    # 1x1 flat path with statistics, two images
+    x1, w1 = make_conv(2, 12, 21, 64, 256, 1, seed=2)
+    gn = torch.zeros(2, 32, 2, device=dev())
+    y = K().conv2d_fprop(bf(nhwc(x1)).to(dev()), bf(w1.permute(0, 2, 3, 1).contiguous()).to(dev()), gn_sum=gn)
+    ref = O.conv2d(x1, w1).reshape(2, 32, -1)
+    assert rel_err(nchw(y.float().cpu()), O.conv2d(x1, w1)) < 4e-3
+    assert rel_err(gn[..., 0].cpu(), ref.sum(-1)) < 1e-3
+    assert rel_err(gn[..., 1].cpu(), (ref * ref).sum(-1)) < 1e-3
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_dgrad(case):
+    N, H, W, Cin, Cout, k, s, p, bn = case
+    if Cout % 64 != 0:
+        pytest.skip("dgrad reduction (Cout) must be a multiple of 64")
+    x, w = make_conv(N, H, W, Cin, Cout, k, seed=3)
+    x.requires_grad_(True)
+    y = O.conv2d(x, w, None, s, p)
+    g = torch.Generator().manual_seed(9)
+    dy = bf(torch.randn(y.shape, generator=g)).float()
+    (ref,) = torch.autograd.grad(y, x, dy)
+    wt = bf(w.permute(1, 2, 3, 0).contiguous()).to(dev())  # [Cin,KH,KW,Cout]
+    dx = K().conv2d_dgrad(bf(nhwc(dy)).to(dev()), wt, (H, W), stride=s, pad=p, bn_hint=bn if Cin % max(bn, 1) == 0 else 0)
+    got = nchw(dx.float().cpu())
+    assert rel_err(got, ref) < 4e-3, (case, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_wgrad(case):
+    N, H, W, Cin, Cout, k, s, p, bn = case
+    x, w = make_conv(N, H, W, Cin, Cout, k, seed=4)
+    w.requires_grad_(True)
+    y = O.conv2d(x, w, None, s, p)
+    g = torch.Generator().manual_seed(11)
+    dy = bf(torch.randn(y.shape, generator=g)).float()
+    (ref,) = torch.autograd.grad(y, w, dy)
+    dw = K().conv2d_wgrad(bf(nhwc(x)).to(dev()), bf(nhwc(dy)).to(dev()), (k, k), stride=s, pad=p)
+    assert rel_err(dw.cpu(), ref) < 1e-4, (case, rel_err(dw.cpu(), ref))
+
+
+def test_gemm_wgrad_layouts():
+    g = torch.Generator().manual_seed(2)
+    R, Kin, Nout = 300, 49 * 64, 128  # fc6-like: x columns are (s, c) with c inner (64), torch wants (c, s)
+    x = bf(torch.randn(R, Kin, generator=g)).float()
+    dy = bf(torch.randn(R, Nout, generator=g)).float()
+    ref = dy.t() @ x  # [Nout, (s,c)]
+    ref_torch = ref.reshape(Nout, 49, 64).permute(0, 2, 1).reshape(Nout, Kin)  # [Nout, (c,s)]
+    out = torch.zeros(Nout, Kin, device=dev())
+    K().gemm_wgrad(bf(x).to(dev()), bf(dy).to(dev()), out, s_m=Kin, n_inner=64, s_n_inner=49, s_n_outer=1)
+    assert rel_err(out.cpu(), ref_torch) < 1e-4
+    out = torch.zeros(Nout, Kin, device=dev())
+    K().gemm_wgrad(bf(x).to(dev()), bf(dy).to(dev()), out, s_m=Kin)
+    assert rel_err(out.cpu(), ref) < 1e-4
+
+
+def test_deconv2x2():
+    g = torch.Generator().manual_seed(6)
+    N, h, w, Cin, Cout = 3, 28, 28, 256, 256
+    x = bf(torch.randn(N, Cin, h, w, generator=g)).float().requires_grad_(True)
+    wt = bf(torch.randn(Cin, Cout, 2, 2, generator=g) / 16).float().requires_grad_(True)
+    b = torch.randn(Cout, generator=g)
+    y = F.relu(F.conv_transpose2d(x, wt, b, stride=2))
+    dy = bf(torch.randn(y.shape, generator=g)).float()
+    dy_eff = dy * (y > 0)
+    rx, rw = torch.autograd.grad(y, (x, wt), dy)
+    wd = bf(wt.detach().permute(2, 3, 1, 0).reshape(4 * Cout, Cin).contiguous()).to(dev())      # [(dy,dx,co)][ci]
+    wdt = bf(wt.detach().permute(0, 2, 3, 1).reshape(Cin, 4 * Cout).contiguous()).to(dev())     # [ci][(dy,dx,co)]
+    xd = bf(nhwc(x.detach())).to(dev())
+    yd = K().deconv2x2_fprop(xd, wd, b.repeat(4).to(dev()), relu=True)
+    assert rel_err(nchw(yd.float().cpu()), y.detach()) < 4e-3
+    dyd = bf(nhwc(dy_eff)).to(dev())
+    dx = K().deconv2x2_dgrad(dyd, wdt)
+    assert rel_err(nchw(dx.float().cpu()), rx) < 4e-3
+    dw = K().deconv2x2_wgrad(xd, dyd)
+    assert rel_err(dw.cpu(), rw) < 1e-4
+
+
+@pytest.mark.parametrize("C,H,W,N", [(64, 48, 84, 2), (256, 24, 42, 1), (2048, 6, 11, 3), (128, 13, 7, 2)])
+def test_groupnorm_fwd_bwd(C, H, W, N):
+    g = torch.Generator().manual_seed(C)
+    x = bf(torch.randn(N, C, H, W, generator=g) * 2 + 0.5).float().requires_grad_(True)
+    gamma = (torch.rand(C, generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.2).requires_grad_(True)
+    res = bf(torch.randn(N, C, H, W, generator=g)).float()
+    k = K()
+    xd = bf(nhwc(x.detach())).to(dev())
+    sums = k.gn_stats(xd)
+    for relu, use_res in [(True, False), (False, False), (True, True)]:
+        y = O.group_norm(x, gamma, beta)
+        if use_res:
+            y = y + res
+        if relu:
+            y = F.relu(y)
+        yd = k.gn_apply(xd, sums, gamma.detach().to(dev()), beta.detach().to(dev()),
+                        bf(nhwc(res)).to(dev()) if use_res else None, relu=relu)
+        assert rel_err(nchw(yd.float().cpu()), y.detach()) < 4e-3
+        dy = bf(torch.randn(y.shape, generator=g)).float()
+        rx, rg, rb = torch.autograd.grad(y, (x, gamma, beta), dy)
+        mode = 0 if not relu else (2 if use_res else 1)
+        # the kernel takes its ReLU mask from the bf16 output it produced itself (mode 2) or recomputes it
+        # (mode 1); pixels where the oracle's pre-activation is within bf16 rounding of 0 may flip, hence 2e-2
+        dx, dres, dg, db = k.gn_backward(xd, sums, gamma.detach().to(dev()), beta.detach().to(dev()),
+                                         bf(nhwc(dy)).to(dev()), yout=yd if mode == 2 else None, mask_mode=mode,
+                                         want_dres=use_res)
+        assert rel_err(nchw(dx.float().cpu()), rx) < 2e-2, (relu, use_res, rel_err(nchw(dx.float().cpu()), rx))
+        assert rel_err(dg.cpu(), rg) < 2e-2
+        assert rel_err(db.cpu(), rb) < 2e-2
+        if use_res:
+            assert rel_err(nchw(dres.float().cpu()), dy * (y.detach() > 0)) < 2e-2
+
+
+def test_roi_align_fwd_bwd():
+    g = torch.Generator().manual_seed(3)
+    N, C = 2, 256
+    shapes = [(48, 84), (24, 42), (12, 21), (6, 11)]
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    feats = [bf(torch.randn(N, C, h, w, generator=g)).float().requires_grad_(True) for h, w in shapes]
+    R = 64
+    ctr = torch.rand(R, 2, generator=g) * torch.tensor([336.0, 192.0])
+    wh = torch.exp(torch.rand(R, 2, generator=g) * 5.0) + 2
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1).clamp(min=0)
+    boxes[:, 2].clamp_(max=336)
+    boxes[:, 3].clamp_(max=192)
+    rois = torch.cat([torch.randint(0, N, (R, 1), generator=g).float(), boxes], 1)
+    k = K()
+    for P in (7, 14):
+        ref = O.roi_align_multiscale(feats, scales, rois, P)
+        out = k.roi_align_fwd([bf(nhwc(f.detach())).to(dev()) for f in feats], scales, rois.to(dev()), P)
+        got = out.float().cpu().permute(0, 3, 1, 2)
+        assert rel_err(got, ref.detach()) < 4e-3
+        dy = bf(torch.randn(ref.shape, generator=g)).float()
+        refg = torch.autograd.grad(ref, feats, dy, allow_unused=True)
+        outs = k.roi_align_bwd(bf(dy.permute(0, 2, 3, 1).contiguous()).to(dev()), [(N, h, w, C) for h, w in shapes],
+                               scales, rois.to(dev()), P)
+        for gg, rr in zip(outs, refg):
+            rr = torch.zeros_like(feats[0]) if rr is None else rr
+            if rr.abs().sum() == 0:
+                assert gg.abs().sum().item() == 0
+            else:
+                assert rel_err(nchw(gg.cpu()), rr) < 1e-4
+
+
+def test_mask_targets():
+    g = torch.Generator().manual_seed(8)
+    G, H, W, R, M = 3, 60, 90, 40, 28
+    masks = (torch.rand(G, H, W, generator=g) > 0.6).to(torch.uint8)
+    ctr = torch.rand(R, 2, generator=g) * torch.tensor([float(W), float(H)])
+    wh = torch.rand(R, 2, generator=g) * 60 + 1
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    rois = torch.cat([torch.randint(0, G, (R, 1), generator=g).float(), boxes], 1)
+    ref = O.mask_targets(masks, rois, M)
+    got = K().mask_targets(masks.to(dev()), rois.to(dev()), M)
+    assert (got.cpu() - ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["LOVASZ", "BCE"])
+def test_mask_loss(kind):
+    g = torch.Generator().manual_seed(12)
+    R, Cc, M = 5, 2, 56
+    logits = (torch.randn(R, Cc, M, M, generator=g) * 2).requires_grad_(True)
+    labels = torch.ones(R, dtype=torch.int64)
+    targets = (torch.rand(R, M, M, generator=g) > 0.5).float()
+    targets[0, :10] = torch.rand(10, M, generator=g)          # fractional RoIAlign targets
+    if kind == "LOVASZ":
+        targets[1, 5:9] = 37.0                                # > 1 -> ignored (255)
+    ref = O.mask_loss(logits, labels, targets, kind)
+    (rg,) = torch.autograd.grad(ref, logits)
+    loss, dl = K().mask_loss(logits.detach().to(dev()), labels.to(dev()), targets.to(dev()), kind)
+    assert abs(loss.item() - ref.item()) < 1e-4 * max(1.0, abs(ref.item()))
+    assert rel_err(dl.cpu(), rg) < 1e-3
+
+
+def test_mask_paste_threshold_and_bbox():
+    g = torch.Generator().manual_seed(21)
+    H, W, M = 480, 854, 56
+    logits = torch.randn(2, 2, M, M, generator=g) * 3
+    # smooth blob so that the thresholded mask is non-trivial
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, M), torch.linspace(-1, 1, M), indexing="ij")
+    logits[:, 1] += 6 * (1 - 2 * (xx ** 2 + yy ** 2))
+    labels = torch.ones(2, dtype=torch.int64)
+    boxes = torch.tensor([[100.3, 50.7, 400.9, 300.2], [-20.5, 200.0, 120.25, 500.75]])
+    k = K()
+    for d in range(2):
+        ref = O.paste_probs(logits[d:d + 1], labels[d:d + 1], boxes[d:d + 1], H, W)  # [1,1,H,W]
+        ref_t = O.threshold_targets(ref)
+        chan = torch.tensor([d], dtype=torch.int32)
+        probs, target, stats = k.mask_paste_threshold(logits.to(dev()), chan.to(dev()), labels.to(dev()),
+                                                      boxes.to(dev()), 1, 1, H, W)
+        assert (probs.cpu() - ref).abs().max().item() < 1e-5
+        flips = (target.cpu() != ref_t) & ((ref - 0.5).abs() > 1e-5)
+        assert flips.sum().item() == 0
+        rb = O.mask_to_boxes(target.cpu()[0, 0], [1.0])[0]
+        st = stats.cpu()[0, 0]
+        assert [st[0].item(), st[1].item(), st[2].item() + 1, st[3].item() + 1] == rb.tolist()
+        assert st[4].item() == int((target.cpu() == 1).sum())
+        st2 = k.mask_to_bbox(target, 1).cpu()[0, 0]
+        assert st2.tolist() == st.tolist()
+    # no detection: all background
+    probs, target, stats = k.mask_paste_threshold(logits.to(dev()), torch.tensor([-1], dtype=torch.int32).to(dev()),
+                                                  labels.to(dev()), boxes.to(dev()), 1, 1, H, W)
+    assert probs.abs().sum().item() == 0 and target.abs().sum().item() == 0 and stats.cpu()[0, 0, 4].item() == 0
+
+
+def test_meta_update_bit_exact():
+    g = torch.Generator().manual_seed(1)
+    shapes = [(64, 3, 7, 7), (64,), (256, 64, 1, 1), (1024, 12544), (1024,), (2, 1024), (256, 256, 3, 3), (5,), (3, 1)]
+    params = [torch.randn(s, generator=g) for s in shapes]
+    grads = [torch.randn(s, generator=g) for s in shapes]
+    lrs = [torch.rand((s[0],) + (1,) * (len(s) - 1), generator=g) * 1e-3 for s in shapes]
+    k = K()
+    for use_log in (False, True):
+        lr_in = [l.log() for l in lrs] if use_log else lrs
+        ref = O.meta_update(params, grads, lr_in, use_log)
+        dp = [p.to(dev()) for p in params]
+        dg = [x.to(dev()) for x in grads]
+        dl = [x.to(dev()) for x in lr_in]
+        do = [torch.empty_like(p) for p in dp]
+        k.meta_update(k.MetaUpdatePlan(dp, dg, dl, do), use_log)
+        for o, r in zip(do, ref):
+            if use_log:  # expf on device vs CPU differs in the last ulp of lr
+                assert torch.allclose(o.cpu(), r, rtol=1e-6, atol=1e-9)
+            else:        # bit exact: same fp32 multiply and subtract
+                assert torch.equal(o.cpu(), r)
+
+
+def test_transform_and_stem():
+    g = torch.Generator().manual_seed(4)
+    img = torch.rand(2, 3, 120, 214, generator=g)
+    ref, (oh, ow) = O.transform_image(img, min_size=200, max_size=333)
+    Hp, Wp = ref.shape[-2:]
+    k = K()
+    out = k.transform(img.to(dev()), oh, ow, Hp, Wp, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+    got = out.float().cpu()[..., :3].permute(0, 3, 1, 2)
+    assert (got - ref).abs().max().item() < 0.02  # one bf16 rounding of values up to ~2.6
+    assert out.float().cpu()[..., 3:].abs().sum().item() == 0
+    # stem: im2col + flat GEMM == 7x7/2 conv
+    w = bf(torch.randn(64, 3, 7, 7, generator=g) / 12).float()
+    col, Ho, Wo = k.im2col_stem(out)
+    w2 = torch.zeros(64, 192)
+    w2[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)
+    y = k.conv2d_fprop(col.view(1, 1, -1, 192), bf(w2).view(64, 1, 1, 192).to(dev()))
+    refc = O.conv2d(got, w, None, 2, 3)
+    assert rel_err(y.float().cpu().view(2, Ho, Wo, 64).permute(0, 3, 1, 2), refc) < 4e-3
+    # pooling helpers
+    x = bf(torch.randn(2, 64, 23, 31, generator=g)).float().requires_grad_(True)
+    yp = F.max_pool2d(x, 3, 2, 1)
+    xd = bf(nhwc(x.detach())).to(dev())
+    yd = k.maxpool_fwd(xd)
+    assert torch.equal(nchw(yd.float().cpu()), yp.detach())
+    dy = bf(torch.randn(yp.shape, generator=g)).float()
+    (rx,) = torch.autograd.grad(yp, x, dy)
+    dx = k.maxpool_bwd(xd, yd, bf(nhwc(dy)).to(dev()))
+    assert rel_err(nchw(dx.float().cpu()), rx) < 4e-3
+    s = k.subsample2(xd)
+    assert torch.equal(nchw(s.float().cpu()), F.max_pool2d(x.detach(), 1, 2, 0))
+    u = k.sum2x2(bf(nhwc(x.detach()[:, :, :22, :30])).to(dev()))
+    assert rel_err(nchw(u.float().cpu()), F.avg_pool2d(x.detach()[:, :, :22, :30], 2) * 4) < 4e-3
+    c = k.colsum(xd.view(-1, 64))
+    assert rel_err(c.cpu(), x.detach().sum((0, 2, 3))) < 1e-4
