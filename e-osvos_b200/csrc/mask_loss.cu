@@ -57,7 +57,7 @@ lovasz_hinge_kernel(const float* __restrict__ logits, const long long* __restric
     float yy = 0.f;
     if (i < P) {
       yy = y[i];
-      if (yy != 255.0f) {
+      if (!(yy > 1.0f)) {  // mask_rcnn.py:86: targets > 1 become 255 = ignored
         k = 1.0f - x[i] * (2.0f * yy - 1.0f);
         ++nv;
       }

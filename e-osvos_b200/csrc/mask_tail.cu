@@ -37,8 +37,9 @@ struct BoxStat {  // per (image, id): xmin, ymin, xmax, ymax (inclusive pixel ex
   int v[5];
 };
 
-__device__ __forceinline__ void warp_box_update(int* stat, bool on, int x, int y) {
+__device__ __forceinline__ void warp_box_update(int* stat, bool on, int x, int y, bool count_it = true) {
   const unsigned m = __ballot_sync(0xffffffffu, on);
+  const unsigned mc = __ballot_sync(0xffffffffu, on && count_it);
   if (m == 0) return;
   int xmin = on ? x : INT_MAX, ymin = on ? y : INT_MAX, xmax = on ? x : -1, ymax = on ? y : -1;
 #pragma unroll
@@ -53,7 +54,7 @@ __device__ __forceinline__ void warp_box_update(int* stat, bool on, int x, int y
     atomicMin(stat + 1, ymin);
     atomicMax(stat + 2, xmax);
     atomicMax(stat + 3, ymax);
-    atomicAdd(stat + 4, __popc(m));
+    if (mc) atomicAdd(stat + 4, __popc(mc));
   }
 }
 
@@ -144,16 +145,17 @@ mask_to_bbox_kernel(const float* __restrict__ target, int* __restrict__ stats, i
   const int b0 = __shfl_sync(0xffffffffu, b, 0);
   const bool uniform = __all_sync(0xffffffffu, b == b0);
   for (int k = 0; k < K; ++k) {
-    const bool on = inb && (v == (float)(k + 1) || v == 255.0f);
+    const bool exact = inb && v == (float)(k + 1);
+    const bool on = exact || (inb && v == 255.0f);   // box covers ignore pixels, count only the id itself
     if (uniform) {
-      warp_box_update(stats + ((size_t)b0 * K + k) * 5, on, x, y);
+      warp_box_update(stats + ((size_t)b0 * K + k) * 5, on, x, y, exact);
     } else if (on) {
       int* s = stats + ((size_t)b * K + k) * 5;
       atomicMin(s + 0, x);
       atomicMin(s + 1, y);
       atomicMax(s + 2, x);
       atomicMax(s + 3, y);
-      atomicAdd(s + 4, 1);
+      if (exact) atomicAdd(s + 4, 1);
     }
   }
 }

@@ -48,22 +48,22 @@ meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ 
         }
       }
       float4 o;
-      o.x = pv.x - gv.x * l[0];
-      o.y = pv.y - gv.y * l[1];
-      o.z = pv.z - gv.z * l[2];
-      o.w = pv.w - gv.w * l[3];
+      o.x = __fsub_rn(pv.x, __fmul_rn(gv.x, l[0]));  // no FMA contraction: bit-exact with p - (g * lr)
+      o.y = __fsub_rn(pv.y, __fmul_rn(gv.y, l[1]));
+      o.z = __fsub_rn(pv.z, __fmul_rn(gv.z, l[2]));
+      o.w = __fsub_rn(pv.w, __fmul_rn(gv.w, l[3]));
       *reinterpret_cast<float4*>(out + i) = o;
     }
     for (long long i = start + (nv << 2) + threadIdx.x; i < start + n; i += MU_THREADS) {
       float lv = __ldg(lr + i / row_len);
       if (use_log) lv = expf(lv);
-      out[i] = p[i] - g[i] * lv;
+      out[i] = __fsub_rn(p[i], __fmul_rn(g[i], lv));
     }
   } else {
     for (long long i = start + threadIdx.x; i < start + n; i += MU_THREADS) {
       float lv = __ldg(lr + i / row_len);
       if (use_log) lv = expf(lv);
-      out[i] = p[i] - g[i] * lv;
+      out[i] = __fsub_rn(p[i], __fmul_rn(g[i], lv));
     }
   }
 }

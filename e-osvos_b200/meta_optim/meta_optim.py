@@ -1,0 +1,211 @@
+"""MetaOptimizer with learned initialisation and learned per-neuron learning rates -- same constructor,
+attributes, state-dict keys and methods as reference src/meta_optim/meta_optim.py:10-214 -- whose
+`step` applies  theta <- theta - lr (.) grad  to ALL parameter tensors with ONE fused CUDA kernel
+(libeosvos_b200: eosvos_meta_update) instead of >= 402 elementwise launches.
+
+Meta-training keeps working: the fused update is an autograd Function whose backward gives
+d/d theta = upstream and d/d lr = -rowsum(upstream (.) grad) (first-order BPTT, reference
+src/util/meta_run.py:124-214).  Second-order meta-gradients (second_order_gradients=True while
+training) would need double-backward through hand-written kernels and raise NotImplementedError.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+from torch.autograd.function import once_differentiable
+
+from .. import kernels as K
+from .meta_model import MetaModel
+
+
+class _FusedUpdateFn(torch.autograd.Function):
+    """outs_i = p_i - lr_i * g_i for every tensor i in one launch."""
+
+    @staticmethod
+    def forward(ctx, use_log, n, *tensors):
+        params, grads, lrs = tensors[:n], tensors[n:2 * n], tensors[2 * n:]
+        ps = [p.detach().contiguous() for p in params]
+        gs = [g.detach().contiguous() for g in grads]
+        ls = [l.detach().contiguous() for l in lrs]
+        total = sum(p.numel() for p in ps)
+        arena = torch.empty(total, device=ps[0].device, dtype=torch.float32)
+        outs, off = [], 0
+        for p in ps:
+            outs.append(arena[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        K.meta_update(K.MetaUpdatePlan(ps, gs, ls, outs), use_log)
+        ctx.use_log, ctx.n = use_log, n
+        ctx.save_for_backward(*gs, *ls)
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *douts):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        gs, ls = saved[:n], saved[n:]
+        dps, dls = [], []
+        for i in range(n):
+            d = douts[i]
+            if d is None:
+                dps.append(None)
+                dls.append(None)
+                continue
+            dps.append(d)
+            if ctx.needs_input_grad[2 + 2 * n + i]:
+                prod = -(d * gs[i])
+                red = [k for k in range(prod.dim()) if ls[i].shape[k] == 1 and prod.shape[k] != 1] \
+                    if ls[i].dim() == prod.dim() else None
+                if red is None:
+                    dl = prod.sum().reshape(ls[i].shape) if ls[i].numel() == 1 else prod.reshape(ls[i].shape)
+                else:
+                    dl = prod.sum(dim=red, keepdim=True) if red else prod
+                if ctx.use_log:
+                    dl = dl * ls[i].exp()
+                dls.append(dl)
+            else:
+                dls.append(None)
+        return (None, None, *dps, *([None] * n), *dls)
+
+
+class MetaOptimizer(nn.Module):
+
+    def __init__(self, model, init_lr, learn_model_init, second_order_gradients, lr_hierarchy_level,
+                 use_log_init_lr, max_lr):
+        super(MetaOptimizer, self).__init__()
+        self._optim = None
+        self._train_loss = None
+        self._device = 'cpu'
+        self._learn_model_init = learn_model_init
+        self._second_order_gradients = second_order_gradients
+        self._use_log_init_lr = use_log_init_lr
+        self._max_lr = max_lr
+        self._lr_hierarchy_level = lr_hierarchy_level
+
+        self.meta_model = MetaModel(model)
+
+        def _maybe_log(t):
+            return t.log() if self._use_log_init_lr else t
+
+        # learning-rate parameters, meta_optim.py:28-69 (same RNG consumption: one rand_like per tensor)
+        if lr_hierarchy_level == 'SINGLE':
+            self.log_init_lr = torch.nn.Parameter(_maybe_log(torch.ones(1, 1).mul(init_lr)))
+        elif lr_hierarchy_level == 'TENSOR':
+            lr = torch.ones(self.meta_model.num_param_groups, 1).mul(init_lr)
+            lr += torch.rand_like(lr).sub(0.5) * init_lr
+            self.log_init_lr = torch.nn.Parameter(_maybe_log(lr))
+        elif lr_hierarchy_level in ('PARAM', 'NEURON'):
+            self.log_init_lr = []
+            for name, param in model.named_parameters():
+                if not param.requires_grad:
+                    continue
+                if lr_hierarchy_level == 'PARAM':
+                    lr = torch.ones_like(param).mul(init_lr)
+                else:
+                    lr = torch.ones((param.shape[0],) + (1,) * (len(param.shape) - 1)).mul(init_lr)
+                lr += torch.rand_like(lr).sub(0.5) * init_lr
+                lr = torch.nn.Parameter(_maybe_log(lr))
+                self.register_parameter(f"log_init_lr_{name.replace('.', '-')}", lr)
+                self.log_init_lr.append(lr)
+        else:
+            raise NotImplementedError
+
+        # learned initialisation theta_0, meta_optim.py:71-78
+        self._model_init = OrderedDict()
+        for name, param in model.named_parameters():
+            if param.requires_grad:
+                self._model_init[name] = param
+        if self._learn_model_init:
+            for name, param in self._model_init.items():
+                self.register_parameter(f"model_init_{name.replace('.', '-')}", param)
+
+        self.state = {}
+        self._init_state()
+
+    # ---- meta_optim.py:83-107
+    def _lr_values(self, lrs):
+        if isinstance(lrs, list):
+            vals = [l.exp().mean() if self._use_log_init_lr else l.mean() for l in lrs]
+            return vals
+        return lrs.exp() if self._use_log_init_lr else lrs
+
+    @property
+    def init_lr(self):
+        v = self._lr_values(self.log_init_lr)
+        return torch.Tensor(v) if isinstance(v, list) else v
+
+    @property
+    def state_lr(self):
+        v = self._lr_values(self.state["log_lr"])
+        return torch.tensor(v) if isinstance(v, list) else v
+
+    def init_zero_grad(self):
+        output = 0.0
+        for param in self.parameters():
+            output = output + param.mean()
+        output.backward()
+        self.zero_grad()
+
+    # ---- meta_optim.py:116-133
+    def clamp_init_lr(self):
+        min_clamp = -33 if self._use_log_init_lr else 0
+        max_clamp = None
+        if self._max_lr is not None:
+            max_clamp = torch.log(torch.tensor(self._max_lr)) if self._use_log_init_lr else self._max_lr
+        if isinstance(self.log_init_lr, list):
+            self.log_init_lr = [l.data.clamp_(min_clamp, max_clamp) for l in self.log_init_lr]
+        else:
+            self.log_init_lr.data.clamp_(min_clamp, max_clamp)
+
+    # ---- meta_optim.py:135-163
+    def to(self, device):
+        super(MetaOptimizer, self).to(device)
+        self._device = device
+        if isinstance(self.state['log_lr'], list):
+            self.state['log_lr'] = [l.to(device) for l in self.state['log_lr']]
+        else:
+            self.state['log_lr'] = self.state['log_lr'].to(device)
+
+    def reset(self, keep_state=False):
+        if keep_state:
+            if isinstance(self.log_init_lr, list):
+                self.state['log_lr'] = [l.detach() for l in self.state['log_lr']]
+            else:
+                self.state['log_lr'] = self.state['log_lr'].detach()
+            self.meta_model.detach_param_groups()
+        else:
+            self.meta_model.init_param_groups(self._model_init)
+            self._init_state()
+
+    def _init_state(self):
+        if self._lr_hierarchy_level == 'SINGLE':
+            self.state["log_lr"] = self.log_init_lr.repeat(self.meta_model.num_param_groups, 1)
+        else:
+            self.state["log_lr"] = self.log_init_lr
+        self.state["num_steps"] = 0
+
+    def set_train_loss(self, train_loss):
+        if not self.training or not self._second_order_gradients:
+            train_loss = train_loss.detach()
+        self._train_loss = train_loss
+
+    # ---- meta_optim.py:177-214, fused
+    def step(self, train_loss):
+        if self.training and self._second_order_gradients:
+            raise NotImplementedError(
+                "second_order_gradients=True needs create_graph through hand-written backward kernels; "
+                "the B200 path supports the reference default (first-order, cfgs/meta.yaml:40)")
+        groups = list(self.meta_model.param_groups())
+        params = [p for _, _, _, p in groups]
+        # same tensors, same order as [p for p in model.parameters() if p.requires_grad] (meta_optim.py:202-204)
+        grads = torch.autograd.grad(train_loss, params)
+        lrs = self.state["log_lr"]
+        if not isinstance(lrs, list):
+            lrs = [lrs[i] for i in range(len(params))]
+        dev = params[0].device
+        lrs = [l if l.device == dev else l.to(dev) for l in lrs]
+        grads = [g if g.device == dev else g.to(dev) for g in grads]
+        n = len(params)
+        new_params = _FusedUpdateFn.apply(bool(self._use_log_init_lr), n, *params, *grads, *lrs)
+        self.meta_model.set_param_groups(new_params)
+        self.state["num_steps"] += 1

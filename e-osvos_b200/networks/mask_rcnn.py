@@ -1,0 +1,520 @@
+"""Drop-in for the reference's `networks.mask_rcnn.MaskRCNN` (reference src/networks/mask_rcnn.py:423-775)
+whose forward/backward runs on the hand-written sm_100a kernels of libeosvos_b200.so.
+
+Same constructor, same `forward(inputs, targets, box_coord_perm, flip_label)` contract, same module
+tree (it subclasses torchvision's MaskRCNN exactly like the reference does, so `named_parameters()`,
+`state_dict()`, `model.rpn._eval_augment_proposals_mode`, `model.roi_heads.detections_per_img` ...
+are the reference's).  Parameters are read from the module tree on every call, so MetaModel's
+replacement of `module._parameters[name]` by non-leaf tensors (reference meta_model.py:78-80) is seen.
+
+What runs where:
+  * convs / GroupNorm / ReLU / pooling / Linear / deconv / RoIAlign / mask loss / inference tail:
+    CUDA kernels through the C ABI (ops.py);
+  * anchor generation, box coding, IoU matching, samplers, top-k + NMS, the small RPN / box losses:
+    the torchvision / torch operators the reference itself calls (kept in PyTorch so
+    that RNG consumption -- device randperm, CPU torch.rand for EXTEND -- is identical).
+There is no CPU path: tensors must be CUDA tensors on an sm_100 device.
+"""
+import types
+from collections import OrderedDict
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+from torchvision.models.detection import MaskRCNN as _MaskRCNN
+from torchvision.models.detection.backbone_utils import resnet_fpn_backbone
+from torchvision.models.detection.roi_heads import fastrcnn_loss
+from torchvision.ops import MultiScaleRoIAlign
+from torchvision.ops import boxes as box_ops
+from torchvision.ops.misc import FrozenBatchNorm2d
+
+from .. import kernels as K
+from .. import ops
+
+
+class _ImageListLike:
+    """What AnchorGenerator needs from an ImageList: padded tensor shape + per-image sizes."""
+
+    def __init__(self, shape, image_sizes, device):
+        self.tensors = torch.empty(shape, device="meta")
+        self.image_sizes = image_sizes
+        self._device = device
+
+
+class MaskRCNN(_MaskRCNN):
+
+    def __init__(self, backbone, num_classes, batch_norm=None, train_encoder=True,
+                 roi_pool_output_sizes=None, eval_augment_rpn_proposals_mode=None,
+                 replace_batch_with_group_norms=False, box_nms_thresh=0.5,
+                 maskrcnn_loss='LOVASZ'):
+        # construction order mirrors reference mask_rcnn.py:430-520 so that a given torch seed yields
+        # the same random initialisation.
+        self._num_groups = 32
+        backbone_model = resnet_fpn_backbone(backbone_name=backbone, weights=None, trainable_layers=5)
+
+        mask_roi_pool, box_roi_pool = None, None
+        if roi_pool_output_sizes is not None:
+            box_roi_pool = MultiScaleRoIAlign(featmap_names=['0', '1', '2', '3'],
+                                              output_size=roi_pool_output_sizes['box'], sampling_ratio=2)
+            mask_roi_pool = MultiScaleRoIAlign(featmap_names=['0', '1', '2', '3'],
+                                               output_size=roi_pool_output_sizes['mask'], sampling_ratio=2)
+
+        super(MaskRCNN, self).__init__(backbone_model, num_classes, box_roi_pool=box_roi_pool,
+                                       mask_roi_pool=mask_roi_pool, mask_head=None,
+                                       box_score_thresh=box_nms_thresh)
+
+        self.num_classes = num_classes
+        self.rpn._eval_augment_proposals_mode = eval_augment_rpn_proposals_mode
+        self.roi_heads._eval_augment_proposals_mode = eval_augment_rpn_proposals_mode
+        self.roi_heads.maskrcnn_loss = maskrcnn_loss
+        self._roi_sizes = roi_pool_output_sizes or {'box': 7, 'mask': 14}
+
+        if replace_batch_with_group_norms:
+            self.replace_batch_with_group_norms()
+        self._uses_group_norm = replace_batch_with_group_norms
+
+        self._train_encoder = train_encoder
+        if not train_encoder:
+            self.requires_grad_(False)
+            self.rpn.requires_grad_(True)
+            self.roi_heads.box_head.requires_grad_(True)
+            self.roi_heads.box_predictor.requires_grad_(True)
+            self.roi_heads.mask_head.requires_grad_(True)
+            self.roi_heads.mask_predictor.requires_grad_(True)
+        else:
+            self.backbone.requires_grad_(True)
+
+        self._accum_batch_norm_stats = True
+        if batch_norm is not None:
+            self._accum_batch_norm_stats = batch_norm['accum_stats']
+            for m in self.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.weight.requires_grad = batch_norm['learn_weight']
+                    m.bias.requires_grad = batch_norm['learn_bias']
+
+        self._second_order_derivates_module_names = ['roi_heads']
+        self.last_param_group_names = ['roi_heads.box_predictor.cls_score.weight',
+                                       'roi_heads.box_predictor.cls_score.bias',
+                                       'roi_heads.box_predictor.bbox_pred.weight',
+                                       'roi_heads.box_predictor.bbox_pred.bias',
+                                       'roi_heads.mask_predictor.mask_fcn_logits.weight',
+                                       'roi_heads.mask_predictor.mask_fcn_logits.bias']
+        self._anchor_cache = {}
+        # test hooks (tests/test_model_gpu.py): bypass RPN proposals / capture stage outputs
+        self.fixed_proposals = None
+        self.capture = None
+
+    # ---- reference API (mask_rcnn.py:523-570) ------------------------------------------------
+    def replace_batch_with_group_norms(self):
+        for module in self.modules():
+            bn_keys = [k for k, m in module._modules.items()
+                       if isinstance(m, FrozenBatchNorm2d) or isinstance(m, nn.BatchNorm2d)]
+            for k in bn_keys:
+                batch_norm = module._modules[k]
+                group_norm = nn.GroupNorm(self._num_groups, batch_norm.weight.shape[0])
+                group_norm.weight.data = batch_norm.weight
+                group_norm.bias.data = batch_norm.bias
+                module._modules[k] = group_norm
+
+    def named_parameters_with_second_order_derivate(self, recurse=True):
+        for name, param in self.named_parameters(recurse=recurse):
+            if param.requires_grad and any(m in name for m in self._second_order_derivates_module_names):
+                yield name, param
+
+    def named_parameters_without_second_order_derivate(self, recurse=True):
+        for name, param in self.named_parameters(recurse=recurse):
+            if param.requires_grad and not any(m in name for m in self._second_order_derivates_module_names):
+                yield name, param
+
+    def train(self, mode=True):
+        super(MaskRCNN, self).train(mode)
+        if not self._train_encoder:
+            self.backbone.eval()
+        if not self._accum_batch_norm_stats:
+            for m in self.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.eval()
+        return self
+
+    def train_without_dropout(self):
+        self.train()
+        for m in self.modules():
+            if isinstance(m, torch.nn.Dropout2d) or isinstance(m, torch.nn.Dropout):
+                m.eval()
+
+    # ---- targets (reference mask_rcnn.py:582-714), bbox on the device ---------------------------
+    def _build_targets(self, targets, flip_label, device):
+        if flip_label:
+            targets = 1 - targets
+        B = targets.shape[0]
+        Kc = max(self.num_classes - 1, 1)
+        t32 = targets.to(torch.float32).contiguous()
+        stats_d = K.mask_to_bbox(t32, Kc)
+        ign_d = (t32 == 255.0).flatten(1).any(dim=1).to(torch.int32)
+        packed = torch.cat([stats_d.flatten(), ign_d]).cpu()   # ONE small D2H per forward (the reference does several)
+        stats = packed[:B * Kc * 5].view(B, Kc, 5)
+        ign = packed[B * Kc * 5:]
+        out = []
+        for b in range(B):
+            mask = t32[b]                            # [1,H,W]
+            # ids present = ids owning at least one pixel (reference: torch.unique minus {0, 255})
+            ids = [k + 1 for k in range(Kc) if int(stats[b, k, 4]) > 0]
+            num_objs = len(ids)
+            assert num_objs >= 1, f"num_objs: {num_objs}"
+            obj_ids = torch.tensor(ids, dtype=torch.float32, device=device)
+            masks = mask == obj_ids[:, None, None]
+            has_ignore = bool(int(ign[b]))
+            if has_ignore:
+                masks = masks | (mask == 255.0)
+            boxes = []
+            for oid in ids:
+                xmin, ymin, xmax, ymax, _ = stats[b, oid - 1].tolist()
+                boxes.append([xmin, ymin, xmax + 1, ymax + 1])
+            boxes = torch.as_tensor(boxes, dtype=torch.float32)
+            labels = obj_ids.type(torch.int64)
+            masks = masks.type(torch.uint8)
+            if has_ignore:
+                masks[(mask == 255.0).expand_as(masks)] = 255
+                masks[(mask == 0.0).expand_as(masks)] = 255
+            if flip_label:
+                masks = 1 - masks
+            area = (boxes[:, 3] - boxes[:, 1]) * (boxes[:, 2] - boxes[:, 0])
+            out.append({"boxes": boxes.to(device), "labels": labels, "masks": masks,
+                        "image_id": torch.tensor([0], device=device), "area": area.to(device),
+                        "iscrowd": torch.zeros((num_objs,), dtype=torch.int64, device=device)})
+        return out
+
+    # ---- transform (tv transform.py:119-160, 25-84, 237-255) ------------------------------------
+    def _resized_size(self, h, w):
+        tr = self.transform
+        if self.training:
+            size = tr.torch_choice(tr.min_size)      # consumes CPU RNG exactly like torchvision
+        else:
+            size = tr.min_size[-1]
+        im_shape = torch.tensor([h, w])
+        mn = torch.min(im_shape).to(dtype=torch.float32)
+        mx = torch.max(im_shape).to(dtype=torch.float32)
+        scale = torch.min(torch.tensor(float(size)) / mn, torch.tensor(float(tr.max_size)) / mx).item()
+        import math
+        return int(math.floor(float(h) * scale)), int(math.floor(float(w) * scale))
+
+    def _transform(self, inputs, targets):
+        tr = self.transform
+        B, _, h, w = inputs.shape
+        oh, ow = self._resized_size(h, w)
+        div = int(tr.size_divisible)
+        Hp, Wp = (oh + div - 1) // div * div, (ow + div - 1) // div * div
+        x8 = K.transform(inputs.to(torch.float32).contiguous(), oh, ow, Hp, Wp, tr.image_mean, tr.image_std, Cs=8)
+        if targets is not None:
+            rh = torch.tensor(oh, dtype=torch.float32, device=inputs.device) / torch.tensor(
+                h, dtype=torch.float32, device=inputs.device)
+            rw = torch.tensor(ow, dtype=torch.float32, device=inputs.device) / torch.tensor(
+                w, dtype=torch.float32, device=inputs.device)
+            new = []
+            for t in targets:
+                t = dict(t)
+                xmin, ymin, xmax, ymax = t["boxes"].unbind(1)
+                t["boxes"] = torch.stack((xmin * rw, ymin * rh, xmax * rw, ymax * rh), dim=1)
+                if self.training:
+                    t["masks"] = K.mask_resize_nearest(t["masks"].contiguous(), oh, ow)
+                new.append(t)
+            targets = new
+        return x8, targets, (oh, ow), (Hp, Wp)
+
+    # ---- backbone (tv resnet.py Bottleneck v1.5 + FPN), NHWC bf16 --------------------------------
+    def _norm_args(self, n):
+        if not isinstance(n, nn.GroupNorm):
+            raise NotImplementedError(
+                "the B200 path implements the GroupNorm model the reference's configs build "
+                "(cfgs/meta.yaml:76 replace_batch_with_group_norms: True)")
+        return n.weight, n.bias
+
+    def _bottleneck(self, blk, x):
+        s = blk.conv2.stride[0]
+        out = ops.conv_gn(x, blk.conv1.weight, *self._norm_args(blk.bn1), None, 1, 0, True)
+        out = ops.conv_gn(out, blk.conv2.weight, *self._norm_args(blk.bn2), None, s, 1, True)
+        if blk.downsample is not None:
+            ds = blk.downsample[0].stride[0]
+            identity = ops.conv_gn(x, blk.downsample[0].weight, *self._norm_args(blk.downsample[1]), None, ds, 0,
+                                   False)
+        else:
+            identity = x
+        return ops.conv_gn(out, blk.conv3.weight, *self._norm_args(blk.bn3), identity, 1, 0, True)
+
+    def _backbone(self, x8):
+        body = self.backbone.body
+        x = ops.stem(x8, body.conv1.weight, *self._norm_args(body.bn1))
+        x = ops.maxpool3x3s2(x)
+        feats = []
+        for name in ("layer1", "layer2", "layer3", "layer4"):
+            for blk in getattr(body, name):
+                x = self._bottleneck(blk, x)
+            feats.append(x)
+        fpn = self.backbone.fpn
+
+        def conv_of(m):
+            return m[0] if isinstance(m, nn.Sequential) else m
+
+        inner = [conv_of(m) for m in fpn.inner_blocks]
+        layer = [conv_of(m) for m in fpn.layer_blocks]
+        last_inner = ops.conv2d(feats[3], inner[3].weight, inner[3].bias)
+        results = [ops.conv2d(last_inner, layer[3].weight, layer[3].bias, pad=1)]
+        for idx in (2, 1, 0):
+            fh, fw = feats[idx].shape[1:3]
+            if fh != 2 * last_inner.shape[1] or fw != 2 * last_inner.shape[2]:
+                raise NotImplementedError("FPN levels must be exact 2x of each other (inputs are padded to /32)")
+            last_inner = ops.conv2d(feats[idx], inner[idx].weight, inner[idx].bias, res=last_inner, res_half=True)
+            results.insert(0, ops.conv2d(last_inner, layer[idx].weight, layer[idx].bias, pad=1))
+        results.append(ops.subsample2(results[-1]))
+        return results  # P2..P6
+
+    # ---- RPN (reference mask_rcnn.py:217-344) ---------------------------------------------------
+    def _anchors(self, image_shape, image_sizes, feat_shapes, device):
+        key = (tuple(image_shape), tuple(image_sizes), tuple(feat_shapes), str(device))
+        if key not in self._anchor_cache:
+            il = _ImageListLike(image_shape, list(image_sizes), device)
+            fms = [torch.empty((image_shape[0], 1, h, w), device=device, dtype=torch.float32) for h, w in feat_shapes]
+            self._anchor_cache = {key: [a.detach() for a in self.rpn.anchor_generator(il, fms)]}
+        return self._anchor_cache[key]
+
+    def _rpn(self, feats, image_shape, image_sizes, targets):
+        rpn = self.rpn
+        head = rpn.head
+        conv = head.conv[0][0] if isinstance(head.conv, nn.Sequential) else head.conv
+        N = feats[0].shape[0]
+        obj, dlt, feat_shapes = [], [], []
+        for f in feats:
+            _, H, W, C = f.shape
+            t = ops.conv2d(f, conv.weight, conv.bias, pad=1, relu=True)
+            o = ops.fused_heads(t.reshape(-1, C), [head.cls_logits.weight, head.bbox_pred.weight],
+                                [head.cls_logits.bias, head.bbox_pred.bias])
+            A = head.cls_logits.weight.shape[0]
+            obj.append(o[:, :A].reshape(N, H * W * A, 1))
+            dlt.append(o[:, A:A + 4 * A].reshape(N, H * W * A, 4))
+            feat_shapes.append((H, W))
+        num_anchors_per_level = [o.shape[1] for o in obj]
+        objectness = torch.cat(obj, dim=1).flatten(0, -2)
+        pred_bbox_deltas = torch.cat(dlt, dim=1).flatten(0, -2)
+        if self.capture is not None:
+            self.capture.update(objectness=objectness.detach(), deltas=pred_bbox_deltas.detach())
+        anchors = self._anchors(image_shape, image_sizes, feat_shapes, feats[0].device)
+        proposals = rpn.box_coder.decode(pred_bbox_deltas.detach(), anchors).view(N, -1, 4)
+        boxes, scores = rpn.filter_proposals(proposals, objectness, image_sizes, num_anchors_per_level)
+
+        mode = rpn._eval_augment_proposals_mode
+        if not self.training and targets is not None and mode is not None:
+            # reference mask_rcnn.py:251-332: jittered copies of the previous-frame box (CPU torch.rand, same
+            # call order => same random stream)
+            random_share = 0.1
+            post = rpn.post_nms_top_n()
+            num_box_augs = post // 2 if mode == 'EXTEND' else post
+            img_height, img_width = image_shape[-2:]
+            for i, target in enumerate(targets):
+                tb = target['boxes'].cpu()
+                target_boxes = []
+                for box in tb:
+                    bw, bh = box[2] - box[0], box[3] - box[1]
+                    x_mins = box[0] - torch.rand((num_box_augs,)) * bw * random_share
+                    y_mins = box[1] - torch.rand((num_box_augs,)) * bh * random_share
+                    x_maxs = box[2] + torch.rand((num_box_augs,)) * bw * random_share
+                    y_maxs = box[3] + torch.rand((num_box_augs,)) * bh * random_share
+                    target_boxes.append(torch.stack([x_mins.clamp(0, img_width), y_mins.clamp(0, img_height),
+                                                     x_maxs.clamp(0, img_width), y_maxs.clamp(0, img_height)], dim=1))
+                target_boxes = torch.cat(target_boxes, dim=0).to(scores[0].device)
+                if mode == 'EXTEND':
+                    boxes[i] = torch.cat([boxes[i][:post // 2], target_boxes], dim=0)
+                elif mode == 'REPLACE':
+                    boxes[i] = target_boxes
+                else:
+                    raise NotImplementedError
+
+        losses = {}
+        if self.training:
+            labels, matched_gt_boxes = rpn.assign_targets_to_anchors(anchors, targets)
+            regression_targets = rpn.box_coder.encode(matched_gt_boxes, anchors)
+            loss_objectness, loss_rpn_box_reg = rpn.compute_loss(objectness, pred_bbox_deltas, labels,
+                                                                 regression_targets)
+            losses = {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
+        return boxes, losses
+
+    # ---- RoI heads (reference mask_rcnn.py:95-214, 347-420) -------------------------------------
+    _SCALES = (1 / 4, 1 / 8, 1 / 16, 1 / 32)
+
+    @staticmethod
+    def _rois5(boxes):
+        return torch.cat([torch.cat([torch.full((b.shape[0], 1), i, dtype=b.dtype, device=b.device), b], dim=1)
+                          for i, b in enumerate(boxes)], dim=0).to(torch.float32).contiguous()
+
+    def _postprocess_detections(self, class_logits, box_regression, proposals, image_shapes):
+        rh = self.roi_heads
+        device = class_logits.device
+        num_classes = class_logits.shape[-1]
+        boxes_per_image = [len(b) for b in proposals]
+        pred_boxes = rh.box_coder.decode(box_regression, proposals)
+        pred_scores = F.softmax(class_logits, -1)
+        pred_boxes = pred_boxes.split(boxes_per_image, 0)
+        pred_scores = pred_scores.split(boxes_per_image, 0)
+        all_boxes, all_scores, all_labels = [], [], []
+        for boxes, scores, image_shape in zip(pred_boxes, pred_scores, image_shapes):
+            boxes = box_ops.clip_boxes_to_image(boxes, image_shape)
+            labels = torch.arange(num_classes, device=device).view(1, -1).expand_as(scores)
+            boxes, scores, labels = boxes[:, 1:], scores[:, 1:], labels[:, 1:]
+            boxes, scores, labels = boxes.reshape(-1, 4), scores.flatten(), labels.flatten()
+            inds = torch.nonzero(scores > rh.score_thresh).squeeze(1)
+            boxes, scores, labels = boxes[inds], scores[inds], labels[inds]
+            keep = box_ops.remove_small_boxes(boxes, min_size=1e-2)
+            boxes, scores, labels = boxes[keep], scores[keep], labels[keep]
+            keep = box_ops.batched_nms(boxes, scores, labels, rh.nms_thresh)
+            keep = keep[:rh.detections_per_img]
+            all_boxes.append(boxes[keep])
+            all_scores.append(scores[keep])
+            all_labels.append(labels[keep])
+        return all_boxes, all_scores, all_labels
+
+    def _mask_branch(self, feats, mask_proposals):
+        rh = self.roi_heads
+        P = self._roi_sizes['mask']
+        x = ops.roi_align(feats[:4], self._SCALES, self._rois5(mask_proposals), P)
+        for blk in rh.mask_head:
+            conv = blk[0] if isinstance(blk, nn.Sequential) else blk
+            x = ops.conv2d(x, conv.weight, conv.bias, pad=1, relu=True)
+        mp = rh.mask_predictor
+        x = ops.deconv2x2(x, mp.conv5_mask.weight, mp.conv5_mask.bias, relu=True)
+        n, M, _, C = x.shape
+        o = ops.fused_heads(x.reshape(-1, C), [mp.mask_fcn_logits.weight], [mp.mask_fcn_logits.bias])
+        ncls = mp.mask_fcn_logits.weight.shape[0]
+        return o[:, :ncls].reshape(n, M, M, ncls).permute(0, 3, 1, 2).contiguous()   # [n, ncls, M, M] fp32
+
+    def _roi_heads(self, feats, proposals, image_sizes, targets):
+        rh = self.roi_heads
+        if self.training:
+            proposals, matched_idxs, labels, regression_targets = rh.select_training_samples(proposals, targets)
+        Pb = self._roi_sizes['box']
+        bx = ops.roi_align(feats[:4], self._SCALES, self._rois5(proposals), Pb)
+        R, _, _, C = bx.shape
+        h = ops.linear(bx.reshape(R, Pb * Pb * C), rh.box_head.fc6.weight, rh.box_head.fc6.bias, relu=True, inner=C)
+        h = ops.linear(h, rh.box_head.fc7.weight, rh.box_head.fc7.bias, relu=True)
+        bp = rh.box_predictor
+        o = ops.fused_heads(h, [bp.cls_score.weight, bp.bbox_pred.weight], [bp.cls_score.bias, bp.bbox_pred.bias])
+        nc = bp.cls_score.weight.shape[0]
+        class_logits, box_regression = o[:, :nc], o[:, nc:nc + 4 * nc]
+        if self.capture is not None:
+            self.capture.update(class_logits=class_logits.detach(), box_regression=box_regression.detach(),
+                                sampled_proposals=[p.detach() for p in proposals])
+
+        result, losses = [], {}
+        if self.training:
+            loss_classifier, loss_box_reg = fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
+            losses = dict(loss_classifier=loss_classifier, loss_box_reg=loss_box_reg)
+            mask_proposals, pos_matched_idxs = [], []
+            for img_id in range(len(proposals)):
+                pos = torch.nonzero(labels[img_id] > 0).squeeze(1)
+                mask_proposals.append(proposals[img_id][pos])
+                pos_matched_idxs.append(matched_idxs[img_id][pos])
+        else:
+            boxes, scores, labels = self._postprocess_detections(class_logits, box_regression, proposals, image_sizes)
+            for i in range(len(boxes)):
+                result.append(dict(boxes=boxes[i], labels=labels[i], scores=scores[i]))
+            mask_proposals = [p["boxes"] for p in result]
+
+        n_mask = sum(p.shape[0] for p in mask_proposals)
+        if n_mask > 0:
+            mask_logits = self._mask_branch(feats, mask_proposals)
+            if self.capture is not None:
+                self.capture.update(mask_logits=mask_logits.detach())
+        elif len(mask_proposals) > 1:
+            raise NotImplementedError
+        else:
+            mask_logits = torch.zeros((0, self.num_classes, 2 * self._roi_sizes['mask'], 2 * self._roi_sizes['mask']),
+                                      device=feats[0].device)
+
+        if self.training:
+            kind = rh.maskrcnn_loss
+            if kind not in ('BCE', 'LOVASZ'):
+                raise NotImplementedError
+            if n_mask == 0:
+                loss_mask = torch.zeros((), device=feats[0].device)
+            else:
+                gt_masks = [t["masks"] for t in targets]
+                gt_labels = [t["labels"] for t in targets]
+                lab = torch.cat([l[idxs] for l, idxs in zip(gt_labels, pos_matched_idxs)], dim=0)
+                offs, rois = 0, []
+                for m, p, i in zip(gt_masks, mask_proposals, pos_matched_idxs):
+                    rois.append(torch.cat([(i + offs).to(p)[:, None], p], dim=1))
+                    offs += m.shape[0]
+                M = mask_logits.shape[-1]
+                tg = K.mask_targets(torch.cat(gt_masks, 0).contiguous(),
+                                    torch.cat(rois, 0).to(torch.float32).contiguous(), M)
+                loss_mask = ops.mask_loss(mask_logits, lab.contiguous(), tg, kind)
+            losses.update(dict(loss_mask=loss_mask))
+        else:
+            for r in result:
+                r["mask_logits_all"] = mask_logits   # class select + sigmoid + paste are fused in the tail kernel
+        return result, losses, mask_logits
+
+    # ---- forward (reference mask_rcnn.py:572-775) -----------------------------------------------
+    def forward(self, inputs, targets=None, box_coord_perm=None, flip_label=False):
+        device = inputs.device
+        if device.type != "cuda":
+            raise RuntimeError("eosvos_b200.MaskRCNN runs on sm_100 CUDA devices only (no CPU fallback)")
+        if targets is not None:
+            targets = self._build_targets(targets, flip_label, device)
+        if self.training and targets is None:
+            raise ValueError("targets should not be None in training mode")
+        B, _, h, w = inputs.shape
+        x8, targets_t, (oh, ow), (Hp, Wp) = self._transform(inputs, targets)
+        image_sizes = [(oh, ow)] * B
+        image_shape = (B, 3, Hp, Wp)
+
+        grad_ctx = torch.enable_grad() if self.training else torch.no_grad()
+        with grad_ctx:
+            feats = self._backbone(x8)
+            proposals, rpn_losses = self._rpn(feats, image_shape, image_sizes, targets_t)
+            if self.fixed_proposals is not None:
+                proposals = [p.to(device).clone() for p in self.fixed_proposals]
+            if self.capture is not None:
+                self.capture.update(feats=feats, proposals=[p.detach() for p in proposals], x8=x8)
+            detections, det_losses, mask_logits = self._roi_heads(feats, proposals, image_sizes, targets_t)
+
+        if self.training:
+            raw = {}
+            raw.update(det_losses)
+            raw.update(rpn_losses)
+            losses = {n: l for n, l in raw.items() if l.requires_grad}
+            loss = sum([l for l in losses.values()])
+            return loss, losses
+
+        # eval: first detection of every class -> dense probability map + box (mask_rcnn.py:732-775),
+        # boxes rescaled to the input frame (tv transform.py:257-278), paste/threshold fused on device
+        Kc = self.num_classes - 1
+        rh_ = torch.tensor(h, dtype=torch.float32, device=device) / torch.tensor(oh, dtype=torch.float32, device=device)
+        rw_ = torch.tensor(w, dtype=torch.float32, device=device) / torch.tensor(ow, dtype=torch.float32, device=device)
+        det_boxes, det_labels, chan, off = [], [], [], 0
+        cls_ids = torch.arange(1, self.num_classes, device=device)
+        for det in detections:
+            b = det["boxes"]
+            xmin, ymin, xmax, ymax = b.unbind(1)
+            b = torch.stack((xmin * rw_, ymin * rh_, xmax * rw_, ymax * rh_), dim=1)
+            lab = det["labels"]
+            if lab.shape[0] > 0:
+                eq = lab[None, :] == cls_ids[:, None]
+                first = eq.to(torch.int32).argmax(dim=1)
+                chan.append(torch.where(eq.any(dim=1), first + off, torch.full_like(first, -1)))
+            else:
+                chan.append(torch.full((Kc,), -1, dtype=torch.int64, device=device))
+            det_boxes.append(b)
+            det_labels.append(lab)
+            off += lab.shape[0]
+        det_boxes = torch.cat(det_boxes, 0).to(torch.float32).contiguous()
+        det_labels = torch.cat(det_labels, 0).to(torch.int64).contiguous()
+        chan = torch.cat(chan, 0).to(torch.int32).contiguous()
+        probs, tgt, stats = K.mask_paste_threshold(mask_logits, chan, det_labels, det_boxes, B, Kc, h, w, 0.5,
+                                                   want_target=True)
+        safe = chan.clamp(min=0).to(torch.int64)
+        if det_boxes.shape[0] > 0:
+            out_boxes = torch.where((chan >= 0)[:, None], det_boxes[safe], torch.zeros_like(det_boxes[safe]))
+        else:
+            out_boxes = torch.zeros((B * Kc, 4), device=device)
+        self.last_propagated_target = tgt        # threshold/argmax of helper_func.py:113-121, already on device
+        self.last_target_stats = stats
+        return probs, out_boxes.view(B, Kc, 4)

@@ -1,0 +1,476 @@
+"""torch.autograd.Function wrappers around the CUDA kernels.
+
+They exist so that the reference's MetaOptimizer.step -- which calls torch.autograd.grad(loss, params)
+on parameter tensors that live in module._parameters as NON-LEAF tensors (reference
+src/meta_optim/meta_optim.py:202-204, src/meta_optim/meta_model.py:78-80) -- keeps working unchanged
+on top of hand-written forward/backward kernels.  Activations flow between Functions as NHWC bf16;
+parameters and their gradients are fp32 in torch's layouts.  Second-order (create_graph=True) is not
+supported by hand-written backward kernels: Functions are marked once_differentiable, so asking for it
+raises instead of silently falling back.
+"""
+import weakref
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import kernels as K
+
+# --------------------------------------------------------------------------------------------
+# parameter -> tensor-core operand layouts (bf16), cached per live parameter tensor
+# --------------------------------------------------------------------------------------------
+_prep_cache = {}
+
+
+def _cache_get(p, kind):
+    key = (id(p), kind)
+    hit = _prep_cache.get(key)
+    if hit is not None:
+        ref, version, ptr, val = hit
+        if ref() is p and version == p._version and ptr == p.data_ptr():
+            return val
+    return None
+
+
+def _cache_put(p, kind, val):
+    key = (id(p), kind)
+
+    def _drop(_, key=key):
+        _prep_cache.pop(key, None)
+
+    _prep_cache[key] = (weakref.ref(p, _drop), p._version, p.data_ptr(), val)
+    return val
+
+
+def clear_prep_cache():
+    _prep_cache.clear()
+
+
+def _permute_to(src, shape, dims, sstride, dtype=torch.bfloat16):
+    out = torch.empty(shape, device=src.device, dtype=dtype)
+    dstride = [1, 1, 1, 1]
+    for i in (2, 1, 0):
+        dstride[i] = dstride[i + 1] * dims[i + 1]
+    K.permute_cast(src, out, dims, sstride, dstride)
+    return out
+
+
+def prep_conv_w(w):
+    """fp32 [O,I,KH,KW] -> bf16 [O,KH,KW,I] (fprop B operand)."""
+    hit = _cache_get(w, "f")
+    if hit is not None:
+        return hit
+    wd = w.detach().contiguous()
+    O, I, KH, KW = wd.shape
+    T = KH * KW
+    out = _permute_to(wd, (O, KH, KW, I), (1, O, T, I), (0, I * T, 1, T))
+    return _cache_put(w, "f", out)
+
+
+def prep_conv_wt(w):
+    """fp32 [O,I,KH,KW] -> bf16 [I,KH,KW,O] (dgrad B operand)."""
+    hit = _cache_get(w, "t")
+    if hit is not None:
+        return hit
+    wd = w.detach().contiguous()
+    O, I, KH, KW = wd.shape
+    T = KH * KW
+    out = _permute_to(wd, (I, KH, KW, O), (1, I, T, O), (0, T, 1, I * T))
+    return _cache_put(w, "t", out)
+
+
+def prep_linear_w(w, inner=0):
+    """fp32 [O, K] -> bf16 [O,1,1,K]; with inner=C the K axis is re-ordered (c, s) -> (s, c)
+    (fc6 consumes NHWC-pooled features)."""
+    kind = ("lf", inner)
+    hit = _cache_get(w, kind)
+    if hit is not None:
+        return hit
+    wd = w.detach().contiguous()
+    O, Kd = wd.shape
+    if inner:
+        C, S = inner, Kd // inner
+        out = _permute_to(wd, (O, 1, 1, Kd), (1, O, S, C), (0, Kd, 1, S))
+    else:
+        out = _permute_to(wd, (O, 1, 1, Kd), (1, 1, O, Kd), (0, 0, Kd, 1))
+    return _cache_put(w, kind, out)
+
+
+def prep_linear_wt(w, inner=0):
+    """fp32 [O, K] -> bf16 [K,1,1,O] (dgrad operand), same K re-ordering as prep_linear_w."""
+    kind = ("lt", inner)
+    hit = _cache_get(w, kind)
+    if hit is not None:
+        return hit
+    wd = w.detach().contiguous()
+    O, Kd = wd.shape
+    if inner:
+        C, S = inner, Kd // inner
+        out = _permute_to(wd, (Kd, 1, 1, O), (1, S, C, O), (0, 1, S, Kd))
+    else:
+        out = _permute_to(wd, (Kd, 1, 1, O), (1, 1, Kd, O), (0, 0, 1, Kd))
+    return _cache_put(w, kind, out)
+
+
+def _fused_head_w(ws, pad_to):
+    """Stacks several [O_i, K(,1,1)] fp32 weights into one bf16 [pad_to,1,1,K] (zero rows beyond sum O_i)
+    and the transposed [K,1,1,64] operand (zero-padded columns) used by the backward GEMMs."""
+    kind = ("head", pad_to)
+    hit = _cache_get(ws[0], kind)
+    if hit is not None and all(a is b() and a._version == v for a, (b, v) in zip(ws[1:], hit[2])):
+        return hit[0], hit[1]
+    flat = torch.cat([w.detach().reshape(w.shape[0], -1) for w in ws], 0)
+    O, Kd = flat.shape
+    wf = torch.zeros((pad_to, 1, 1, Kd), device=flat.device, dtype=torch.bfloat16)
+    wf.view(pad_to, Kd)[:O] = flat.to(torch.bfloat16)
+    wt = torch.zeros((Kd, 1, 1, 64), device=flat.device, dtype=torch.bfloat16)
+    wt.view(Kd, 64)[:, :O] = flat.t().to(torch.bfloat16)
+    _cache_put(ws[0], kind, (wf, wt, [(weakref.ref(w), w._version) for w in ws[1:]]))
+    return wf, wt
+
+
+def _gn_cpg_ok(C):
+    return C % 32 == 0
+
+
+# --------------------------------------------------------------------------------------------
+# conv (+bias) (+residual, optionally on the 2x coarser grid) (+ReLU)
+# --------------------------------------------------------------------------------------------
+class Conv2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, res, stride, pad, relu, res_half):
+        wf = prep_conv_w(w)
+        y = K.conv2d_fprop(x, wf, bias.detach() if bias is not None else None, res, stride=stride, pad=pad, relu=relu,
+                           res_half=res_half)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.cfg = (stride, pad, relu, res_half, bias is not None, res is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        stride, pad, relu, res_half, has_bias, has_res = ctx.cfg
+        dy = dy.contiguous()
+        if relu:
+            dy = K.relu_bwd(dy, y)
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv2d_dgrad(dy, prep_conv_wt(w), x.shape[1:3], stride=stride, pad=pad)
+        if ctx.needs_input_grad[1]:
+            dw = K.conv2d_wgrad(x, dy, w.shape[2:], stride=stride, pad=pad)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = K.colsum(dy.view(-1, dy.shape[-1]))
+        if has_res and ctx.needs_input_grad[3]:
+            dres = K.sum2x2(dy) if res_half else dy
+        return dx, dw, db, dres, None, None, None, None
+
+
+def conv2d(x, w, bias=None, res=None, stride=1, pad=0, relu=False, res_half=False):
+    return Conv2dFn.apply(x, w, bias, res, stride, pad, relu, res_half)
+
+
+# --------------------------------------------------------------------------------------------
+# conv -> GroupNorm(32) (+residual) (+ReLU): statistics come out of the conv epilogue
+# --------------------------------------------------------------------------------------------
+class ConvGnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, res, stride, pad, relu):
+        wf = prep_conv_w(w)
+        N = x.shape[0]
+        sums = torch.zeros((N, 32, 2), device=x.device, dtype=torch.float32)
+        z = K.conv2d_fprop(x, wf, stride=stride, pad=pad, gn_sum=sums)
+        g, b = gamma.detach(), beta.detach()
+        y = K.gn_apply(z, sums, g, b, res, relu=relu)
+        mode = 0 if not relu else (2 if res is not None else 1)
+        ctx.save_for_backward(x, w, gamma, beta, z, sums, y if mode == 2 else None)
+        ctx.cfg = (stride, pad, mode, res is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, gamma, beta, z, sums, y = ctx.saved_tensors
+        stride, pad, mode, has_res = ctx.cfg
+        dy = dy.contiguous()
+        dz, dres, dgamma, dbeta = K.gn_backward(z, sums, gamma.detach(), beta.detach(), dy, yout=y, mask_mode=mode,
+                                                want_dres=has_res and ctx.needs_input_grad[4])
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv2d_dgrad(dz, prep_conv_wt(w), x.shape[1:3], stride=stride, pad=pad)
+        if ctx.needs_input_grad[1]:
+            dw = K.conv2d_wgrad(x, dz, w.shape[2:], stride=stride, pad=pad)
+        return dx, dw, dgamma, dbeta, dres, None, None, None
+
+
+def conv_gn(x, w, gamma, beta, res=None, stride=1, pad=0, relu=True):
+    return ConvGnFn.apply(x, w, gamma, beta, res, stride, pad, relu)
+
+
+# --------------------------------------------------------------------------------------------
+# stem: 7x7/2 conv (explicit im2col, K = 147 -> 192) -> GN -> ReLU.  No data gradient.
+# --------------------------------------------------------------------------------------------
+def _prep_stem_w(w):
+    hit = _cache_get(w, "stem")
+    if hit is not None:
+        return hit
+    wd = w.detach().contiguous()
+    O, I, KH, KW = wd.shape
+    T = KH * KW
+    Kp = ((T * I + 63) // 64) * 64
+    out = torch.zeros((O, 1, 1, Kp), device=wd.device, dtype=torch.bfloat16)
+    # dst[o][t*I + c] = src[o][c][t]
+    K.permute_cast(wd, out, (1, O, T, I), (0, I * T, 1, T), (0, Kp, I, 1))
+    return _cache_put(w, "stem", out)
+
+
+class StemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x8, w, gamma, beta):
+        O, I, KH, KW = w.shape
+        wf = _prep_stem_w(w)
+        Kp = wf.shape[-1]
+        N = x8.shape[0]
+        col, Ho, Wo = K.im2col_stem(x8, KH, KW, 2, 3, Kp)
+        sums = torch.zeros((N, 32, 2), device=x8.device, dtype=torch.float32)
+        z = K.conv2d_fprop(col.view(N, 1, Ho * Wo, Kp), wf, gn_sum=sums).view(N, Ho, Wo, O)
+        y = K.gn_apply(z, sums, gamma.detach(), beta.detach(), None, relu=True)
+        ctx.save_for_backward(col, w, gamma, beta, z, sums)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        col, w, gamma, beta, z, sums = ctx.saved_tensors
+        O, I, KH, KW = w.shape
+        dz, _, dgamma, dbeta = K.gn_backward(z, sums, gamma.detach(), beta.detach(), dy.contiguous(), mask_mode=1)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(w, dtype=torch.float32)
+            T = KH * KW
+            # column n = t*I + c  ->  torch offset c*T + t
+            K.gemm_wgrad(col, dz.view(-1, O), dw, s_m=I * T, n_inner=I, s_n_inner=T, s_n_outer=1)
+        return None, dw, dgamma, dbeta
+
+
+def stem(x8, w, gamma, beta):
+    return StemFn.apply(x8, w, gamma, beta)
+
+
+class MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = K.maxpool_fwd(x, 3, 2, 1)
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        return K.maxpool_bwd(x, y, dy.contiguous(), 3, 2, 1)
+
+
+def maxpool3x3s2(x):
+    return MaxPoolFn.apply(x)
+
+
+class Subsample2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.in_shape = tuple(x.shape)
+        return K.subsample2(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        return K.subsample2_bwd(dy.contiguous(), ctx.in_shape)
+
+
+def subsample2(x):
+    return Subsample2Fn.apply(x)
+
+
+# --------------------------------------------------------------------------------------------
+# Linear (+bias) (+ReLU) on [R, K] bf16 rows
+# --------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, relu, inner):
+        R, Kd = x.shape
+        O = w.shape[0]
+        wf = prep_linear_w(w, inner)
+        y = K.conv2d_fprop(x.view(1, 1, R, Kd), wf, bias.detach() if bias is not None else None, relu=relu).view(R, O)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.cfg = (relu, inner, bias is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        relu, inner, has_bias = ctx.cfg
+        R, Kd = x.shape
+        O = w.shape[0]
+        dy = dy.contiguous()
+        if relu:
+            dy = K.relu_bwd(dy, y)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv2d_dgrad(dy.view(1, 1, R, O), prep_linear_wt(w, inner), (1, R)).view(R, Kd)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros((O, Kd), device=x.device, dtype=torch.float32)
+            if inner:
+                K.gemm_wgrad(x, dy, dw, s_m=Kd, n_inner=inner, s_n_inner=Kd // inner, s_n_outer=1)
+            else:
+                K.gemm_wgrad(x, dy, dw, s_m=Kd)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = K.colsum(dy)
+        return dx, dw, db, None, None
+
+
+def linear(x, w, bias=None, relu=False, inner=0):
+    return LinearFn.apply(x, w, bias, relu, inner)
+
+
+# --------------------------------------------------------------------------------------------
+# fused small-N heads: several 1x1 convs / Linears sharing one input, fp32 output [rows, 16]
+# --------------------------------------------------------------------------------------------
+class HeadFn(torch.autograd.Function):
+    """y[rows, 16] (fp32) = x[rows, K] @ cat(ws)^T + cat(bs); columns beyond sum(O_i) are zero."""
+
+    @staticmethod
+    def forward(ctx, x, *wb):
+        n = len(wb) // 2
+        ws, bs = wb[:n], wb[n:]
+        rows, Kd = x.shape
+        wf, _ = _fused_head_w(ws, 16)
+        bias = torch.zeros(16, device=x.device, dtype=torch.float32)
+        o = 0
+        for b in bs:
+            bias[o:o + b.numel()] = b.detach()
+            o += b.numel()
+        y = K.conv2d_fprop(x.view(1, 1, rows, Kd), wf, bias, out_fp32=True).view(rows, 16)
+        ctx.save_for_backward(x, *ws)
+        ctx.n = n
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x = ctx.saved_tensors[0]
+        ws = ctx.saved_tensors[1:]
+        n = ctx.n
+        rows, Kd = x.shape
+        dyp = torch.zeros((rows, 64), device=x.device, dtype=torch.bfloat16)
+        dyp[:, :16] = dy
+        _, wt = _fused_head_w(ws, 16)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv2d_dgrad(dyp.view(1, 1, rows, 64), wt, (1, rows)).view(rows, Kd)
+        dwf = torch.zeros((64, Kd), device=x.device, dtype=torch.float32)
+        K.gemm_wgrad(x, dyp, dwf, s_m=Kd)
+        dbf = dy.sum(0)
+        dws, dbs = [], []
+        o = 0
+        for w in ws:
+            O = w.shape[0]
+            dws.append(dwf[o:o + O].reshape(w.shape))
+            dbs.append(dbf[o:o + O])
+            o += O
+        return (dx, *dws, *dbs)
+
+
+def fused_heads(x, ws, bs):
+    return HeadFn.apply(x, *ws, *bs)
+
+
+# --------------------------------------------------------------------------------------------
+# 2x2/2 transposed conv (+bias) (+ReLU)
+# --------------------------------------------------------------------------------------------
+def _prep_deconv(w):
+    hit = _cache_get(w, "dc")
+    if hit is not None:
+        return hit
+    wd = w.detach().contiguous()
+    I, O = wd.shape[:2]
+    # fwd operand [(dy,dx,o)][i]: src[i][o][g] ; dgrad operand [i][(dy,dx,o)]
+    wf = _permute_to(wd, (4 * O, I), (1, 4, O, I), (0, 1, 4, 4 * O))
+    wt = _permute_to(wd, (I, 4 * O), (1, I, 4, O), (0, 4 * O, 1, 4))
+    return _cache_put(w, "dc", (wf, wt))
+
+
+class Deconv2x2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, relu):
+        wf, _ = _prep_deconv(w)
+        y = K.deconv2x2_fprop(x, wf, bias.detach().repeat(4).contiguous() if bias is not None else None, relu=relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.cfg = (relu, bias is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        relu, has_bias = ctx.cfg
+        dy = dy.contiguous()
+        if relu:
+            dy = K.relu_bwd(dy, y)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = K.deconv2x2_dgrad(dy, _prep_deconv(w)[1])
+        if ctx.needs_input_grad[1]:
+            dw = K.deconv2x2_wgrad(x, dy)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = K.colsum(dy.view(-1, dy.shape[-1]))
+        return dx, dw, db, None
+
+
+def deconv2x2(x, w, bias=None, relu=False):
+    return Deconv2x2Fn.apply(x, w, bias, relu)
+
+
+# --------------------------------------------------------------------------------------------
+# multi-scale RoIAlign over the 4 FPN levels
+# --------------------------------------------------------------------------------------------
+class RoiAlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rois, P, scales, f0, f1, f2, f3):
+        feats = [f0, f1, f2, f3]
+        out = K.roi_align_fwd(feats, scales, rois, P)
+        ctx.save_for_backward(rois)
+        ctx.cfg = (P, tuple(scales), [tuple(f.shape) for f in feats])
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (rois,) = ctx.saved_tensors
+        P, scales, shapes = ctx.cfg
+        grads = K.roi_align_bwd(dout.contiguous(), shapes, scales, rois, P)
+        return (None, None, None, *[g.to(torch.bfloat16) for g in grads])
+
+
+def roi_align(feats, scales, rois, P):
+    return RoiAlignFn.apply(rois, P, scales, *feats)
+
+
+# --------------------------------------------------------------------------------------------
+# mask loss (forward and gradient produced together by one kernel)
+# --------------------------------------------------------------------------------------------
+class MaskLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, targets, kind):
+        loss, dlogits = K.mask_loss(logits.contiguous(), labels, targets, kind)
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None, None, None
+
+
+def mask_loss(logits, labels, targets, kind):
+    return MaskLossFn.apply(logits, labels, targets, kind)

@@ -1,0 +1,98 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.pt by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_shims.py) on seeded synthetic inputs.  Run in the build
+container:  python -m oracle.make_golden
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shims  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+MIN_SIZE, MAX_SIZE = 160, 266      # transform.min/max_size override that keeps the CPU suite fast
+
+
+def synthetic_frame(seed, h=96, w=170):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(1, 3, h, w, generator=g)
+    tgt = torch.zeros(1, 1, h, w)
+    tgt[0, 0, 30:70, 50:120] = 1
+    return img, tgt
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    mr, ll, mo, mm = ref_shims.reference_modules()
+
+    # --- Lovasz hinge (loss_lovasz.py:78-126) ------------------------------------------------
+    g = torch.Generator().manual_seed(7)
+    logits = (torch.randn(4, 56, 56, generator=g) * 2).requires_grad_(True)
+    labels = (torch.rand(4, 56, 56, generator=g) > 0.5).float()
+    labels[0, :8] = torch.rand(8, 56, generator=g)
+    labels[1, 3:6] = 255.0
+    loss = ll.lovasz_hinge(logits, labels, per_image=True, ignore=255.0)
+    (grad,) = torch.autograd.grad(loss, logits)
+    torch.save({"logits": logits.detach(), "labels": labels, "loss": loss.detach(), "grad": grad},
+               os.path.join(OUT, "lovasz.pt"))
+
+    # --- MetaOptimizer.step on a small module (meta_optim.py:177-214) --------------------------
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.GroupNorm(4, 8), torch.nn.Flatten(),
+                              torch.nn.Linear(8 * 6 * 6, 5))
+    for use_log in (False, True):
+        torch.manual_seed(6)
+        opt = mo.MetaOptimizer(net, init_lr=1e-2, learn_model_init=True, second_order_gradients=False,
+                               lr_hierarchy_level='NEURON', use_log_init_lr=use_log, max_lr=None)
+        opt.reset()
+        opt.eval()
+        x = torch.randn(2, 3, 8, 8, generator=torch.Generator().manual_seed(9))
+        l = net(x).square().mean()
+        params = [p.detach().clone() for p in net.parameters()]
+        grads = torch.autograd.grad(l, list(net.parameters()), retain_graph=True)
+        opt.step(l)
+        new = [p.detach().clone() for _, _, _, p in opt.meta_model.param_groups()]
+        torch.save({"params": params, "grads": [g_.detach() for g_ in grads],
+                    "lrs": [l_.detach().clone() for l_ in opt.state["log_lr"]], "new": new, "use_log": use_log},
+                   os.path.join(OUT, f"meta_update_{'log' if use_log else 'lin'}.pt"))
+        opt.reset()
+
+    # --- model: train forward + grads + one step + eval forward (mask_rcnn.py:572-775) ----------
+    for kind in ("LOVASZ", "BCE"):
+        model = ref_shims.build_reference_model(seed=1, maskrcnn_loss=kind, min_size=MIN_SIZE, max_size=MAX_SIZE)
+        img, tgt = synthetic_frame(11)
+        torch.manual_seed(3)
+        opt = mo.MetaOptimizer(model, init_lr=1e-3, learn_model_init=True, second_order_gradients=False,
+                               lr_hierarchy_level='NEURON', use_log_init_lr=False, max_lr=None)
+        opt.reset()
+        opt.eval()
+        model.train_without_dropout()
+        torch.manual_seed(21)
+        loss, losses = model(img, tgt)
+        names = [n for n, p in model.named_parameters() if p.requires_grad]
+        grads = torch.autograd.grad(loss, [p for p in model.parameters() if p.requires_grad], retain_graph=True)
+        gnorm = {n: g_.norm().item() for n, g_ in zip(names, grads)}
+        keep = ["backbone.body.conv1.weight", "backbone.body.layer2.0.conv2.weight", "backbone.fpn.layer_blocks.0.0.weight",
+                "rpn.head.conv.0.0.weight", "roi_heads.box_head.fc6.weight", "roi_heads.mask_predictor.conv5_mask.weight",
+                "roi_heads.mask_predictor.mask_fcn_logits.bias"]
+        gsample = {n: g_.flatten()[:64].clone() for n, g_ in zip(names, grads) if n in keep}
+        opt.set_train_loss(loss)
+        opt.step(loss)
+        opt.meta_model.detach_param_groups()
+        pnorm = {f"{n_m}.{n_p}": p.norm().item() for n_m, _, n_p, p in opt.meta_model.param_groups()}
+        model.eval()
+        torch.manual_seed(22)
+        with torch.no_grad():
+            probs, boxes = model(img, tgt)
+        torch.save({"img": img, "tgt": tgt, "loss": loss.detach(), "losses": {k: v.detach() for k, v in losses.items()},
+                    "grad_norms": gnorm, "grad_samples": gsample, "param_norms_after_step": pnorm,
+                    "eval_probs": probs.half(), "eval_boxes": boxes, "min_size": MIN_SIZE, "max_size": MAX_SIZE},
+                   os.path.join(OUT, f"model_small_{kind.lower()}.pt"))
+        opt.reset()
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
