@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the e-OSVOS hot path (BASELINE.json: "fine-tune iters/s + inference frames/s, 480p
+e-OSVOS-100-OnA").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One STEP = one online-adaptation block of the e-OSVOS-100-OnA schedule on one 854x480 object
+(evaluate.py:140-317): ITERS_PER_STEP fine-tune iterations at batch 3 (forward + backward + fused
+MetaOptimizer update) followed by FRAMES_PER_STEP inference frames with target propagation -- the 10:3
+iteration:frame ratio of a 70-frame video under e-OSVOS-100-OnA (230 iterations, 69 frames).
+`value` = fine-tune iterations/s (device-resident inputs); `frames_per_s` = inference object-frames/s;
+`e2e` = the same block driven through the public API from pinned HOST buffers (H2D of every batch/frame,
+D2H of every loss/probability map inside the timed region).  With N > 1 every rank runs its own objects
+(weak scaling, no data-path collective); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+ITERS_PER_STEP = 10
+FRAMES_PER_STEP = 3
+BATCH = 3
+H, W = 480, 854
+METRIC = "finetune_iters_per_s"
+UNIT = "iter/s (batch 3, 854x480)"
+WORKLOAD = ("e-OSVOS-100-OnA block on synthetic DAVIS-2017-val-shaped 854x480 video: 10 fine-tune iters (batch 3, "
+            "LOVASZ) + 3 inference frames per step, Mask R-CNN R50-GN-FPN random init")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def build_workload(seed):
+    """One synthetic object: first frame + label, pre-augmented fine-tune batches, inference frames (host)."""
+    import random
+    from eosvos_b200.util import augment, synthetic
+    frames, labels = synthetic.make_video(seed, num_frames=1 + FRAMES_PER_STEP, height=H, width=W, num_objects=1)
+    fr = torch.from_numpy(frames).permute(0, 3, 1, 2).float().div(255.0).contiguous()
+    gt0 = torch.from_numpy((labels[0] == 1).astype(np.float32))
+    f0 = fr[0].permute(1, 2, 0).contiguous().numpy()
+    random.seed(seed)
+    batches = []
+    for _ in range(4):      # a small pool of augmented first-frame batches (evaluate.py:224-225)
+        imgs, gts = [], []
+        for _ in range(BATCH):
+            im, g = augment.augment_first_frame(f0, gt0.numpy())
+            imgs.append(torch.from_numpy(np.ascontiguousarray(im.transpose(2, 0, 1))))
+            gts.append(torch.from_numpy(np.ascontiguousarray(g))[None])
+        batches.append((torch.stack(imgs).contiguous(), torch.stack(gts).contiguous()))
+    return fr, gt0, batches
+
+
+def build_model(device):
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200.meta_optim.meta_optim import MetaOptimizer
+    from eosvos_b200.networks.mask_rcnn import MaskRCNN
+    torch.manual_seed(1)
+    model = MaskRCNN('resnet50', num_classes=2,
+                     batch_norm={'accum_stats': False, 'learn_weight': False, 'learn_bias': False},
+                     train_encoder=True, roi_pool_output_sizes={'box': 7, 'mask': 28},
+                     eval_augment_rpn_proposals_mode='EXTEND', replace_batch_with_group_norms=True,
+                     box_nms_thresh=0.5, maskrcnn_loss='LOVASZ')
+    meta_optim = MetaOptimizer(model, init_lr=1e-3, learn_model_init=True, second_order_gradients=False,
+                               lr_hierarchy_level='NEURON', use_log_init_lr=False, max_lr=None)
+    model.to(device)
+    meta_optim.to(device)
+    meta_optim.reset()
+    meta_optim.eval()
+    model.roi_heads.detections_per_img = 1
+    return model, meta_optim
+
+
+def run_block(model, meta_optim, get_batch, get_frame, start_target, step_idx, ev=None, read_back=False):
+    """One step: ITERS_PER_STEP fine-tune iterations + FRAMES_PER_STEP propagated inference frames."""
+    from eosvos_b200.util import evaluate as E
+    if ev is not None:
+        ev[0].record()
+    sink = 0.0
+    meta_optim.reset()          # theta <- theta_0 at the start of the block (evaluate.py:196-199, 'FULL' reset)
+    meta_optim.eval()
+
+    def on_iter(epoch, loss):
+        nonlocal sink
+        if read_back:
+            sink += loss.item()              # evaluate.py:263 train_loss.item()
+
+    E.finetune(model, meta_optim, lambda epoch: get_batch(step_idx * ITERS_PER_STEP + epoch), ITERS_PER_STEP,
+               seed=1, round_idx=1 + step_idx, on_iter=on_iter)
+    if ev is not None:
+        ev[1].record()
+    probs, boxes = E.run_frames(model, (get_frame(i) for i in range(FRAMES_PER_STEP)), start_target)
+    if read_back:
+        sink += float(probs.cpu().sum())     # evaluate.py:302 probs_frame_range.cpu()
+    if ev is not None:
+        ev[2].record()
+    return sink
+
+
+def conv_roofline(device, peaks, peak_kind, reps=20):
+    """Live CUDA-event timing of the dominant kernel: conv_fprop_kernel<256> on the 3x3 256->256 convolution at
+    the P2 level (192x336) at batch 3 -- the FPN output conv and the RPN head conv, forward and (as dgrad) backward."""
+    from eosvos_b200 import kernels as K
+    x = torch.randn(BATCH, 192, 336, 256, device=device).bfloat16()
+    w = (torch.randn(256, 3, 3, 256, device=device) * 0.02).bfloat16()
+    flops = 2.0 * BATCH * 192 * 336 * 256 * 256 * 9
+    for _ in range(3):
+        K.conv2d_fprop(x, w, stride=1, pad=1)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        K.conv2d_fprop(x, w, stride=1, pad=1)
+    e1.record()
+    torch.cuda.synchronize(device)
+    dur = e0.elapsed_time(e1) / reps * 1e-3
+    achieved = flops / dur / 1e12
+    peak = float(peaks["bf16_tflops"]) if "bf16_tflops" in peaks else 1590.0
+    return {"bound": "tensor", "kernel": "conv_fprop_kernel<256,4> 3x3 256->256 @192x336 x3", "achieved": round(achieved, 1),
+            "peak": peak, "peak_kind": f"{peak_kind} burst (kernel timed alone)", "unit": "TFLOP/s",
+            "frac": round(achieved / peak, 4), "flops_per_launch": flops, "us_per_launch": round(dur * 1e6, 1),
+            "traffic": None}
+
+
+def update_roofline(device, meta_optim, model, peaks, peak_kind, reps=20):
+    """HBM roofline of the fused MetaOptimizer update on the real 201-tensor parameter set (528.1 MB / step)."""
+    from eosvos_b200 import kernels as K
+    params = [p.detach() for *_, p in meta_optim.meta_model.param_groups()]
+    grads = [torch.randn_like(p) for p in params]
+    lrs = [l.detach() for l in meta_optim.state["log_lr"]]
+    outs = [torch.empty_like(p) for p in params]
+    plan = K.MetaUpdatePlan(params, grads, lrs, outs)
+    nbytes = 12.0 * sum(p.numel() for p in params) + 4.0 * sum(l.numel() for l in lrs)
+    for _ in range(3):
+        K.meta_update(plan)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        K.meta_update(plan)
+    e1.record()
+    torch.cuda.synchronize(device)
+    dur = e0.elapsed_time(e1) / reps * 1e-3
+    peak = float(peaks["hbm_gbs"])
+    return {"bound": "hbm", "kernel": "meta_update_kernel (201 tensors, 43,975,515 params)",
+            "achieved": round(nbytes / dur / 1e9, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+            "frac": round(nbytes / dur / 1e9 / peak, 4), "bytes_per_launch": nbytes, "us_per_launch": round(dur * 1e6, 1)}
+
+
+def cpu_baseline(sample_iters=1, sample_frames=1):
+    """The reference's CPU path (oracle port of mask_rcnn.py / meta_optim.py, torch CPU fp32) on a bounded sample of
+    the same workload: `sample_iters` fine-tune iterations at batch 3 and `sample_frames` inference frames."""
+    from oracle import model_oracle as MO
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fr, gt0, batches = build_workload(seed=1)
+    model = MO.build_oracle_model(seed=1, maskrcnn_loss="LOVASZ")
+    model.roi_heads.detections_per_img = 1
+    torch.manual_seed(3)
+    opt = MO.OracleMetaOptimizer(model, 1e-3)
+    opt.reset()
+    model.train_without_dropout()
+    t0 = time.perf_counter()
+    for i in range(sample_iters):
+        inputs, gts = batches[i % len(batches)]
+        torch.manual_seed(1 + i)
+        loss, _ = model(inputs, gts)
+        opt.step(loss)
+    t_ft = time.perf_counter() - t0
+    model.eval()
+    t0 = time.perf_counter()
+    MO.run_frames(model, [fr[1 + i] for i in range(sample_frames)], gt0[None, None])
+    t_inf = time.perf_counter() - t0
+    return {"value": sample_iters / t_ft, "unit": UNIT, "cores": cores, "kind": "port",
+            "frames_per_s": sample_frames / t_inf,
+            "sample": f"{sample_iters} fine-tune iteration(s) at batch {BATCH} ({t_ft:.1f} s) + {sample_frames} "
+                      f"inference frame(s) ({t_inf:.1f} s), oracle/model_oracle.py on torch CPU fp32"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # reference arm: the reference's own CPU implementation of the path (oracle port; /root/reference is not
+        # on the GPU box and ships no native code to compile), all host threads, bounded sample per step.
+        vals, fvals = [], []
+        for _ in range(max(args.warmup, 0) and 0):
+            pass
+        t0 = time.perf_counter()
+        n = max(1, min(args.steps, 2))
+        base = None
+        for _ in range(n):
+            base = cpu_baseline(1, 1)
+            vals.append(base["value"])
+            fvals.append(base["frames_per_s"])
+        wall = time.perf_counter() - t0
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": n, "warmup": 0, "ms_per_step": 1e3 * wall / n, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_s": float(np.mean(fvals)),
+                "config": {"workload": WORKLOAD}, "gpu_launches": 0,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": base["cores"], "kind": "port",
+                                 "sample": base["sample"]},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    device = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    from eosvos_b200 import _lib
+    peaks, peak_kind = load_peaks()
+    model, meta_optim = build_model(device)
+    fr, gt0, batches = build_workload(seed=1 + rank)      # every rank fine-tunes on its own object (weak scaling)
+
+    # ---- device-resident inputs (kernel-level `value`)
+    dev_batches = [(a.to(device), b.to(device)) for a, b in batches]
+    dev_frames = [fr[1 + i:2 + i].to(device) for i in range(FRAMES_PER_STEP)]
+    dev_target = gt0[None, None].to(device)
+    # ---- pinned host inputs (`e2e`)
+    pin_batches = [(a.pin_memory(), b.pin_memory()) for a, b in batches]
+    pin_frames = [fr[1 + i:2 + i].pin_memory() for i in range(FRAMES_PER_STEP)]
+
+    def dev_batch(i):
+        return dev_batches[i % len(dev_batches)]
+
+    def dev_frame(i):
+        return dev_frames[i]
+
+    def host_batch(i):
+        a, b = pin_batches[i % len(pin_batches)]
+        return a.to(device, non_blocking=True), b.to(device, non_blocking=True)
+
+    def host_frame(i):
+        return pin_frames[i].to(device, non_blocking=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for s in range(args.warmup):
+        run_block(model, meta_optim, dev_batch, dev_frame, dev_target, s)
+    # ---- timed region 1: device-resident inputs
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        run_block(model, meta_optim, dev_batch, dev_frame, dev_target, args.warmup + s, evs[s])
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ft_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    inf_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
+    total_ms = evs[0][0].elapsed_time(evs[-1][2])
+
+    # ---- timed region 2: end to end from pinned host memory, results read back
+    for s in range(1):
+        run_block(model, meta_optim, host_batch, host_frame, dev_target, 1000 + s, read_back=True)
+    evs2 = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        run_block(model, meta_optim, host_batch, host_frame, dev_target, 2000 + s, evs2[s], read_back=True)
+    barrier()
+    ft2_ms = sum(e[0].elapsed_time(e[1]) for e in evs2)
+    inf2_ms = sum(e[1].elapsed_time(e[2]) for e in evs2)
+
+    times = torch.tensor([ft_ms, inf_ms, total_ms, ft2_ms, inf2_ms], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ft_ms, inf_ms, total_ms, ft2_ms, inf2_ms = times.tolist()
+
+    if rank == 0:
+        n_it = args.steps * ITERS_PER_STEP * world
+        n_fr = args.steps * FRAMES_PER_STEP * world
+        h2d = ITERS_PER_STEP * (batches[0][0].numel() + batches[0][1].numel()) * 4 + FRAMES_PER_STEP * fr[0:1].numel() * 4
+        d2h = ITERS_PER_STEP * 4 + FRAMES_PER_STEP * H * W * 4
+        line = {
+            "metric": METRIC, "value": n_it / (ft_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "frames_per_s": n_fr / (inf_ms * 1e-3),
+            "config": {"workload": WORKLOAD, "iters_per_step": ITERS_PER_STEP, "frames_per_step": FRAMES_PER_STEP,
+                       "batch": BATCH, "l2": "inputs+activations per iteration (>2 GB) exceed the 126 MB L2",
+                       "parallelism": f"objects sharded over {world} GPU(s), no data-path collective"},
+            "e2e": {"value": n_it / (ft2_ms * 1e-3), "unit": UNIT, "frames_per_s": n_fr / (inf2_ms * 1e-3),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "wall_s": wall, "clocks": clocks,
+        }
+        line["roofline"] = conv_roofline(device, peaks, peak_kind)
+        line["roofline_update"] = update_roofline(device, meta_optim, model, peaks, peak_kind)
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(1, 1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@ SIGNATURES = {
     "eosvos_last_error": [],
     "eosvos_version": [],
     "eosvos_device_check": [_I],
+    "eosvos_launch_count": [],
     "eosvos_conv2d_fprop": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "eosvos_conv2d_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "eosvos_conv2d_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -55,7 +56,7 @@ SIGNATURES = {
     "eosvos_relu_bwd": [_P, _P, _P, _L, _P],
     "eosvos_colsum": [_P, _P, _L, _I, _P],
 }
-_RESTYPES = {"eosvos_last_error": c_char_p}
+_RESTYPES = {"eosvos_last_error": c_char_p, "eosvos_launch_count": ctypes.c_ulonglong}
 
 
 class EosvosError(RuntimeError):
@@ -92,6 +93,10 @@ def call(name, *args):
     if rc != 0:
         raise EosvosError(f"{name} failed ({rc}): {last_error()}")
     return rc
+
+
+def launch_count():
+    return int(load().eosvos_launch_count())
 
 
 _checked_devices = set()

@@ -15,7 +15,9 @@ int set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof g_err, "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
   return EOSVOS_ERR_CUDA;
 }
+static unsigned long long g_launches = 0;
 int check_launch(const char* name) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, name);
   return 0;
@@ -34,6 +36,9 @@ int num_sms() {
 }  // namespace eosvos
 
 extern "C" const char* eosvos_last_error(void) { return eosvos::g_err; }
+
+// number of kernel launches issued by this library so far (bench.py's gpu_launches)
+extern "C" unsigned long long eosvos_launch_count(void) { return eosvos::g_launches; }
 
 extern "C" int eosvos_version(void) { return EOSVOS_B200_VERSION; }
 

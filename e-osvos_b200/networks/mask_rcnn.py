@@ -191,10 +191,8 @@ class MaskRCNN(_MaskRCNN):
             size = tr.torch_choice(tr.min_size)      # consumes CPU RNG exactly like torchvision
         else:
             size = tr.min_size[-1]
-        im_shape = torch.tensor([h, w])
-        mn = torch.min(im_shape).to(dtype=torch.float32)
-        mx = torch.max(im_shape).to(dtype=torch.float32)
-        scale = torch.min(torch.tensor(float(size)) / mn, torch.tensor(float(tr.max_size)) / mx).item()
+        # torchvision 0.26 eager path ("the normal way"): plain Python (double) arithmetic
+        scale = min(size / min(h, w), tr.max_size / max(h, w))
         import math
         return int(math.floor(float(h) * scale)), int(math.floor(float(w) * scale))
 

@@ -1,0 +1,36 @@
+"""First-frame augmentation used while fine-tuning (host side, as in the reference):
+RandomHorizontalFlip + RandomScaleNRotate(rots=(-30,30), scales=(.75,1.25)) -- reference
+src/data/custom_transforms.py:9-89,188-211, composed in src/util/helper_func.py:254-263."""
+import random
+
+import cv2
+import numpy as np
+
+
+def random_flip(image, gt):
+    if random.random() < 0.5:
+        image, gt = cv2.flip(image, flipCode=1), cv2.flip(gt, flipCode=1)
+    return image, gt
+
+
+def _warp(a, rot, sc, label):
+    h, w = a.shape[:2]
+    M = cv2.getRotationMatrix2D((w / 2, h / 2), rot, sc)
+    return cv2.warpAffine(a, M, (w, h), flags=cv2.INTER_NEAREST if label else cv2.INTER_CUBIC)
+
+
+def random_scale_rotate(image, gt, rots=(-30, 30), scales=(.75, 1.25)):
+    num_labels = len(np.unique(gt))
+    while True:
+        rot = (rots[1] - rots[0]) * random.random() - (rots[1] - rots[0]) / 2
+        sc = (scales[1] - scales[0]) * random.random() - (scales[1] - scales[0]) / 2 + 1
+        aug_gt = _warp(gt, rot, sc, True)
+        if not num_labels > 1 or len(np.unique(aug_gt)) == num_labels:
+            break
+    return _warp(image, rot, sc, False), aug_gt
+
+
+def augment_first_frame(image_hwc, gt_hw):
+    """image float32 [H,W,3] in [0,1], gt float32 [H,W] -> augmented copies (same dtypes)."""
+    image, gt = random_flip(image_hwc, gt_hw)
+    return random_scale_rotate(image, gt)

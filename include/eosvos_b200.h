@@ -31,6 +31,7 @@ typedef void* eosvos_stream_t;
 const char* eosvos_last_error(void);
 int eosvos_version(void);
 int eosvos_device_check(int device);
+unsigned long long eosvos_launch_count(void);
 
 /* ---- K1: dense contractions on tcgen05 (reference: cuDNN conv / ATen addmm reached from
  *      src/networks/mask_rcnn.py:716 forward and src/meta_optim/meta_optim.py:202-204 backward) */
