@@ -167,8 +167,8 @@ def conv_roofline(device, peaks, peak_kind, reps=20):
     """Live CUDA-event timing of the dominant kernel: conv_fprop_kernel<256> on the 3x3 256->256 convolution at
     the P2 level (192x336) at batch 3 -- the FPN output conv and the RPN head conv, forward and (as dgrad) backward."""
     from eosvos_b200 import kernels as K
-    x = torch.randn(BATCH, 192, 336, 256, device=device).bfloat16()
-    w = (torch.randn(256, 3, 3, 256, device=device) * 0.02).bfloat16()
+    x = torch.randn(BATCH, 192, 336, 256, device=device).to(K.ACT_DTYPE)
+    w = (torch.randn(256, 3, 3, 256, device=device) * 0.02).to(K.ACT_DTYPE)
     flops = 2.0 * BATCH * 192 * 336 * 256 * 256 * 9
     for _ in range(3):
         K.conv2d_fprop(x, w, stride=1, pad=1)
@@ -291,7 +291,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
 
-    from eosvos_b200 import _lib
+    from eosvos_b200 import _lib, kernels
+    ACT_NAME = "f16" if kernels.ACT_DTYPE == torch.float16 else "bf16"
     peaks, peak_kind = load_peaks()
     model, meta_optim = build_model(device)
     fr, gt0, batches = build_workload(seed=1 + rank)      # every rank fine-tunes on its own object (weak scaling)
@@ -366,7 +367,7 @@ def main():
         line = {
             "metric": METRIC, "value": n_it / (ft_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": ACT_NAME, "data": "synthetic",
             "frames_per_s": n_fr / (inf_ms * 1e-3),
             "config": {"workload": WORKLOAD, "iters_per_step": ITERS_PER_STEP, "frames_per_step": FRAMES_PER_STEP,
                        "batch": BATCH, "l2": "inputs+activations per iteration (>2 GB) exceed the 126 MB L2",

@@ -25,16 +25,17 @@ SIGNATURES = {
     "eosvos_version": [],
     "eosvos_device_check": [_I],
     "eosvos_launch_count": [],
+    "eosvos_act_dtype": [],
     "eosvos_conv2d_fprop": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "eosvos_conv2d_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "eosvos_conv2d_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "eosvos_gemm_wgrad": [_P, _P, _P, _L, _I, _I, _L, _I, _L, _L, _I, _I, _P],
+    "eosvos_conv2d_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P],
+    "eosvos_gemm_wgrad": [_P, _P, _P, _L, _I, _I, _L, _I, _L, _L, _F, _I, _I, _P],
     "eosvos_deconv2x2_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "eosvos_deconv2x2_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "eosvos_deconv2x2_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "eosvos_deconv2x2_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "eosvos_gn_stats": [_P, _P, _I, _I, _I, _P],
     "eosvos_gn_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
-    "eosvos_gn_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
+    "eosvos_gn_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _F, _P],
     "eosvos_roi_align_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "eosvos_roi_align_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "eosvos_mask_targets": [_P, _P, _P, _I, _I, _I, _I, _P],
@@ -54,7 +55,7 @@ SIGNATURES = {
     "eosvos_subsample2": [_P, _P, _I, _I, _I, _I, _I, _P],
     "eosvos_sum2x2": [_P, _P, _I, _I, _I, _I, _P],
     "eosvos_relu_bwd": [_P, _P, _P, _L, _P],
-    "eosvos_colsum": [_P, _P, _L, _I, _P],
+    "eosvos_colsum": [_P, _P, _L, _I, _F, _P],
 }
 _RESTYPES = {"eosvos_last_error": c_char_p, "eosvos_launch_count": ctypes.c_ulonglong}
 

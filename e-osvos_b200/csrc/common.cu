@@ -2,6 +2,8 @@
 #include "common.h"
 #include "../../include/eosvos_b200.h"
 #include <string.h>
+#include <cuda.h>
+#include "act.cuh"
 
 namespace eosvos {
 
@@ -39,6 +41,9 @@ extern "C" const char* eosvos_last_error(void) { return eosvos::g_err; }
 
 // number of kernel launches issued by this library so far (bench.py's gpu_launches)
 extern "C" unsigned long long eosvos_launch_count(void) { return eosvos::g_launches; }
+
+// 0 = bfloat16, 1 = float16: storage type of activations / tensor-core operands in this build
+extern "C" int eosvos_act_dtype(void) { return EOSVOS_ACT_CODE; }
 
 extern "C" int eosvos_version(void) { return EOSVOS_B200_VERSION; }
 

@@ -14,7 +14,7 @@
 #include "../../include/eosvos_b200.h"
 
 namespace eosvos {
-int make_tensor_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+int make_tensor_map_act(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estride);
 int launch_fprop(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, int m_tiles,
                  cudaStream_t stream);
@@ -127,18 +127,18 @@ static int run_fprop(const AView& av, const int extent[4], const int conv_stride
   p.out_fp32 = ep.out_fp32;
   p.n_valid = n_valid;
   p.ogroup = ep.ogroup;
-  p.res = reinterpret_cast<const __nv_bfloat16*>(ep.res);
+  p.res = reinterpret_cast<const act_t*>(ep.res);
   p.gn_sum = ep.gn_sum;
   p.gn_cpg = ep.gn_cpg;
   p.gn_dim = ep.gn_dim;
   if (ep.ogroup) EOSVOS_REQUIRE(ep.ogroup % bn == 0, "fprop: output group must be a multiple of the column tile");
 
   CUtensorMap tmA, tmB;
-  EOSVOS_TRY(make_tensor_map_bf16(&tmA, av.base, 5, av.dims, av.strides, box, av.estride));
+  EOSVOS_TRY(make_tensor_map_act(&tmA, av.base, 5, av.dims, av.strides, box, av.estride));
   const uint64_t bdims[2] = {b_k, b_rows};
   const uint64_t bstr[1] = {b_k * 2};
   const uint32_t bbox[2] = {64, (uint32_t)bn};
-  EOSVOS_TRY(make_tensor_map_bf16(&tmB, b_base, 2, bdims, bstr, bbox, nullptr));
+  EOSVOS_TRY(make_tensor_map_act(&tmB, b_base, 2, bdims, bstr, bbox, nullptr));
   return launch_fprop(bn, tmA, tmB, p, (int)m_tiles, stream);
 }
 
@@ -370,7 +370,7 @@ namespace eosvos {
 static int run_wgrad(const AView& a_view, const AView& b_view, const int extent[4], const int b_stride[4], int sp_w,
                      int sp_h, int num_taps, const int (*tda)[5], const int (*tdb)[5], int m_valid, int n_valid,
                      float* dw, long long s_m, long long s_tap, int n_inner, long long s_n_inner,
-                     long long s_n_outer, int bn_hint, int split_hint, cudaStream_t stream) {
+                     long long s_n_outer, float alpha, int bn_hint, int split_hint, cudaStream_t stream) {
   WgradParams p;
   memset(&p, 0, sizeof p);
   int tw = 1, th = 1;
@@ -419,16 +419,17 @@ static int run_wgrad(const AView& a_view, const AView& b_view, const int extent[
   p.n_inner = n_inner > 0 ? n_inner : 0x7fffffff;
   p.n_inner_stride = s_n_inner;
   p.n_outer_stride = s_n_outer;
+  p.alpha = alpha;
   CUtensorMap tmA, tmB;
-  EOSVOS_TRY(make_tensor_map_bf16(&tmA, a_view.base, 5, a_view.dims, a_view.strides, boxa, a_view.estride));
-  EOSVOS_TRY(make_tensor_map_bf16(&tmB, b_view.base, 5, b_view.dims, b_view.strides, boxb, b_view.estride));
+  EOSVOS_TRY(make_tensor_map_act(&tmA, a_view.base, 5, a_view.dims, a_view.strides, boxa, a_view.estride));
+  EOSVOS_TRY(make_tensor_map_act(&tmB, b_view.base, 5, b_view.dims, b_view.strides, boxb, b_view.estride));
   dim3 grid((unsigned)split, (unsigned)(m_tiles * p.n_tiles_n), (unsigned)num_taps);
   return launch_wgrad(bn, tmA, tmB, p, grid, stream);
 }
 }  // namespace eosvos
 
 extern "C" int eosvos_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
-                                   int KH, int KW, int stride, int pad, int bn_hint, int split_hint,
+                                   int KH, int KW, int stride, int pad, float alpha, int bn_hint, int split_hint,
                                    eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EOSVOS_REQUIRE(x && dy && dw, "conv2d_wgrad: null pointer");
@@ -453,7 +454,7 @@ extern "C" int eosvos_conv2d_wgrad(const void* x, const void* dy, float* dw, int
     AView b = nhwc_view(x, 1, 1, (int)M, Cin, 1);
     const int ext[4] = {(int)M, 1, 1, 1};
     const int bs[4] = {1, 1, 1, 1};
-    return run_wgrad(a, b, ext, bs, 0, -1, 1, tda, tdb, Cout, Cin, dw, (long long)Cin, 0, 0, 1, 0, bn_hint,
+    return run_wgrad(a, b, ext, bs, 0, -1, 1, tda, tdb, Cout, Cin, dw, (long long)Cin, 0, 0, 1, 0, alpha, bn_hint,
                      split_hint, stream);
   }
   AView a = nhwc_view(dy, N, Ho, Wo, Cout, 1);
@@ -461,7 +462,7 @@ extern "C" int eosvos_conv2d_wgrad(const void* x, const void* dy, float* dw, int
   const int ext[4] = {Wo, Ho, N, 1};
   const int bs[4] = {stride, stride, 1, 1};
   return run_wgrad(a, b, ext, bs, 0, 1, nt, tda, tdb, Cout, Cin, dw, (long long)T * Cin, 1, 0, (long long)T, 0,
-                   bn_hint, split_hint, stream);
+                   alpha, bn_hint, split_hint, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -553,7 +554,7 @@ extern "C" int eosvos_deconv2x2_dgrad(const void* dy, const void* wdt, void* dx,
 }
 
 extern "C" int eosvos_deconv2x2_wgrad(const void* x, const void* dy, float* dw, int N, int h, int w, int Cin, int Cout,
-                                      int bn_hint, int split_hint, eosvos_stream_t stream_) {
+                                      float alpha, int bn_hint, int split_hint, eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EOSVOS_REQUIRE(x && dy && dw, "deconv2x2_wgrad: null pointer");
   EOSVOS_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "deconv2x2_wgrad: bad channel counts");
@@ -580,16 +581,16 @@ extern "C" int eosvos_deconv2x2_wgrad(const void* x, const void* dy, float* dw, 
   const int ext[4] = {w, 1, h, N};
   const int bs[4] = {1, 1, 1, 1};
   // torch ConvTranspose2d layout dw[ci][co][dy][dx]
-  return run_wgrad(a, b, ext, bs, 0, 2, 4, tda, tdb, Cout, Cin, dw, 4LL, 1, 0, 4LL * Cout, 0, bn_hint, split_hint,
-                   stream);
+  return run_wgrad(a, b, ext, bs, 0, 2, 4, tda, tdb, Cout, Cin, dw, 4LL, 1, 0, 4LL * Cout, 0, alpha, bn_hint,
+                   split_hint, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
 // flat weight gradient with a caller-defined destination layout (Linear, fc6, stem im2col).
 // ---------------------------------------------------------------------------------------------
 extern "C" int eosvos_gemm_wgrad(const void* x, const void* dy, float* dw, long long rows, int n_cols, int m_cols,
-                                 long long s_m, int n_inner, long long s_n_inner, long long s_n_outer, int bn_hint,
-                                 int split_hint, eosvos_stream_t stream_) {
+                                 long long s_m, int n_inner, long long s_n_inner, long long s_n_outer, float alpha,
+                                 int bn_hint, int split_hint, eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EOSVOS_REQUIRE(x && dy && dw, "gemm_wgrad: null pointer");
   EOSVOS_REQUIRE(n_cols % 8 == 0 && m_cols % 8 == 0, "gemm_wgrad: column counts must be multiples of 8");
@@ -600,5 +601,5 @@ extern "C" int eosvos_gemm_wgrad(const void* x, const void* dy, float* dw, long 
   const int ext[4] = {(int)rows, 1, 1, 1};
   const int bs[4] = {1, 1, 1, 1};
   return run_wgrad(a, b, ext, bs, 0, -1, 1, tda, tdb, m_cols, n_cols, dw, s_m, 0, n_inner, s_n_inner, s_n_outer,
-                   bn_hint, split_hint, stream);
+                   alpha, bn_hint, split_hint, stream);
 }

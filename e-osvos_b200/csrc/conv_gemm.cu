@@ -81,7 +81,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_act(128, BN, 0, 0);
       for (int it = 0; it < num_it; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -93,7 +93,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int k = 0; k < 4; ++k) {
           const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
           const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)((it | k) != 0));
+          umma_f16kind(tmem_base, ad, bd, idesc, (uint32_t)((it | k) != 0));
         }
         umma_commit(&empty[s]);
       }
@@ -179,15 +179,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (valid) {
         if (p.res) {
-          const __nv_bfloat16* rp = p.res + roff + col0;
+          const act_t* rp = p.res + roff + col0;
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             if (col0 + j8 * 8 < p.n_valid) {
               const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j8 * 8));
-              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+              const act2_t* rh = reinterpret_cast<const act2_t*>(&rv);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const float2 rf = __bfloat1622float2(rh[k]);
+                const float2 rf = act22float2(rh[k]);
                 f[j8 * 8 + 2 * k] += rf.x;
                 f[j8 * 8 + 2 * k + 1] += rf.y;
               }
@@ -207,15 +207,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
           }
         } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
+          act_t* op = reinterpret_cast<act_t*>(p.out) + o;
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             if (col0 + j8 * 8 < p.n_valid) {
               uint4 w;
-              w.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-              w.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-              w.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-              w.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+              w.x = pack_act2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+              w.y = pack_act2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+              w.z = pack_act2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+              w.w = pack_act2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
               *reinterpret_cast<uint4*>(op + j8 * 8) = w;
             }
           }
@@ -324,7 +324,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+        constexpr uint32_t idesc = make_idesc_act(128, BN, 1, 1);
         const int ksteps = p.kpad >> 4;
         for (int it = 0; it < num_it; ++it) {
           const int s = it % STAGES;
@@ -336,7 +336,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t ad = make_smem_desc_sw128(a_addr + k * 2048, SLOT, 1024);
             const uint64_t bd = make_smem_desc_sw128(b_addr + k * 2048, SLOT, 1024);
-            umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)((it | k) != 0));
+            umma_f16kind(tmem_base, ad, bd, idesc, (uint32_t)((it | k) != 0));
           }
           umma_commit(&empty[s]);
         }
@@ -360,7 +360,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (n < p.n_valid) {
               const int no = n / p.n_inner;
               atomicAdd(dst + (long long)no * p.n_outer_stride + (long long)(n - no * p.n_inner) * p.n_inner_stride,
-                        __uint_as_float(v[j]));
+                        __uint_as_float(v[j]) * p.alpha);
             }
           }
         }
@@ -395,7 +395,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // dims/box/estride are given innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
-int make_tensor_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+int make_tensor_map_act(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estride) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(EOSVOS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -407,7 +407,7 @@ int make_tensor_map_bf16(CUtensorMap* m, const void* base, int rank, const uint6
     es[i] = estride ? estride[i] : 1;
   }
   for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = fn(m, EOSVOS_TMA_DTYPE, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -1,7 +1,7 @@
 // Device-side parameter blocks for the two tcgen05 implicit-GEMM kernels (conv_gemm.cu).
 #pragma once
 #include <stdint.h>
-#include <cuda_bf16.h>
+#include "act.cuh"
 
 namespace eosvos {
 
@@ -26,7 +26,7 @@ struct FpropParams {
   int odim[4];
   int ogroup;                     // 0, or columns per output group (deconv sub-pixel groups)
   long long ogroup_off[4];
-  const __nv_bfloat16* res;       // optional residual: out = act(acc + bias + res[(coord >> rshift) . rstride + col])
+  const act_t* res;       // optional residual: out = act(acc + bias + res[(coord >> rshift) . rstride + col])
   long long rstride[4];
   int rshift[4];
   float* gn_sum;                  // optional GroupNorm partial statistics: [gn_n][32][2] fp32 (sum, sumsq)
@@ -52,6 +52,7 @@ struct WgradParams {
   long long dw_m_stride, dw_tap_stride;
   int n_inner;
   long long n_inner_stride, n_outer_stride;
+  float alpha;   // every accumulated value is multiplied by alpha (1 / loss-scale of the fp16 backward)
 };
 
 }  // namespace eosvos

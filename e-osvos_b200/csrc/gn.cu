@@ -7,35 +7,35 @@
 // + 1 write).  Backward = one reduction pass + one apply pass.
 #include "common.h"
 #include "../../include/eosvos_b200.h"
-#include <cuda_bf16.h>
+#include "act.cuh"
 
 namespace eosvos {
 
 constexpr int GN_GROUPS = 32;
 constexpr int GN_THREADS = 256;
 
-__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+__device__ __forceinline__ void load8(const act_t* p, float (&f)[8]) {
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const act2_t* h = reinterpret_cast<const act2_t*>(&v);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float2 t = __bfloat1622float2(h[k]);
+    const float2 t = act22float2(h[k]);
     f[2 * k] = t.x;
     f[2 * k + 1] = t.y;
   }
 }
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+__device__ __forceinline__ void store8(act_t* p, const float (&f)[8]) {
   uint4 v;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+  act2_t* h = reinterpret_cast<act2_t*>(&v);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  for (int k = 0; k < 4; ++k) h[k] = floats2act2(f[2 * k], f[2 * k + 1]);
   *reinterpret_cast<uint4*>(p) = v;
 }
 
 // ---------------------------------------------------------------------------------------------
 // statistics: sums[n][g] = (sum x, sum x^2).  grid = (chunks, N); C/8 must divide GN_THREADS.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums,
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const act_t* __restrict__ x, float* __restrict__ sums,
                                                              int HW, int C, int chunk_pixels) {
   __shared__ float sm[GN_GROUPS * 2];
   const int n = blockIdx.y;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat1
   float s1[8], s2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
-  const __nv_bfloat16* base = x + (size_t)n * HW * C + (size_t)my_cv * 8;
+  const act_t* base = x + (size_t)n * HW * C + (size_t)my_cv * 8;
   for (int p = p0 + threadIdx.x / cv; p < p1; p += pix_per_pass) {
     float f[8];
     load8(base + (size_t)p * C, f);
@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat1
 // apply: y = relu?( (x - mean) * rstd * gamma + beta  (+ res) )
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GN_THREADS)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
-                const float* __restrict__ beta, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y,
+gn_apply_kernel(const act_t* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const act_t* __restrict__ res, act_t* __restrict__ y,
                 int HW, int C, int chunk_pixels, float eps, int relu) {
   const int n = blockIdx.y;
   const int cv = C >> 3;
@@ -137,9 +137,9 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
 //   mask_mode 0: dy_eff = dy;  1: dy_eff = dy * (xhat*gamma+beta > 0);  2: dy_eff = dy * (yout > 0)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GN_THREADS)
-gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sums,
+gn_bwd_reduce_kernel(const act_t* __restrict__ x, const float* __restrict__ sums,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yout,
+                     const act_t* __restrict__ dy, const act_t* __restrict__ yout,
                      float* __restrict__ part, int HW, int C, int chunk_pixels, float eps, int mask_mode) {
   extern __shared__ float smp[];  // [C][2]
   const int n = blockIdx.y;
@@ -194,10 +194,10 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
 
 // backward pass 2: dx = rstd * (gamma*dy_eff - (A_g + xhat*B_g)/m);  optional d_res = dy_eff
 __global__ void __launch_bounds__(GN_THREADS)
-gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sums,
+gn_bwd_apply_kernel(const act_t* __restrict__ x, const float* __restrict__ sums,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yout,
-                    const float* __restrict__ part, __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
+                    const act_t* __restrict__ dy, const act_t* __restrict__ yout,
+                    const float* __restrict__ part, act_t* __restrict__ dx, act_t* __restrict__ dres,
                     int HW, int C, int chunk_pixels, float eps, int mask_mode) {
   __shared__ float gA[GN_GROUPS], gB[GN_GROUPS];
   const int n = blockIdx.y;
@@ -254,7 +254,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 
 // dgamma[c] = sum_n part[n][c][1], dbeta[c] = sum_n part[n][c][0]
 __global__ void gn_bwd_param_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int N, int C) {
+                                    float* __restrict__ dbeta, int N, int C, float alpha) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a = 0.f, b = 0.f;
@@ -262,8 +262,8 @@ __global__ void gn_bwd_param_kernel(const float* __restrict__ part, float* __res
     b += part[((size_t)n * C + c) * 2];
     a += part[((size_t)n * C + c) * 2 + 1];
   }
-  dgamma[c] = a;
-  dbeta[c] = b;
+  dgamma[c] = a * alpha;
+  dbeta[c] = b * alpha;
 }
 
 static int gn_chunk(int HW, int N, int C, int* chunks) {
@@ -295,7 +295,7 @@ extern "C" int eosvos_gn_stats(const void* x, float* sums, int N, int HW, int C,
   if (e != cudaSuccess) return set_cuda_error(e, "gn_stats memset");
   int chunks;
   const int chunk = gn_chunk(HW, N, C, &chunks);
-  gn_stats_kernel<<<dim3(chunks, N), GN_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), sums, HW, C,
+  gn_stats_kernel<<<dim3(chunks, N), GN_THREADS, 0, stream>>>(reinterpret_cast<const act_t*>(x), sums, HW, C,
                                                               chunk);
   return check_launch("gn_stats_kernel");
 }
@@ -307,15 +307,15 @@ extern "C" int eosvos_gn_apply(const void* x, const float* sums, const float* ga
   int chunks;
   const int chunk = gn_chunk(HW, N, C, &chunks);
   gn_apply_kernel<<<dim3(chunks, N), GN_THREADS, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), sums, gamma, beta, reinterpret_cast<const __nv_bfloat16*>(res),
-      reinterpret_cast<__nv_bfloat16*>(y), HW, C, chunk, eps, relu);
+      reinterpret_cast<const act_t*>(x), sums, gamma, beta, reinterpret_cast<const act_t*>(res),
+      reinterpret_cast<act_t*>(y), HW, C, chunk, eps, relu);
   return check_launch("gn_apply_kernel");
 }
 
 // part: scratch [N][C][2] fp32 (zeroed here).  mask_mode: 0 none, 1 recompute ReLU mask, 2 mask from yout.
 extern "C" int eosvos_gn_backward(const void* x, const float* sums, const float* gamma, const float* beta,
                                   const void* dy, const void* yout, float* part, void* dx, void* dres, float* dgamma,
-                                  float* dbeta, int N, int HW, int C, float eps, int mask_mode,
+                                  float* dbeta, int N, int HW, int C, float eps, int mask_mode, float alpha,
                                   eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EOSVOS_TRY(gn_check(N, HW, C));
@@ -324,17 +324,17 @@ extern "C" int eosvos_gn_backward(const void* x, const float* sums, const float*
   if (e != cudaSuccess) return set_cuda_error(e, "gn_backward memset");
   int chunks;
   const int chunk = gn_chunk(HW, N, C, &chunks);
-  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
-  const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
-  const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(yout);
+  const act_t* xb = reinterpret_cast<const act_t*>(x);
+  const act_t* dyb = reinterpret_cast<const act_t*>(dy);
+  const act_t* yb = reinterpret_cast<const act_t*>(yout);
   gn_bwd_reduce_kernel<<<dim3(chunks, N), GN_THREADS, (size_t)C * 2 * sizeof(float), stream>>>(
       xb, sums, gamma, beta, dyb, yb, part, HW, C, chunk, eps, mask_mode);
   EOSVOS_TRY(check_launch("gn_bwd_reduce_kernel"));
   gn_bwd_apply_kernel<<<dim3(chunks, N), GN_THREADS, 0, stream>>>(xb, sums, gamma, beta, dyb, yb, part,
-                                                                  reinterpret_cast<__nv_bfloat16*>(dx),
-                                                                  reinterpret_cast<__nv_bfloat16*>(dres), HW, C, chunk,
+                                                                  reinterpret_cast<act_t*>(dx),
+                                                                  reinterpret_cast<act_t*>(dres), HW, C, chunk,
                                                                   eps, mask_mode);
   EOSVOS_TRY(check_launch("gn_bwd_apply_kernel"));
-  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, dgamma, dbeta, N, C);
+  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, dgamma, dbeta, N, C, alpha);
   return check_launch("gn_bwd_param_kernel");
 }

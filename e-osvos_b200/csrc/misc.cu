@@ -5,25 +5,25 @@
 //   max-pool  : torchvision ResNet stem (3x3 / s2 / p1) and FPN LastLevelMaxPool (1x1 / s2)
 #include "common.h"
 #include "../../include/eosvos_b200.h"
-#include <cuda_bf16.h>
+#include "act.cuh"
 
 namespace eosvos {
 
-__device__ __forceinline__ void ld8f(const __nv_bfloat16* p, float (&f)[8]) {
+__device__ __forceinline__ void ld8f(const act_t* p, float (&f)[8]) {
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const act2_t* h = reinterpret_cast<const act2_t*>(&v);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float2 t = __bfloat1622float2(h[k]);
+    const float2 t = act22float2(h[k]);
     f[2 * k] = t.x;
     f[2 * k + 1] = t.y;
   }
 }
-__device__ __forceinline__ void st8f(__nv_bfloat16* p, const float (&f)[8]) {
+__device__ __forceinline__ void st8f(act_t* p, const float (&f)[8]) {
   uint4 v;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+  act2_t* h = reinterpret_cast<act2_t*>(&v);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  for (int k = 0; k < 4; ++k) h[k] = floats2act2(f[2 * k], f[2 * k + 1]);
   *reinterpret_cast<uint4*>(p) = v;
 }
 
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) permute_cast_kernel(const TS* __restrict_
 // scale = in/out), zero-padded NHWC bf16 with Cs stored channels (3 used).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-transform_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int h, int w, int oh, int ow,
+transform_kernel(const float* __restrict__ img, act_t* __restrict__ out, int B, int h, int w, int oh, int ow,
                  int Hp, int Wp, int Cs, float m0, float m1, float m2, float is0, float is1, float is2) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * Hp * Wp;
@@ -84,8 +84,8 @@ transform_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
       v[c] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
     }
   }
-  __nv_bfloat16* o = out + (size_t)idx * Cs;
-  for (int c = 0; c < Cs; ++c) o[c] = __float2bfloat16(c < 3 ? v[c] : 0.f);
+  act_t* o = out + (size_t)idx * Cs;
+  for (int c = 0; c < Cs; ++c) o[c] = float2act(c < 3 ? v[c] : 0.f);
 }
 
 // nearest resize of id masks (legacy 'nearest': src = floor(dst * in/out)), fp32 -> uint8, padded
@@ -105,7 +105,7 @@ mask_resize_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, i
 // stem im2col: x [N,H,W,Cs] bf16 (3 used) -> col [N*Ho*Wo][Kp] bf16, k = (kh*KW + kw)*3 + c
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-im2col_stem_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W, int Cs,
+im2col_stem_kernel(const act_t* __restrict__ x, act_t* __restrict__ col, int N, int H, int W, int Cs,
                    int Ho, int Wo, int KH, int KW, int stride, int pad, int Kp) {
   const int kv = Kp >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,11 +116,11 @@ im2col_stem_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   const int wo = (int)(row % Wo);
   const int ho = (int)((row / Wo) % Ho);
   const int n = (int)(row / ((long long)Wo * Ho));
-  __align__(16) __nv_bfloat16 vals[8];
+  __align__(16) act_t vals[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = k8 * 8 + j;
-    __nv_bfloat16 v = __float2bfloat16(0.f);
+    act_t v = float2act(0.f);
     if (k < KH * KW * 3) {
       const int c = k % 3;
       const int t = k / 3;
@@ -138,7 +138,7 @@ im2col_stem_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 // in window scan order, as ATen) so no index tensor is stored.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, int C,
+maxpool_fwd_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, int N, int H, int W, int C,
                    int Ho, int Wo, int ksz, int stride, int pad) {
   const int cv = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,8 +168,8 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 
 // dx[hi,wi] = sum over windows containing (hi,wi) whose first arg-max is (hi,wi) of dy[window]
 __global__ void __launch_bounds__(256)
-maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
-                   const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C,
+maxpool_bwd_kernel(const act_t* __restrict__ x, const act_t* __restrict__ y,
+                   const act_t* __restrict__ dy, act_t* __restrict__ dx, int N, int H, int W, int C,
                    int Ho, int Wo, int ksz, int stride, int pad) {
   const int cv = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,7 +217,7 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 
 // FPN LastLevelMaxPool (kernel 1, stride 2) forward and backward
 __global__ void __launch_bounds__(256)
-subsample2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, int Ho,
+subsample2_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, int N, int H, int W, int C, int Ho,
                   int Wo, int backward) {
   const int cv = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,7 +242,7 @@ subsample2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
 
 // backward of nearest 2x upsampling: dcoarse[h,w] = sum of the 2x2 fine gradients
 __global__ void __launch_bounds__(256)
-sum2x2_kernel(const __nv_bfloat16* __restrict__ dfine, __nv_bfloat16* __restrict__ dcoarse, int N, int Hc, int Wc, int C) {
+sum2x2_kernel(const act_t* __restrict__ dfine, act_t* __restrict__ dcoarse, int N, int Hc, int Wc, int C) {
   const int cv = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * Hc * Wc * cv) return;
@@ -267,7 +267,7 @@ sum2x2_kernel(const __nv_bfloat16* __restrict__ dfine, __nv_bfloat16* __restrict
 
 // dy_eff = dy * (y > 0)   (fused conv+bias+ReLU backward entry)
 __global__ void __launch_bounds__(256)
-relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out,
+relu_bwd_kernel(const act_t* __restrict__ dy, const act_t* __restrict__ y, act_t* __restrict__ out,
                 long long nvec) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec) return;
@@ -281,7 +281,8 @@ relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __res
 
 // bias gradient: out[c] += sum_rows dy[row][c]; dy bf16 [M][C]
 __global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ out, long long M, int C, int rows_per_block) {
+colsum_kernel(const act_t* __restrict__ dy, float* __restrict__ out, long long M, int C, int rows_per_block,
+              float alpha) {
   extern __shared__ float sm[];  // [C]
   const int cv = C >> 3;
   const int my_cv = threadIdx.x % cv;
@@ -304,7 +305,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ out, lon
     for (int k = 0; k < 8; ++k) atomicAdd(&sm[my_cv * 8 + k], acc[k]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(&out[i], sm[i]);
+  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(&out[i], sm[i] * alpha);
 }
 
 static inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
@@ -313,7 +314,7 @@ static inline unsigned blocks_for(long long total) { return (unsigned)((total + 
 
 using namespace eosvos;
 
-// dtype codes: 0 = fp32, 1 = bf16
+// dtype codes: 0 = fp32, 1 = activation type (act_t)
 extern "C" int eosvos_permute_cast(const void* src, void* dst, const long long* dims, const long long* sstride,
                                    const long long* dstride, int src_dtype, int dst_dtype, eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -329,17 +330,17 @@ extern "C" int eosvos_permute_cast(const void* src, void* dst, const long long* 
   if (total == 0) return 0;
   const unsigned nb = blocks_for(total);
   if (src_dtype == 0 && dst_dtype == 1)
-    permute_cast_kernel<float, __nv_bfloat16><<<nb, 256, 0, stream>>>(reinterpret_cast<const float*>(src),
-                                                                     reinterpret_cast<__nv_bfloat16*>(dst), pm, total);
+    permute_cast_kernel<float, act_t><<<nb, 256, 0, stream>>>(reinterpret_cast<const float*>(src),
+                                                                     reinterpret_cast<act_t*>(dst), pm, total);
   else if (src_dtype == 1 && dst_dtype == 0)
-    permute_cast_kernel<__nv_bfloat16, float><<<nb, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src),
+    permute_cast_kernel<act_t, float><<<nb, 256, 0, stream>>>(reinterpret_cast<const act_t*>(src),
                                                                      reinterpret_cast<float*>(dst), pm, total);
   else if (src_dtype == 0 && dst_dtype == 0)
     permute_cast_kernel<float, float><<<nb, 256, 0, stream>>>(reinterpret_cast<const float*>(src),
                                                              reinterpret_cast<float*>(dst), pm, total);
   else if (src_dtype == 1 && dst_dtype == 1)
-    permute_cast_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), pm, total);
+    permute_cast_kernel<act_t, act_t><<<nb, 256, 0, stream>>>(
+        reinterpret_cast<const act_t*>(src), reinterpret_cast<act_t*>(dst), pm, total);
   else
     return set_error(EOSVOS_ERR_ARG, "permute_cast: unknown dtype code");
   return check_launch("permute_cast_kernel");
@@ -351,7 +352,7 @@ extern "C" int eosvos_transform(const float* img, void* out, int B, int h, int w
   EOSVOS_REQUIRE(img && out && mean3 && std3, "transform: null pointer");
   EOSVOS_REQUIRE(Cs >= 3 && oh <= Hp && ow <= Wp, "transform: bad geometry");
   const long long total = (long long)B * Hp * Wp;
-  transform_kernel<<<blocks_for(total), 256, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, h, w, oh, ow, Hp,
+  transform_kernel<<<blocks_for(total), 256, 0, stream>>>(img, reinterpret_cast<act_t*>(out), B, h, w, oh, ow, Hp,
                                                         Wp, Cs, mean3[0], mean3[1], mean3[2], 1.f / std3[0],
                                                         1.f / std3[1], 1.f / std3[2]);
   return check_launch("transform_kernel");
@@ -373,8 +374,8 @@ extern "C" int eosvos_im2col_stem(const void* x, void* col, int N, int H, int W,
   EOSVOS_REQUIRE(Kp % 64 == 0 && Kp >= KH * KW * 3, "im2col_stem: Kp must be a multiple of 64 covering KH*KW*3");
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   const long long total = (long long)N * Ho * Wo * (Kp >> 3);
-  im2col_stem_kernel<<<blocks_for(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                          reinterpret_cast<__nv_bfloat16*>(col), N, H, W, Cs, Ho, Wo, KH,
+  im2col_stem_kernel<<<blocks_for(total), 256, 0, stream>>>(reinterpret_cast<const act_t*>(x),
+                                                          reinterpret_cast<act_t*>(col), N, H, W, Cs, Ho, Wo, KH,
                                                           KW, stride, pad, Kp);
   return check_launch("im2col_stem_kernel");
 }
@@ -385,7 +386,7 @@ extern "C" int eosvos_maxpool_fwd(const void* x, void* y, int N, int H, int W, i
   EOSVOS_REQUIRE(x && y && C % 8 == 0, "maxpool_fwd: bad arguments");
   const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
   maxpool_fwd_kernel<<<blocks_for((long long)N * Ho * Wo * (C >> 3)), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), N, H, W, C, Ho, Wo, ksz, stride,
+      reinterpret_cast<const act_t*>(x), reinterpret_cast<act_t*>(y), N, H, W, C, Ho, Wo, ksz, stride,
       pad);
   return check_launch("maxpool_fwd_kernel");
 }
@@ -396,8 +397,8 @@ extern "C" int eosvos_maxpool_bwd(const void* x, const void* y, const void* dy, 
   EOSVOS_REQUIRE(x && y && dy && dx && C % 8 == 0, "maxpool_bwd: bad arguments");
   const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
   maxpool_bwd_kernel<<<blocks_for((long long)N * H * W * (C >> 3)), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(y),
-      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<__nv_bfloat16*>(dx), N, H, W, C, Ho, Wo, ksz, stride,
+      reinterpret_cast<const act_t*>(x), reinterpret_cast<const act_t*>(y),
+      reinterpret_cast<const act_t*>(dy), reinterpret_cast<act_t*>(dx), N, H, W, C, Ho, Wo, ksz, stride,
       pad);
   return check_launch("maxpool_bwd_kernel");
 }
@@ -408,8 +409,8 @@ extern "C" int eosvos_subsample2(const void* x, void* y, int N, int H, int W, in
   EOSVOS_REQUIRE(x && y && C % 8 == 0, "subsample2: bad arguments");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = backward ? (long long)N * H * W * (C >> 3) : (long long)N * Ho * Wo * (C >> 3);
-  subsample2_kernel<<<blocks_for(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                         reinterpret_cast<__nv_bfloat16*>(y), N, H, W, C, Ho, Wo,
+  subsample2_kernel<<<blocks_for(total), 256, 0, stream>>>(reinterpret_cast<const act_t*>(x),
+                                                         reinterpret_cast<act_t*>(y), N, H, W, C, Ho, Wo,
                                                          backward);
   return check_launch("subsample2_kernel");
 }
@@ -418,7 +419,7 @@ extern "C" int eosvos_sum2x2(const void* dfine, void* dcoarse, int N, int Hc, in
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EOSVOS_REQUIRE(dfine && dcoarse && C % 8 == 0, "sum2x2: bad arguments");
   sum2x2_kernel<<<blocks_for((long long)N * Hc * Wc * (C >> 3)), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dfine), reinterpret_cast<__nv_bfloat16*>(dcoarse), N, Hc, Wc, C);
+      reinterpret_cast<const act_t*>(dfine), reinterpret_cast<act_t*>(dcoarse), N, Hc, Wc, C);
   return check_launch("sum2x2_kernel");
 }
 
@@ -426,14 +427,14 @@ extern "C" int eosvos_relu_bwd(const void* dy, const void* y, void* out, long lo
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (numel == 0) return 0;
   EOSVOS_REQUIRE(dy && y && out && numel % 8 == 0, "relu_bwd: numel must be a multiple of 8");
-  relu_bwd_kernel<<<blocks_for(numel / 8), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
-                                                           reinterpret_cast<const __nv_bfloat16*>(y),
-                                                           reinterpret_cast<__nv_bfloat16*>(out), numel / 8);
+  relu_bwd_kernel<<<blocks_for(numel / 8), 256, 0, stream>>>(reinterpret_cast<const act_t*>(dy),
+                                                           reinterpret_cast<const act_t*>(y),
+                                                           reinterpret_cast<act_t*>(out), numel / 8);
   return check_launch("relu_bwd_kernel");
 }
 
 // out[c] (fp32, ACCUMULATED: caller zeroes) += column sums of dy [M][C] bf16
-extern "C" int eosvos_colsum(const void* dy, float* out, long long M, int C, eosvos_stream_t stream_) {
+extern "C" int eosvos_colsum(const void* dy, float* out, long long M, int C, float alpha, eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M == 0) return 0;
   EOSVOS_REQUIRE(dy && out, "colsum: null pointer");
@@ -443,7 +444,7 @@ extern "C" int eosvos_colsum(const void* dy, float* out, long long M, int C, eos
   long long rows_per_block = (M + want_blocks - 1) / want_blocks;
   rows_per_block = ((rows_per_block + rpp - 1) / rpp) * rpp;
   const unsigned nb = (unsigned)((M + rows_per_block - 1) / rows_per_block);
-  colsum_kernel<<<nb, 256, C * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), out, M, C,
-                                                        (int)rows_per_block);
+  colsum_kernel<<<nb, 256, C * sizeof(float), stream>>>(reinterpret_cast<const act_t*>(dy), out, M, C,
+                                                        (int)rows_per_block, alpha);
   return check_launch("colsum_kernel");
 }

@@ -6,7 +6,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include "act.cuh"
 #include <stdint.h>
 
 namespace eosvos {
@@ -106,12 +106,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
 // Instruction descriptor for kind::f16, BF16 x BF16 -> FP32.
 //   [4,6) D fmt (1 = f32) | [7,10) A fmt (1 = bf16) | [10,13) B fmt | [15] A major | [16] B major
 //   [17,23) N >> 3 | [24,29) M >> 4.   major: 0 = K-major, 1 = MN-major.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+__host__ __device__ constexpr uint32_t make_idesc_act(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (EOSVOS_MMA_FMT << 7) | (EOSVOS_MMA_FMT << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16kind(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -141,8 +141,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ uint32_t pack_act2(float a, float b) {
+  act2_t h = floats2act2(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 

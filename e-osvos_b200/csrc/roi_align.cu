@@ -7,12 +7,12 @@
 // clamped to [2,5]  (SURVEY.md App. B).
 #include "common.h"
 #include "../../include/eosvos_b200.h"
-#include <cuda_bf16.h>
+#include "act.cuh"
 
 namespace eosvos {
 
 struct RoiLevels {
-  const __nv_bfloat16* feat[4];
+  const act_t* feat[4];
   float* dfeat[4];
   int H[4], W[4];
   float scale[4];
@@ -60,12 +60,12 @@ __device__ __forceinline__ Bilin bilin_setup(float y, float x, int H, int W) {
   return b;
 }
 
-__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
+__device__ __forceinline__ void ld8(const act_t* p, float (&f)[8]) {
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const act2_t* h = reinterpret_cast<const act2_t*>(&v);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float2 t = __bfloat1622float2(h[k]);
+    const float2 t = act22float2(h[k]);
     f[2 * k] = t.x;
     f[2 * k + 1] = t.y;
   }
@@ -74,8 +74,8 @@ __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
 // one thread = one (roi, ph, pw, 8-channel vector); rois: [R][5] = (batch, x1, y1, x2, y2)
 template <bool BWD>
 __global__ void __launch_bounds__(256)
-roi_align_kernel(const RoiLevels lv, const float* __restrict__ rois, __nv_bfloat16* __restrict__ out,
-                 const __nv_bfloat16* __restrict__ dout, int R, int P, int C, int sampling) {
+roi_align_kernel(const RoiLevels lv, const float* __restrict__ rois, act_t* __restrict__ out,
+                 const act_t* __restrict__ dout, int R, int P, int C, int sampling) {
   const int cv = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)R * P * P * cv;
@@ -126,7 +126,7 @@ roi_align_kernel(const RoiLevels lv, const float* __restrict__ rois, __nv_bfloat
           atomicAdd(d + o11 + k, g[k] * bl.w11);
         }
       } else {
-        const __nv_bfloat16* f = lv.feat[l];
+        const act_t* f = lv.feat[l];
         float v00[8], v01[8], v10[8], v11[8];
         ld8(f + o00, v00);
         ld8(f + o01, v01);
@@ -140,9 +140,9 @@ roi_align_kernel(const RoiLevels lv, const float* __restrict__ rois, __nv_bfloat
   }
   if (!BWD) {
     uint4 v;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+    act2_t* h = reinterpret_cast<act2_t*>(&v);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(acc[2 * k] * inv_count, acc[2 * k + 1] * inv_count);
+    for (int k = 0; k < 4; ++k) h[k] = floats2act2(acc[2 * k] * inv_count, acc[2 * k + 1] * inv_count);
     *reinterpret_cast<uint4*>(out + (size_t)idx * 8) = v;
   }
 }
@@ -185,7 +185,7 @@ using namespace eosvos;
 static int fill_levels(RoiLevels* lv, const void* const* feats, float* const* dfeats, const int* Hs, const int* Ws,
                        const float* scales) {
   for (int l = 0; l < 4; ++l) {
-    lv->feat[l] = feats ? reinterpret_cast<const __nv_bfloat16*>(feats[l]) : nullptr;
+    lv->feat[l] = feats ? reinterpret_cast<const act_t*>(feats[l]) : nullptr;
     lv->dfeat[l] = dfeats ? dfeats[l] : nullptr;
     lv->H[l] = Hs[l];
     lv->W[l] = Ws[l];
@@ -205,7 +205,7 @@ extern "C" int eosvos_roi_align_fwd(const void* const* feats, const int* Hs, con
   fill_levels(&lv, feats, nullptr, Hs, Ws, scales);
   const long long total = (long long)R * P * P * (C >> 3);
   roi_align_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-      lv, rois, reinterpret_cast<__nv_bfloat16*>(out), nullptr, R, P, C, sampling);
+      lv, rois, reinterpret_cast<act_t*>(out), nullptr, R, P, C, sampling);
   return check_launch("roi_align_kernel<fwd>");
 }
 
@@ -221,7 +221,7 @@ extern "C" int eosvos_roi_align_bwd(float* const* dfeats, const int* Hs, const i
   fill_levels(&lv, nullptr, dfeats, Hs, Ws, scales);
   const long long total = (long long)R * P * P * (C >> 3);
   roi_align_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-      lv, rois, nullptr, reinterpret_cast<const __nv_bfloat16*>(dout), R, P, C, sampling);
+      lv, rois, nullptr, reinterpret_cast<const act_t*>(dout), R, P, C, sampling);
   return check_launch("roi_align_kernel<bwd>");
 }
 

@@ -1,6 +1,7 @@
 """Tensor-level wrappers over the C ABI (no autograd here; see ops.py).
 
-PyTorch supplies device memory and streams only.  Activations are [N, H, W, C] bf16 contiguous,
+PyTorch supplies device memory and streams only.  Activations are [N, H, W, C] ACT_DTYPE (fp16 in the
+default build, bf16 with -DEOSVOS_ACT_BF16) contiguous,
 parameters fp32 in the reference's (torch) layouts.
 """
 import ctypes
@@ -11,6 +12,8 @@ from . import _lib
 from ._lib import FLAG_OUT_FP32, FLAG_RELU, FLAG_RES_HALF, call
 
 GN_EPS = 1e-5
+# storage type of activations / tensor-core operands, fixed when the library was built
+ACT_DTYPE = torch.float16 if _lib.load().eosvos_act_dtype() == 1 else getattr(torch, "bfloat16")
 
 
 def _stream():
@@ -38,20 +41,20 @@ def _chk(t, dtype=None, name="tensor"):
 def conv2d_fprop(x, w, bias=None, res=None, *, stride=1, pad=0, relu=False, out_fp32=False, res_half=False,
                  gn_sum=None, bn_hint=0, out=None):
     """x [N,H,W,Cin] bf16, w [Cout,KH,KW,Cin] bf16 -> y [N,Ho,Wo,Cout]."""
-    _chk(x, torch.bfloat16, "x")
-    _chk(w, torch.bfloat16, "w")
+    _chk(x, ACT_DTYPE, "x")
+    _chk(w, ACT_DTYPE, "w")
     N, H, W, Cin = x.shape
     Cout, KH, KW, Cin2 = w.shape
     assert Cin == Cin2, (x.shape, w.shape)
     Ho = (H + 2 * pad - KH) // stride + 1
     Wo = (W + 2 * pad - KW) // stride + 1
     if out is None:
-        out = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        out = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32 if out_fp32 else ACT_DTYPE)
     flags = (FLAG_RELU if relu else 0) | (FLAG_OUT_FP32 if out_fp32 else 0) | (FLAG_RES_HALF if res_half else 0)
     if bias is not None:
         _chk(bias, torch.float32, "bias")
     if res is not None:
-        _chk(res, torch.bfloat16, "res")
+        _chk(res, ACT_DTYPE, "res")
     if gn_sum is not None:
         _chk(gn_sum, torch.float32, "gn_sum")
     call("eosvos_conv2d_fprop", _ptr(x), _ptr(w), _ptr(bias), _ptr(res), _ptr(out), _ptr(gn_sum), N, H, W, Cin, Cout,
@@ -61,53 +64,53 @@ def conv2d_fprop(x, w, bias=None, res=None, *, stride=1, pad=0, relu=False, out_
 
 def conv2d_dgrad(dy, wt, in_hw, *, stride=1, pad=0, out_fp32=False, bn_hint=0):
     """dy [N,Ho,Wo,Cout] bf16, wt [Cin,KH,KW,Cout] bf16 -> dx [N,H,W,Cin]."""
-    _chk(dy, torch.bfloat16, "dy")
-    _chk(wt, torch.bfloat16, "wt")
+    _chk(dy, ACT_DTYPE, "dy")
+    _chk(wt, ACT_DTYPE, "wt")
     N, Ho, Wo, Cout = dy.shape
     Cin, KH, KW, Cout2 = wt.shape
     assert Cout == Cout2
     H, W = in_hw
     assert (H + 2 * pad - KH) // stride + 1 == Ho and (W + 2 * pad - KW) // stride + 1 == Wo
-    dx = torch.empty((N, H, W, Cin), device=dy.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    dx = torch.empty((N, H, W, Cin), device=dy.device, dtype=torch.float32 if out_fp32 else ACT_DTYPE)
     call("eosvos_conv2d_dgrad", _ptr(dy), _ptr(wt), _ptr(dx), N, H, W, Cin, Cout, KH, KW, stride, pad,
          FLAG_OUT_FP32 if out_fp32 else 0, bn_hint, _stream())
     return dx
 
 
-def conv2d_wgrad(x, dy, ksize, *, stride=1, pad=0, bn_hint=0, split_hint=0, out=None):
+def conv2d_wgrad(x, dy, ksize, *, stride=1, pad=0, alpha=1.0, bn_hint=0, split_hint=0, out=None):
     """x [N,H,W,Cin], dy [N,Ho,Wo,Cout] bf16 -> dw fp32 [Cout,Cin,KH,KW] (torch layout)."""
-    _chk(x, torch.bfloat16, "x")
-    _chk(dy, torch.bfloat16, "dy")
+    _chk(x, ACT_DTYPE, "x")
+    _chk(dy, ACT_DTYPE, "dy")
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     KH, KW = ksize
     if out is None:
         out = torch.zeros((Cout, Cin, KH, KW), device=x.device, dtype=torch.float32)
-    call("eosvos_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(out), N, H, W, Cin, Cout, KH, KW, stride, pad, bn_hint,
+    call("eosvos_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(out), N, H, W, Cin, Cout, KH, KW, stride, pad, alpha, bn_hint,
          split_hint, _stream())
     return out
 
 
-def gemm_wgrad(x, dy, out, *, s_m, n_inner=0, s_n_inner=1, s_n_outer=0, bn_hint=0, split_hint=0):
+def gemm_wgrad(x, dy, out, *, s_m, n_inner=0, s_n_inner=1, s_n_outer=0, alpha=1.0, bn_hint=0, split_hint=0):
     """out[m*s_m + (n//n_inner)*s_n_outer + (n%n_inner)*s_n_inner] += sum_r dy[r,m] * x[r,n]."""
-    _chk(x, torch.bfloat16, "x")
-    _chk(dy, torch.bfloat16, "dy")
+    _chk(x, ACT_DTYPE, "x")
+    _chk(dy, ACT_DTYPE, "dy")
     _chk(out, torch.float32, "out")
     rows, n_cols = x.shape
     rows2, m_cols = dy.shape
     assert rows == rows2
     call("eosvos_gemm_wgrad", _ptr(x), _ptr(dy), _ptr(out), rows, n_cols, m_cols, s_m, n_inner, s_n_inner, s_n_outer,
-         bn_hint, split_hint, _stream())
+         alpha, bn_hint, split_hint, _stream())
     return out
 
 
 def deconv2x2_fprop(x, wd, bias4=None, *, relu=False, bn_hint=0):
     """x [N,h,w,Cin] bf16, wd [4*Cout, Cin] bf16 ((dy,dx,co) rows) -> y [N,2h,2w,Cout] bf16."""
-    _chk(x, torch.bfloat16, "x")
-    _chk(wd, torch.bfloat16, "wd")
+    _chk(x, ACT_DTYPE, "x")
+    _chk(wd, ACT_DTYPE, "wd")
     N, h, w, Cin = x.shape
     Cout = wd.shape[0] // 4
-    y = torch.empty((N, 2 * h, 2 * w, Cout), device=x.device, dtype=torch.bfloat16)
+    y = torch.empty((N, 2 * h, 2 * w, Cout), device=x.device, dtype=ACT_DTYPE)
     call("eosvos_deconv2x2_fprop", _ptr(x), _ptr(wd), _ptr(bias4), _ptr(y), N, h, w, Cin, Cout,
          FLAG_RELU if relu else 0, bn_hint, _stream())
     return y
@@ -115,30 +118,30 @@ def deconv2x2_fprop(x, wd, bias4=None, *, relu=False, bn_hint=0):
 
 def deconv2x2_dgrad(dy, wdt, *, bn_hint=0):
     """dy [N,2h,2w,Cout] bf16, wdt [Cin, 4*Cout] bf16 -> dx [N,h,w,Cin] bf16."""
-    _chk(dy, torch.bfloat16, "dy")
-    _chk(wdt, torch.bfloat16, "wdt")
+    _chk(dy, ACT_DTYPE, "dy")
+    _chk(wdt, ACT_DTYPE, "wdt")
     N, H2, W2, Cout = dy.shape
     Cin = wdt.shape[0]
-    dx = torch.empty((N, H2 // 2, W2 // 2, Cin), device=dy.device, dtype=torch.bfloat16)
+    dx = torch.empty((N, H2 // 2, W2 // 2, Cin), device=dy.device, dtype=ACT_DTYPE)
     call("eosvos_deconv2x2_dgrad", _ptr(dy), _ptr(wdt), _ptr(dx), N, H2 // 2, W2 // 2, Cin, Cout, 0, bn_hint,
          _stream())
     return dx
 
 
-def deconv2x2_wgrad(x, dy, *, bn_hint=0, split_hint=0):
+def deconv2x2_wgrad(x, dy, *, alpha=1.0, bn_hint=0, split_hint=0):
     """-> dw fp32 [Cin, Cout, 2, 2] (torch ConvTranspose2d layout)."""
-    _chk(x, torch.bfloat16, "x")
-    _chk(dy, torch.bfloat16, "dy")
+    _chk(x, ACT_DTYPE, "x")
+    _chk(dy, ACT_DTYPE, "dy")
     N, h, w, Cin = x.shape
     Cout = dy.shape[-1]
     dw = torch.zeros((Cin, Cout, 2, 2), device=x.device, dtype=torch.float32)
-    call("eosvos_deconv2x2_wgrad", _ptr(x), _ptr(dy), _ptr(dw), N, h, w, Cin, Cout, bn_hint, split_hint, _stream())
+    call("eosvos_deconv2x2_wgrad", _ptr(x), _ptr(dy), _ptr(dw), N, h, w, Cin, Cout, alpha, bn_hint, split_hint, _stream())
     return dw
 
 
 # ------------------------------------------------------------------------------------------- K2
 def gn_stats(x):
-    _chk(x, torch.bfloat16, "x")
+    _chk(x, ACT_DTYPE, "x")
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
     sums = torch.empty((N, 32, 2), device=x.device, dtype=torch.float32)
@@ -147,7 +150,7 @@ def gn_stats(x):
 
 
 def gn_apply(x, sums, gamma, beta, res=None, relu=False, eps=GN_EPS):
-    _chk(x, torch.bfloat16, "x")
+    _chk(x, ACT_DTYPE, "x")
     _chk(sums, torch.float32, "sums")
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
@@ -157,9 +160,9 @@ def gn_apply(x, sums, gamma, beta, res=None, relu=False, eps=GN_EPS):
     return y
 
 
-def gn_backward(x, sums, gamma, beta, dy, yout=None, mask_mode=0, want_dres=False, eps=GN_EPS):
-    _chk(x, torch.bfloat16, "x")
-    _chk(dy, torch.bfloat16, "dy")
+def gn_backward(x, sums, gamma, beta, dy, yout=None, mask_mode=0, want_dres=False, eps=GN_EPS, alpha=1.0):
+    _chk(x, ACT_DTYPE, "x")
+    _chk(dy, ACT_DTYPE, "dy")
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
     part = torch.empty((N, C, 2), device=x.device, dtype=torch.float32)
@@ -168,7 +171,7 @@ def gn_backward(x, sums, gamma, beta, dy, yout=None, mask_mode=0, want_dres=Fals
     dgamma = torch.empty((C,), device=x.device, dtype=torch.float32)
     dbeta = torch.empty((C,), device=x.device, dtype=torch.float32)
     call("eosvos_gn_backward", _ptr(x), _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(yout), _ptr(part),
-         _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), N, HW, C, eps, mask_mode, _stream())
+         _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), N, HW, C, eps, mask_mode, alpha, _stream())
     return dx, dres, dgamma, dbeta
 
 
@@ -185,20 +188,20 @@ def roi_align_fwd(feats, scales, rois, P, sampling=2):
     ptrs, Hs, Ws = _level_args(feats)
     sc = (ctypes.c_float * 4)(*[float(s) for s in scales])
     for i, f in enumerate(feats):
-        _chk(f, torch.bfloat16, "feature level")
+        _chk(f, ACT_DTYPE, "feature level")
         ptrs[i] = f.data_ptr()
         Hs[i], Ws[i] = f.shape[1], f.shape[2]
     C = feats[0].shape[-1]
     _chk(rois, torch.float32, "rois")
     R = rois.shape[0]
-    out = torch.empty((R, P, P, C), device=rois.device, dtype=torch.bfloat16)
+    out = torch.empty((R, P, P, C), device=rois.device, dtype=ACT_DTYPE)
     call("eosvos_roi_align_fwd", ptrs, Hs, Ws, sc, _ptr(rois), _ptr(out), R, P, C, sampling, _stream())
     return out
 
 
 def roi_align_bwd(dout, level_shapes, scales, rois, P, sampling=2):
     """-> list of 4 fp32 NHWC gradient maps (zero-initialised here, atomically accumulated)."""
-    _chk(dout, torch.bfloat16, "dout")
+    _chk(dout, ACT_DTYPE, "dout")
     _chk(rois, torch.float32, "rois")
     ptrs, Hs, Ws = _level_args(level_shapes)
     sc = (ctypes.c_float * 4)(*[float(s) for s in scales])
@@ -311,7 +314,7 @@ def radam_step(p, g, m, v, *, gscale, clip, beta1, beta2, eps, lr, wd, step_size
 
 
 # ------------------------------------------------------------------------------------------- misc
-_DT = {torch.float32: 0, torch.bfloat16: 1}
+_DT = {torch.float32: 0, ACT_DTYPE: 1}
 
 
 def permute_cast(src, dst, dims, sstride, dstride):
@@ -327,7 +330,7 @@ def nchw_to_nhwc_bf16(x):
     """fp32/bf16 [N,C,H,W] -> bf16 [N,H,W,C]."""
     N, C, H, W = x.shape
     x = x.contiguous()
-    out = torch.empty((N, H, W, C), device=x.device, dtype=torch.bfloat16)
+    out = torch.empty((N, H, W, C), device=x.device, dtype=ACT_DTYPE)
     return permute_cast(x, out, (N, H, W, C), (C * H * W, W, 1, H * W), (H * W * C, W * C, C, 1))
 
 
@@ -342,7 +345,7 @@ def nhwc_to_nchw_fp32(x):
 def transform(img, oh, ow, Hp, Wp, mean, std, Cs=8):
     _chk(img, torch.float32, "image")
     B, _, h, w = img.shape
-    out = torch.empty((B, Hp, Wp, Cs), device=img.device, dtype=torch.bfloat16)
+    out = torch.empty((B, Hp, Wp, Cs), device=img.device, dtype=ACT_DTYPE)
     m = (ctypes.c_float * 3)(*mean)
     s = (ctypes.c_float * 3)(*std)
     call("eosvos_transform", _ptr(img), _ptr(out), B, h, w, oh, ow, Hp, Wp, Cs, m, s, _stream())
@@ -358,21 +361,21 @@ def mask_resize_nearest(masks_u8, oh, ow):
 
 
 def im2col_stem(x, KH=7, KW=7, stride=2, pad=3, Kp=192):
-    _chk(x, torch.bfloat16, "x")
+    _chk(x, ACT_DTYPE, "x")
     N, H, W, Cs = x.shape
     Ho = (H + 2 * pad - KH) // stride + 1
     Wo = (W + 2 * pad - KW) // stride + 1
-    col = torch.empty((N * Ho * Wo, Kp), device=x.device, dtype=torch.bfloat16)
+    col = torch.empty((N * Ho * Wo, Kp), device=x.device, dtype=ACT_DTYPE)
     call("eosvos_im2col_stem", _ptr(x), _ptr(col), N, H, W, Cs, KH, KW, stride, pad, Kp, _stream())
     return col, Ho, Wo
 
 
 def maxpool_fwd(x, ksz=3, stride=2, pad=1):
-    _chk(x, torch.bfloat16, "x")
+    _chk(x, ACT_DTYPE, "x")
     N, H, W, C = x.shape
     Ho = (H + 2 * pad - ksz) // stride + 1
     Wo = (W + 2 * pad - ksz) // stride + 1
-    y = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.bfloat16)
+    y = torch.empty((N, Ho, Wo, C), device=x.device, dtype=ACT_DTYPE)
     call("eosvos_maxpool_fwd", _ptr(x), _ptr(y), N, H, W, C, ksz, stride, pad, _stream())
     return y
 
@@ -380,47 +383,47 @@ def maxpool_fwd(x, ksz=3, stride=2, pad=1):
 def maxpool_bwd(x, y, dy, ksz=3, stride=2, pad=1):
     N, H, W, C = x.shape
     dx = torch.empty_like(x)
-    call("eosvos_maxpool_bwd", _ptr(x), _ptr(y), _ptr(_chk(dy, torch.bfloat16)), _ptr(dx), N, H, W, C, ksz, stride,
+    call("eosvos_maxpool_bwd", _ptr(x), _ptr(y), _ptr(_chk(dy, ACT_DTYPE)), _ptr(dx), N, H, W, C, ksz, stride,
          pad, _stream())
     return dx
 
 
 def subsample2(x):
-    _chk(x, torch.bfloat16, "x")
+    _chk(x, ACT_DTYPE, "x")
     N, H, W, C = x.shape
-    y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), device=x.device, dtype=torch.bfloat16)
+    y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), device=x.device, dtype=ACT_DTYPE)
     call("eosvos_subsample2", _ptr(x), _ptr(y), N, H, W, C, 0, _stream())
     return y
 
 
 def subsample2_bwd(dy, in_shape):
-    _chk(dy, torch.bfloat16, "dy")
+    _chk(dy, ACT_DTYPE, "dy")
     N, H, W, C = in_shape
-    dx = torch.empty(in_shape, device=dy.device, dtype=torch.bfloat16)
+    dx = torch.empty(in_shape, device=dy.device, dtype=ACT_DTYPE)
     call("eosvos_subsample2", _ptr(dy), _ptr(dx), N, H, W, C, 1, _stream())
     return dx
 
 
 def sum2x2(dfine):
-    _chk(dfine, torch.bfloat16, "dfine")
+    _chk(dfine, ACT_DTYPE, "dfine")
     N, Hf, Wf, C = dfine.shape
-    out = torch.empty((N, Hf // 2, Wf // 2, C), device=dfine.device, dtype=torch.bfloat16)
+    out = torch.empty((N, Hf // 2, Wf // 2, C), device=dfine.device, dtype=ACT_DTYPE)
     call("eosvos_sum2x2", _ptr(dfine), _ptr(out), N, Hf // 2, Wf // 2, C, _stream())
     return out
 
 
 def relu_bwd(dy, y):
-    _chk(dy, torch.bfloat16, "dy")
-    _chk(y, torch.bfloat16, "y")
+    _chk(dy, ACT_DTYPE, "dy")
+    _chk(y, ACT_DTYPE, "y")
     out = torch.empty_like(dy)
     call("eosvos_relu_bwd", _ptr(dy), _ptr(y), _ptr(out), dy.numel(), _stream())
     return out
 
 
-def colsum(dy2d, out=None):
-    _chk(dy2d, torch.bfloat16, "dy")
+def colsum(dy2d, out=None, alpha=1.0):
+    _chk(dy2d, ACT_DTYPE, "dy")
     M, C = dy2d.shape
     if out is None:
         out = torch.zeros((C,), device=dy2d.device, dtype=torch.float32)
-    call("eosvos_colsum", _ptr(dy2d), _ptr(out), M, C, _stream())
+    call("eosvos_colsum", _ptr(dy2d), _ptr(out), M, C, alpha, _stream())
     return out

@@ -15,6 +15,16 @@ from torch.autograd.function import once_differentiable
 
 from . import kernels as K
 
+ACT = K.ACT_DTYPE
+# Static loss scale of the 16-bit backward pass.  fp32 loss gradients enter the 16-bit domain only in
+# HeadFn.backward (all three fp32 heads), where they are multiplied by GRAD_SCALE; every kernel that emits a
+# parameter gradient multiplies by 1/GRAD_SCALE (`alpha`), so autograd sees exact-scale fp32 gradients.
+GRAD_SCALE = 1024.0 if ACT == torch.float16 else 1.0
+
+
+def _inv_scale():
+    return 1.0 / GRAD_SCALE
+
 # --------------------------------------------------------------------------------------------
 # parameter -> tensor-core operand layouts (bf16), cached per live parameter tensor
 # --------------------------------------------------------------------------------------------
@@ -45,7 +55,7 @@ def clear_prep_cache():
     _prep_cache.clear()
 
 
-def _permute_to(src, shape, dims, sstride, dtype=torch.bfloat16):
+def _permute_to(src, shape, dims, sstride, dtype=ACT):
     out = torch.empty(shape, device=src.device, dtype=dtype)
     dstride = [1, 1, 1, 1]
     for i in (2, 1, 0):
@@ -120,10 +130,10 @@ def _fused_head_w(ws, pad_to):
         return hit[0], hit[1]
     flat = torch.cat([w.detach().reshape(w.shape[0], -1) for w in ws], 0)
     O, Kd = flat.shape
-    wf = torch.zeros((pad_to, 1, 1, Kd), device=flat.device, dtype=torch.bfloat16)
-    wf.view(pad_to, Kd)[:O] = flat.to(torch.bfloat16)
-    wt = torch.zeros((Kd, 1, 1, 64), device=flat.device, dtype=torch.bfloat16)
-    wt.view(Kd, 64)[:, :O] = flat.t().to(torch.bfloat16)
+    wf = torch.zeros((pad_to, 1, 1, Kd), device=flat.device, dtype=ACT)
+    wf.view(pad_to, Kd)[:O] = flat.to(ACT)
+    wt = torch.zeros((Kd, 1, 1, 64), device=flat.device, dtype=ACT)
+    wt.view(Kd, 64)[:, :O] = flat.t().to(ACT)
     _cache_put(ws[0], kind, (wf, wt, [(weakref.ref(w), w._version) for w in ws[1:]]))
     return wf, wt
 
@@ -157,9 +167,9 @@ class Conv2dFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = K.conv2d_dgrad(dy, prep_conv_wt(w), x.shape[1:3], stride=stride, pad=pad)
         if ctx.needs_input_grad[1]:
-            dw = K.conv2d_wgrad(x, dy, w.shape[2:], stride=stride, pad=pad)
+            dw = K.conv2d_wgrad(x, dy, w.shape[2:], stride=stride, pad=pad, alpha=_inv_scale())
         if has_bias and ctx.needs_input_grad[2]:
-            db = K.colsum(dy.view(-1, dy.shape[-1]))
+            db = K.colsum(dy.view(-1, dy.shape[-1]), alpha=_inv_scale())
         if has_res and ctx.needs_input_grad[3]:
             dres = K.sum2x2(dy) if res_half else dy
         return dx, dw, db, dres, None, None, None, None
@@ -193,12 +203,12 @@ class ConvGnFn(torch.autograd.Function):
         stride, pad, mode, has_res = ctx.cfg
         dy = dy.contiguous()
         dz, dres, dgamma, dbeta = K.gn_backward(z, sums, gamma.detach(), beta.detach(), dy, yout=y, mask_mode=mode,
-                                                want_dres=has_res and ctx.needs_input_grad[4])
+                                                want_dres=has_res and ctx.needs_input_grad[4], alpha=_inv_scale())
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = K.conv2d_dgrad(dz, prep_conv_wt(w), x.shape[1:3], stride=stride, pad=pad)
         if ctx.needs_input_grad[1]:
-            dw = K.conv2d_wgrad(x, dz, w.shape[2:], stride=stride, pad=pad)
+            dw = K.conv2d_wgrad(x, dz, w.shape[2:], stride=stride, pad=pad, alpha=_inv_scale())
         return dx, dw, dgamma, dbeta, dres, None, None, None
 
 
@@ -217,7 +227,7 @@ def _prep_stem_w(w):
     O, I, KH, KW = wd.shape
     T = KH * KW
     Kp = ((T * I + 63) // 64) * 64
-    out = torch.zeros((O, 1, 1, Kp), device=wd.device, dtype=torch.bfloat16)
+    out = torch.zeros((O, 1, 1, Kp), device=wd.device, dtype=ACT)
     # dst[o][t*I + c] = src[o][c][t]
     K.permute_cast(wd, out, (1, O, T, I), (0, I * T, 1, T), (0, Kp, I, 1))
     return _cache_put(w, "stem", out)
@@ -242,13 +252,14 @@ class StemFn(torch.autograd.Function):
     def backward(ctx, dy):
         col, w, gamma, beta, z, sums = ctx.saved_tensors
         O, I, KH, KW = w.shape
-        dz, _, dgamma, dbeta = K.gn_backward(z, sums, gamma.detach(), beta.detach(), dy.contiguous(), mask_mode=1)
+        dz, _, dgamma, dbeta = K.gn_backward(z, sums, gamma.detach(), beta.detach(), dy.contiguous(), mask_mode=1,
+                                             alpha=_inv_scale())
         dw = None
         if ctx.needs_input_grad[1]:
             dw = torch.zeros_like(w, dtype=torch.float32)
             T = KH * KW
             # column n = t*I + c  ->  torch offset c*T + t
-            K.gemm_wgrad(col, dz.view(-1, O), dw, s_m=I * T, n_inner=I, s_n_inner=T, s_n_outer=1)
+            K.gemm_wgrad(col, dz.view(-1, O), dw, s_m=I * T, n_inner=I, s_n_inner=T, s_n_outer=1, alpha=_inv_scale())
         return None, dw, dgamma, dbeta
 
 
@@ -320,11 +331,11 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.zeros((O, Kd), device=x.device, dtype=torch.float32)
             if inner:
-                K.gemm_wgrad(x, dy, dw, s_m=Kd, n_inner=inner, s_n_inner=Kd // inner, s_n_outer=1)
+                K.gemm_wgrad(x, dy, dw, s_m=Kd, n_inner=inner, s_n_inner=Kd // inner, s_n_outer=1, alpha=_inv_scale())
             else:
-                K.gemm_wgrad(x, dy, dw, s_m=Kd)
+                K.gemm_wgrad(x, dy, dw, s_m=Kd, alpha=_inv_scale())
         if has_bias and ctx.needs_input_grad[2]:
-            db = K.colsum(dy)
+            db = K.colsum(dy, alpha=_inv_scale())
         return dx, dw, db, None, None
 
 
@@ -361,14 +372,14 @@ class HeadFn(torch.autograd.Function):
         ws = ctx.saved_tensors[1:]
         n = ctx.n
         rows, Kd = x.shape
-        dyp = torch.zeros((rows, 64), device=x.device, dtype=torch.bfloat16)
-        dyp[:, :16] = dy
+        dyp = torch.zeros((rows, 64), device=x.device, dtype=ACT)
+        dyp[:, :16] = dy * GRAD_SCALE        # fp32 -> 16-bit domain: apply the loss scale here
         _, wt = _fused_head_w(ws, 16)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.conv2d_dgrad(dyp.view(1, 1, rows, 64), wt, (1, rows)).view(rows, Kd)
         dwf = torch.zeros((64, Kd), device=x.device, dtype=torch.float32)
-        K.gemm_wgrad(x, dyp, dwf, s_m=Kd)
+        K.gemm_wgrad(x, dyp, dwf, s_m=Kd, alpha=_inv_scale())
         dbf = dy.sum(0)
         dws, dbs = [], []
         o = 0
@@ -420,9 +431,9 @@ class Deconv2x2Fn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = K.deconv2x2_dgrad(dy, _prep_deconv(w)[1])
         if ctx.needs_input_grad[1]:
-            dw = K.deconv2x2_wgrad(x, dy)
+            dw = K.deconv2x2_wgrad(x, dy, alpha=_inv_scale())
         if has_bias and ctx.needs_input_grad[2]:
-            db = K.colsum(dy.view(-1, dy.shape[-1]))
+            db = K.colsum(dy.view(-1, dy.shape[-1]), alpha=_inv_scale())
         return dx, dw, db, None
 
 
@@ -448,7 +459,7 @@ class RoiAlignFn(torch.autograd.Function):
         (rois,) = ctx.saved_tensors
         P, scales, shapes = ctx.cfg
         grads = K.roi_align_bwd(dout.contiguous(), shapes, scales, rois, P)
-        return (None, None, None, *[g.to(torch.bfloat16) for g in grads])
+        return (None, None, None, *[g.to(ACT) for g in grads])
 
 
 def roi_align(feats, scales, rois, P):

@@ -8,7 +8,10 @@
  *   - return 0 on success, a negative code on failure; eosvos_last_error() gives the message;
  *   - no hidden allocation, no hidden synchronisation, nothing throws across the boundary;
  *   - sm_100a only: there is no CPU or other-architecture fallback.
- * Activations are NHWC bf16 ("bf16*" below means __nv_bfloat16), parameters and losses fp32.
+ * Activations / tensor-core operands are NHWC 16-bit floats: IEEE fp16 in the default build, bfloat16 with
+ * -DEOSVOS_ACT_BF16 (eosvos_act_dtype() tells which); parameters, gradients and losses are fp32.  Entry
+ * points that produce parameter gradients take `alpha`, applied to every accumulated value (the inverse
+ * of the static loss scale the fp16 backward runs under).
  */
 #ifndef EOSVOS_B200_H
 #define EOSVOS_B200_H
@@ -32,6 +35,7 @@ const char* eosvos_last_error(void);
 int eosvos_version(void);
 int eosvos_device_check(int device);
 unsigned long long eosvos_launch_count(void);
+int eosvos_act_dtype(void); /* 0 = bfloat16, 1 = float16 (default build) */
 
 /* ---- K1: dense contractions on tcgen05 (reference: cuDNN conv / ATen addmm reached from
  *      src/networks/mask_rcnn.py:716 forward and src/meta_optim/meta_optim.py:202-204 backward) */
@@ -47,19 +51,19 @@ int eosvos_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, 
                         int KW, int stride, int pad, int flags, int bn_hint, eosvos_stream_t stream);
 /* dw[Cout,Cin,KH,KW] (fp32, torch layout) += x (*) dy ; the caller zeroes dw */
 int eosvos_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int KH,
-                        int KW, int stride, int pad, int bn_hint, int split_hint, eosvos_stream_t stream);
+                        int KW, int stride, int pad, float alpha, int bn_hint, int split_hint, eosvos_stream_t stream);
 /* dw[m * s_m + (n / n_inner) * s_n_outer + (n % n_inner) * s_n_inner] += sum_r dy[r][m] * x[r][n]
  * (Linear / stem-im2col weight gradients with an arbitrary destination layout) */
 int eosvos_gemm_wgrad(const void* x, const void* dy, float* dw, long long rows, int n_cols, int m_cols,
-                      long long s_m, int n_inner, long long s_n_inner, long long s_n_outer, int bn_hint,
-                      int split_hint, eosvos_stream_t stream);
+                      long long s_m, int n_inner, long long s_n_inner, long long s_n_outer, float alpha,
+                      int bn_hint, int split_hint, eosvos_stream_t stream);
 /* 2x2 / stride-2 transposed convolution of the mask head (tv MaskRCNNPredictor.conv5_mask) */
 int eosvos_deconv2x2_fprop(const void* x, const void* wd, const float* bias4, void* y, int N, int h, int w, int Cin,
                            int Cout, int flags, int bn_hint, eosvos_stream_t stream);
 int eosvos_deconv2x2_dgrad(const void* dy, const void* wdt, void* dx, int N, int h, int w, int Cin, int Cout,
                            int flags, int bn_hint, eosvos_stream_t stream);
 int eosvos_deconv2x2_wgrad(const void* x, const void* dy, float* dw, int N, int h, int w, int Cin, int Cout,
-                           int bn_hint, int split_hint, eosvos_stream_t stream);
+                           float alpha, int bn_hint, int split_hint, eosvos_stream_t stream);
 
 /* ---- K2/K3: GroupNorm(32) (+residual) (+ReLU)  (reference: mask_rcnn.py:523-534 -> ATen native_group_norm) */
 int eosvos_gn_stats(const void* x, float* sums, int N, int HW, int C, eosvos_stream_t stream);
@@ -67,7 +71,7 @@ int eosvos_gn_apply(const void* x, const float* sums, const float* gamma, const 
                     int N, int HW, int C, float eps, int relu, eosvos_stream_t stream);
 int eosvos_gn_backward(const void* x, const float* sums, const float* gamma, const float* beta, const void* dy,
                        const void* yout, float* part, void* dx, void* dres, float* dgamma, float* dbeta, int N, int HW,
-                       int C, float eps, int mask_mode, eosvos_stream_t stream);
+                       int C, float eps, int mask_mode, float alpha, eosvos_stream_t stream);
 
 /* ---- K4: multi-scale RoIAlign (reference: mask_rcnn.py:113,147 -> torchvision::roi_align) */
 int eosvos_roi_align_fwd(const void* const* feats, const int* Hs, const int* Ws, const float* scales, const float* rois,
@@ -116,7 +120,7 @@ int eosvos_maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, i
 int eosvos_subsample2(const void* x, void* y, int N, int H, int W, int C, int backward, eosvos_stream_t stream);
 int eosvos_sum2x2(const void* dfine, void* dcoarse, int N, int Hc, int Wc, int C, eosvos_stream_t stream);
 int eosvos_relu_bwd(const void* dy, const void* y, void* out, long long numel, eosvos_stream_t stream);
-int eosvos_colsum(const void* dy, float* out, long long M, int C, eosvos_stream_t stream);
+int eosvos_colsum(const void* dy, float* out, long long M, int C, float alpha, eosvos_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,6 @@
 """Parity of every CUDA kernel (called through the C ABI) against the CPU oracle (oracle/ops_oracle.py).
 
-Tolerances (stated per test): operands are bf16 (8-bit mantissa), accumulation fp32.  The oracle is
+Tolerances (stated per test): operands are 16-bit (fp16 by default, bf16 optional), accumulation fp32.  The oracle is
 evaluated in fp32 on the SAME bf16-rounded operands, so the remaining error is accumulation order plus
 one bf16 rounding of the stored result: rel. Frobenius error <= 4e-3 for bf16 outputs, <= 2e-5 for
 fp32 outputs.  Integer / index results (boxes, counts, targets) must match exactly.
@@ -26,7 +26,8 @@ def dev():
 
 
 def bf(x):
-    return x.to(torch.bfloat16)
+    """round to the library's activation storage type (fp16 by default, bf16 with -DEOSVOS_ACT_BF16)"""
+    return x.to(K().ACT_DTYPE)
 
 
 def rel_err(a, b):

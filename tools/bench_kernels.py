@@ -35,11 +35,11 @@ def main():
     res = []
     for name, H, W, Cin, Cout, ks, s in shapes:
         pad = ks // 2
-        x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
-        w = (torch.randn(Cout, ks, ks, Cin, device=dev) * 0.05).bfloat16()
-        wt = (torch.randn(Cin, ks, ks, Cout, device=dev) * 0.05).bfloat16()
+        x = torch.randn(B, H, W, Cin, device=dev).to(k.ACT_DTYPE)
+        w = (torch.randn(Cout, ks, ks, Cin, device=dev) * 0.05).to(k.ACT_DTYPE)
+        wt = (torch.randn(Cin, ks, ks, Cout, device=dev) * 0.05).to(k.ACT_DTYPE)
         Ho, Wo = (H + 2 * pad - ks) // s + 1, (W + 2 * pad - ks) // s + 1
-        dy = torch.randn(B, Ho, Wo, Cout, device=dev).bfloat16()
+        dy = torch.randn(B, Ho, Wo, Cout, device=dev).to(k.ACT_DTYPE)
         flops = 2.0 * B * Ho * Wo * Cout * Cin * ks * ks
         line = {"name": name, "gflop": flops / 1e9}
         for bn in (64, 128, 256):
@@ -57,7 +57,7 @@ def main():
             line[f"wgrad_bn{bn}_tflops"] = round(flops / t / 1e12, 1)
         # GroupNorm at this output shape
         if Cout >= 64:
-            y = torch.randn(B, Ho, Wo, Cout, device=dev).bfloat16()
+            y = torch.randn(B, Ho, Wo, Cout, device=dev).to(k.ACT_DTYPE)
             gam = torch.ones(Cout, device=dev); bet = torch.zeros(Cout, device=dev)
             t1 = timeit(lambda: k.gn_stats(y)); sums = k.gn_stats(y)
             t2 = timeit(lambda: k.gn_apply(y, sums, gam, bet, relu=True))

@@ -7,7 +7,7 @@ from eosvos_b200 import kernels as k
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 
-def bf(x): return x.to(torch.bfloat16)
+def bf(x): return x.to(k.ACT_DTYPE)
 
 def report(name, got, ref):
     d = (got.double() - ref.double())

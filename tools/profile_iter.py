@@ -1,0 +1,28 @@
+"""One warm fine-tune iteration (batch 3, 854x480) + one inference frame inside a cudaProfilerStart/Stop window.
+Use with:  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file ... """
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from eosvos_b200.util import evaluate as E
+
+dev = torch.device("cuda:0")
+model, opt = bench.build_model(dev)
+fr, gt0, batches = bench.build_workload(1)
+db = [(a.to(dev), b.to(dev)) for a, b in batches]
+frames = [fr[1:2].to(dev)]
+tgt = gt0[None, None].to(dev)
+n_warm = int(os.environ.get("WARM", "2"))
+E.finetune(model, opt, lambda e: db[e % 4], n_warm, 1, 1)
+E.run_frames(model, iter(frames), tgt)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+torch.cuda.cudart().cudaProfilerStart()
+E.finetune(model, opt, lambda e: db[e % 4], int(os.environ.get("ITERS", "1")), 1, 2)
+torch.cuda.synchronize()
+t1 = time.perf_counter()
+E.run_frames(model, iter(frames), tgt)
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+t2 = time.perf_counter()
+print(f"finetune {1e3*(t1-t0):.1f} ms, inference frame {1e3*(t2-t1):.1f} ms")
