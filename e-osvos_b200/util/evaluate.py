@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import augment
+from .shard import ona_schedule
 
 
 def set_random_seeds(seed):

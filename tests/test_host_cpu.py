@@ -1,0 +1,132 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/eosvos_b200.h declares, the host
+side mirrors the reference API, the product fails loudly without a GPU, sharding / schedule logic, and a
+world_size-2 gloo run of the multi-GPU plumbing (no compute calls: there is no GPU here)."""
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "eosvos_b200.h")).read()
+    declared = set(re.findall(r"\b(eosvos_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.eosvos_version() == 100
+    assert lib.eosvos_act_dtype() in (0, 1)
+    # error path: no device here -> a negative code and a message, never an exception across the ABI
+    assert lib.eosvos_device_check(0) != 0 and len(_lib.last_error()) > 0
+
+
+def test_no_cpu_fallback():
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200 import _lib, kernels
+    from eosvos_b200.meta_optim.meta_optim import MetaOptimizer
+    with pytest.raises(_lib.EosvosError):
+        kernels.relu_bwd(torch.zeros(8, dtype=kernels.ACT_DTYPE), torch.zeros(8, dtype=kernels.ACT_DTYPE))
+    net = torch.nn.Linear(4, 3)
+    opt = MetaOptimizer(net, 1e-2, True, False, 'NEURON', False, None)
+    opt.reset()
+    opt.eval()
+    loss = net(torch.ones(2, 4)).sum()
+    with pytest.raises(_lib.EosvosError):
+        opt.step(loss)                      # the fused update is a CUDA kernel; on CPU it must raise, not fall back
+
+
+def test_meta_optimizer_mirrors_reference_api():
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200.meta_optim.meta_optim import MetaOptimizer
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.GroupNorm(4, 8), torch.nn.Flatten(),
+                              torch.nn.Linear(8 * 6 * 6, 5))
+    for level, use_log in (("NEURON", False), ("NEURON", True), ("PARAM", False), ("TENSOR", False), ("SINGLE", False)):
+        opt = MetaOptimizer(net, 1e-2, True, False, level, use_log, 0.1)
+        keys = list(opt.state_dict().keys())
+        assert any(k.startswith("model_init_0-weight") for k in keys)
+        if level in ("NEURON", "PARAM"):
+            assert "log_init_lr_0-weight" in keys and opt.state_dict()["log_init_lr_0-weight"].shape == (
+                (8, 1, 1, 1) if level == "NEURON" else (8, 3, 3, 3))
+            assert opt.state_dict()["log_init_lr_1-bias"].shape == (8,)
+        opt.reset()
+        opt.clamp_init_lr()
+        assert opt.state["num_steps"] == 0
+        assert float(torch.as_tensor(opt.init_lr).max()) <= 0.1 + 1e-6
+        opt.meta_model.detach_param_groups()
+        assert all(p.requires_grad and p.is_leaf for *_, p in opt.meta_model.param_groups())
+        opt.reset()
+        assert all(p is q for (*_, p), q in zip(opt.meta_model.param_groups(), opt._model_init.values()))
+    with pytest.raises(NotImplementedError):
+        o = MetaOptimizer(net, 1e-2, True, True, "NEURON", False, None)
+        o.train()
+        o.step(net(torch.ones(1, 3, 8, 8)).sum())
+
+
+def test_ona_schedule_and_sharding():
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200.util import shard, synthetic
+    s = shard.ona_schedule(70, 100, 5, 10)          # e-OSVOS-100-OnA on a 70-frame video
+    assert sum(x[1] for x in s) == 230 and sum(x[3] - x[2] for x in s) == 69 and len(s) == 14
+    assert s[0] == (0, 100, 1, 6) and s[-1][3] == 70
+    assert shard.ona_schedule(10, 10) == [(0, 10, 1, 10)]
+    spec = synthetic.davis_val_shaped_set()
+    units = [(v, o, T) for v, (T, K) in enumerate(spec) for o in range(K)]
+    assert len(spec) == 30
+    for world in (1, 2, 4, 8):
+        shards, loads = shard.shard_units(units, world, num_epochs_eval=100, online_adapt_step=5)
+        assert sorted(u for sh in shards for u in sh) == sorted(units)
+        assert max(loads) <= 1.25 * (sum(loads) / world) + max(loads) / len(units)
+
+
+def test_synthetic_and_augmentation():
+    import random
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200.util import augment, synthetic
+    f1, l1 = synthetic.make_video(3, 3, 120, 214, 2)
+    f2, l2 = synthetic.make_video(3, 3, 120, 214, 2)
+    assert np.array_equal(f1, f2) and np.array_equal(l1, l2) and set(np.unique(l1)) == {0, 1, 2}
+    assert (l1[0] == 1).mean() > 0.01
+    random.seed(1)
+    img, gt = augment.augment_first_frame(f1[0].astype(np.float32) / 255, (l1[0] == 1).astype(np.float32))
+    assert img.shape == (120, 214, 3) and gt.shape == (120, 214) and gt.max() == 1.0
+
+
+def test_two_rank_gloo_plumbing(tmp_path):
+    """N > 1 path on CPU: gloo, world_size 2 -- disjoint shards, max-over-ranks timing reduction."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import torch, torch.distributed as dist
+        import eosvos_b200
+        from eosvos_b200.util import shard, synthetic
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        spec = synthetic.davis_val_shaped_set()
+        units = [(v, o, T) for v, (T, K) in enumerate(spec) for o in range(K)]
+        shards, loads = shard.shard_units(units, w, num_epochs_eval=100, online_adapt_step=5)
+        mine = torch.zeros(len(units)); idx = {{u: i for i, u in enumerate(units)}}
+        for u in shards[r]: mine[idx[u]] = 1
+        dist.all_reduce(mine)
+        t = torch.tensor([float(loads[r])], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert bool((mine == 1).all()), "shards must partition the units"
+        assert abs(t.item() - max(loads)) < 1e-9
+        if r == 0: print("OK", w)
+        dist.destroy_process_group()
+    """))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK 2" in out.stdout, out.stderr[-2000:]
