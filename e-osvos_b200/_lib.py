@@ -43,10 +43,14 @@ SIGNATURES = {
     "eosvos_mask_loss_bce": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "eosvos_mask_paste_threshold": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "eosvos_mask_to_bbox": [_P, _P, _I, _I, _I, _I, _P],
+    "eosvos_nms_scratch_bytes": [_I, _I],
+    "eosvos_nms_segments": [_P, _P, _I, _I, _F, _P, _P, _P],
     "eosvos_meta_update_chunk_elems": [],
     "eosvos_meta_update": [_P, _P, _I, _I, _P],
     "eosvos_radam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
     "eosvos_permute_cast": [_P, _P, _P, _P, _P, _I, _I, _P],
+    "eosvos_permute_cast_multi_chunk_elems": [],
+    "eosvos_permute_cast_multi": [_P, _P, _I, _P],
     "eosvos_transform": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "eosvos_mask_resize_nearest": [_P, _P, _I, _I, _I, _I, _I, _P],
     "eosvos_im2col_stem": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -57,7 +61,7 @@ SIGNATURES = {
     "eosvos_relu_bwd": [_P, _P, _P, _L, _P],
     "eosvos_colsum": [_P, _P, _L, _I, _F, _P],
 }
-_RESTYPES = {"eosvos_last_error": c_char_p, "eosvos_launch_count": ctypes.c_ulonglong}
+_RESTYPES = {"eosvos_nms_scratch_bytes": c_longlong, "eosvos_last_error": c_char_p, "eosvos_launch_count": ctypes.c_ulonglong}
 
 
 class EosvosError(RuntimeError):

@@ -71,7 +71,7 @@ static int pick_bn(int n_cols, long long m_tiles, int bn_hint) {
   if (n_cols <= 128) return 128;
   // wide outputs: 256-column tiles halve A re-reads, but only when the grid still fills the chip
   const long long ctas256 = m_tiles * ((n_cols + 255) / 256);
-  if (n_cols % 256 == 0 && ctas256 >= 2LL * num_sms()) return 256;
+  if (n_cols % 256 == 0 && ctas256 >= (long long)num_sms()) return 256;
   return 128;
 }
 
@@ -121,6 +121,7 @@ static int run_fprop(const AView& av, const int extent[4], const int conv_stride
   }
   const int bn = pick_bn(n_valid, m_tiles, bn_hint);
   p.n_tiles_n = (n_valid + bn - 1) / bn;
+  p.m_tiles = (int)m_tiles;
   p.out = ep.out;
   p.bias = ep.bias;
   p.relu = ep.relu;
@@ -131,6 +132,7 @@ static int run_fprop(const AView& av, const int extent[4], const int conv_stride
   p.gn_sum = ep.gn_sum;
   p.gn_cpg = ep.gn_cpg;
   p.gn_dim = ep.gn_dim;
+  if (ep.gn_sum) EOSVOS_REQUIRE((ep.gn_cpg & (ep.gn_cpg - 1)) == 0, "fprop: GroupNorm channels per group must be a power of two");
   if (ep.ogroup) EOSVOS_REQUIRE(ep.ogroup % bn == 0, "fprop: output group must be a multiple of the column tile");
 
   CUtensorMap tmA, tmB;
@@ -405,8 +407,27 @@ static int run_wgrad(const AView& a_view, const AView& b_view, const int extent[
   p.n_tiles_n = (n_valid + bn - 1) / bn;
   const int m_tiles = (m_valid + 127) / 128;
   const long long base_ctas = (long long)m_tiles * p.n_tiles_n * num_taps;
-  // split the pixel reduction so that the grid covers the chip about twice
-  long long split = split_hint > 0 ? split_hint : (2LL * num_sms() + base_ctas - 1) / base_ctas;
+  // split the pixel reduction so that the grid is a whole number of waves (1 CTA / SM, long-running CTAs: a
+  // partial trailing wave costs a full wave of time); prefer the fewest waves among near-equal efficiencies
+  long long split = 1;
+  if (split_hint > 0) {
+    split = split_hint;
+  } else {
+    const long long sms = num_sms();
+    double best_eff = -1.0;
+    for (int k = 1; k <= 4; ++k) {
+      long long sp = (k * sms) / base_ctas;
+      if (sp < 1) sp = 1;
+      if (sp > tiles) sp = tiles;
+      const long long ctas = base_ctas * sp;
+      const long long waves = (ctas + sms - 1) / sms;
+      const double eff = (double)ctas / (double)(waves * sms);
+      if (eff > best_eff + 0.03) {
+        best_eff = eff;
+        split = sp;
+      }
+    }
+  }
   split = std::max(1LL, std::min(split, tiles));
   p.tiles_per_split = (int)((tiles + split - 1) / split);
   split = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;

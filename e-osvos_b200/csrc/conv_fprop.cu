@@ -1,0 +1,302 @@
+// Persistent tcgen05 implicit-GEMM forward kernel: every conv / Linear / deconv forward and every data
+// gradient of the e-OSVOS hot path (reference call site src/networks/mask_rcnn.py:716 and,
+// for dgrad, src/meta_optim/meta_optim.py:202-204).
+//
+// One CTA per SM slot loops over output tiles (tile = blockIdx.x + i * gridDim.x, column tile fastest so CTAs
+// sharing an A tile run together).  Three pipelines overlap across tiles:
+//   TMA producer warp  -> smem ring (STAGES x {A 128x64, B BNx64}, SWIZZLE_128B, K-major)   full/empty mbarriers
+//   MMA issuer warp    -> tcgen05.mma kind::f16 M=128 N=BN into one of TWO TMEM accumulators  tmem_full/empty
+//   4 epilogue warps   -> tcgen05.ld, bias / residual / ReLU / GroupNorm partial statistics, 128-bit stores
+// so the epilogue of tile i runs under the loads and MMAs of tile i+1 (the HBM-bound 1x1 layers have a single
+// K block per tile and would otherwise pay load latency + MMA + epilogue serially per tile).
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+#include "common.h"
+
+namespace eosvos {
+
+template <int BN>
+struct FpropCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int CTAS_PER_SM = BN == 256 ? 1 : 2;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;      // two accumulators: 128, 256 or 512 columns
+  static constexpr int SMEM = 1024 + STAGES * (128 * 128 + BN * 128) + 256;
+};
+
+__device__ __forceinline__ void gn_flush(float* gn_sum, int n_img, int n_first, int grp, float s1, float s2, bool all_same,
+                                         bool valid, int lane) {
+  if (all_same) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+    }
+    if (lane == 0) {
+      atomicAdd(gn_sum + ((long long)n_first * 32 + grp) * 2, s1);
+      atomicAdd(gn_sum + ((long long)n_first * 32 + grp) * 2 + 1, s2);
+    }
+  } else if (valid) {
+    atomicAdd(gn_sum + ((long long)n_img * 32 + grp) * 2, s1);
+    atomicAdd(gn_sum + ((long long)n_img * 32 + grp) * 2 + 1, s2);
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, FpropCfg<BN>::CTAS_PER_SM)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const FpropParams p) {
+  constexpr int STAGES = FpropCfg<BN>::STAGES;
+  constexpr int A_STAGE = 128 * 128;
+  constexpr int B_STAGE = BN * 128;
+  constexpr uint32_t TMEM_COLS = FpropCfg<BN>::TMEM_COLS;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;    // [2]
+  uint64_t* tempty = tfull + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles_n;
+  const int num_it = p.num_taps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);   // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)p.a_bytes + (uint32_t)B_STAGE;
+      int gi = 0;  // global k-block counter across tiles -> ring stage / phase
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles_n) * BN;
+        int mt = tile / p.n_tiles_n;
+        int base[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          base[d] = (mt % p.ntiles[d]) * p.a_tile_step[d];
+          mt /= p.ntiles[d];
+        }
+        for (int it = 0; it < num_it; ++it, ++gi) {
+          const int s = gi % STAGES;
+          const uint32_t ph = (uint32_t)(gi / STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], tx);
+          const int tap = it / p.kchunks;
+          const int kc = it - tap * p.kchunks;
+          tma_load_5d(sA + s * A_STAGE, &tmA, &full[s], p.tap_delta[tap][0] + kc * 64, base[0] + p.tap_delta[tap][1],
+                      base[1] + p.tap_delta[tap][2], base[2] + p.tap_delta[tap][3], base[3] + p.tap_delta[tap][4]);
+          tma_load_2d(sB + s * B_STAGE, &tmB, &full[s], p.tap_bk[tap] + kc * 64, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_act(128, BN, 0, 0);
+      int gi = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tempty[buf], ((uint32_t)(lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+        for (int it = 0; it < num_it; ++it, ++gi) {
+          const int s = gi % STAGES;
+          const uint32_t ph = (uint32_t)(gi / STAGES) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
+          const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            umma_f16kind(acc, ad, bd, idesc, (uint32_t)((it | k) != 0));
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int n0 = (tile % p.n_tiles_n) * BN;
+      int mt = tile / p.n_tiles_n;
+      int rr = r;
+      bool valid = true;
+      long long off = 0, roff = 0;
+      int gn_n = 0;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int td = mt % p.ntiles[d];
+        mt /= p.ntiles[d];
+        const int i = rr % p.rows_box[d];
+        rr /= p.rows_box[d];
+        const int coord = td * p.rows_box[d] + i;
+        valid = valid && (coord < p.odim[d]);
+        off += (long long)coord * p.ostride[d];
+        roff += (long long)(coord >> p.rshift[d]) * p.rstride[d];
+        if (d == p.gn_dim) gn_n = coord;
+      }
+      valid = valid && (rr == 0);
+      int n_first = 0;
+      bool all_same = true;
+      if (p.gn_sum) {
+        n_first = __shfl_sync(0xffffffffu, gn_n, 0);
+        all_same = __all_sync(0xffffffffu, (gn_n == n_first) || !valid);
+      }
+
+      mbar_wait(&tfull[buf], (uint32_t)(lt >> 1) & 1u);
+      tc_fence_after_sync();
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        const int col0 = n0 + c;
+        if (col0 >= p.n_valid) break;  // uniform across the CTA
+        uint32_t v[32];
+        tmem_ld_32x32(acc + (uint32_t)c, v);
+        tmem_ld_wait();
+        long long o = off + col0;
+        if (p.ogroup) {
+          const int g = col0 / p.ogroup;
+          o = off + p.ogroup_off[g] + (col0 - g * p.ogroup);
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.n_valid) f[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.gn_sum) {
+          // GroupNorm partial statistics on the fp32 accumulators (pre-rounding).  cpg is a power of two;
+          // a group boundary falls after column j when (j + 1) is a multiple of cpg (or at the chunk end).
+          const int cmask = p.gn_cpg - 1;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = valid ? f[j] : 0.f;
+            s1 += x;
+            s2 += x * x;
+            if ((((j + 1) & cmask) == 0) || j == 31) {
+              if (col0 + j < p.n_valid)
+                gn_flush(p.gn_sum, gn_n, n_first, (col0 + j) / p.gn_cpg, s1, s2, all_same, valid, lane);
+              s1 = 0.f;
+              s2 = 0.f;
+            }
+          }
+        }
+        if (valid) {
+          if (p.res) {
+            const act_t* rp = p.res + roff + col0;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              if (col0 + j8 * 8 < p.n_valid) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j8 * 8));
+                const act2_t* rh = reinterpret_cast<const act2_t*>(&rv);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 rf = act22float2(rh[k]);
+                  f[j8 * 8 + 2 * k] += rf.x;
+                  f[j8 * 8 + 2 * k + 1] += rf.y;
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.out_fp32) {
+            float* op = reinterpret_cast<float*>(p.out) + o;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              if (col0 + j4 * 4 < p.n_valid)
+                *reinterpret_cast<float4*>(op + j4 * 4) =
+                    make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
+            }
+          } else {
+            act_t* op = reinterpret_cast<act_t*>(p.out) + o;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              if (col0 + j8 * 8 < p.n_valid) {
+                uint4 w;
+                w.x = pack_act2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+                w.y = pack_act2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+                w.z = pack_act2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+                w.w = pack_act2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+                *reinterpret_cast<uint4*>(op + j8 * 8) = w;
+              }
+            }
+          }
+        }
+      }
+      // hand the accumulator back to the MMA warp
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_fprop_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t stream) {
+  constexpr int SMEM = FpropCfg<BN>::SMEM;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_fprop)");
+    attr_done = true;
+  }
+  const long long total = (long long)p.m_tiles * p.n_tiles_n;
+  const long long slots = (long long)num_sms() * FpropCfg<BN>::CTAS_PER_SM;
+  dim3 grid((unsigned)(total < slots ? total : slots));
+  conv_fprop_kernel<BN><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
+  return check_launch("conv_fprop_kernel");
+}
+
+int launch_fprop(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, int m_tiles,
+                 cudaStream_t stream) {
+  (void)m_tiles;
+  switch (bn) {
+    case 64: return launch_fprop_t<64>(tmA, tmB, p, stream);
+    case 128: return launch_fprop_t<128>(tmA, tmB, p, stream);
+    case 256: return launch_fprop_t<256>(tmA, tmB, p, stream);
+  }
+  return set_error(EOSVOS_ERR_ARG, "launch_fprop: unsupported BN");
+}
+
+}  // namespace eosvos

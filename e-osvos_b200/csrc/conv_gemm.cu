@@ -13,225 +13,6 @@
 namespace eosvos {
 
 // =============================================================================================
-// fprop: A via 5-D TMA boxes (a shifted window per filter tap), B via 2-D TMA, both K-major SW128
-// =============================================================================================
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, (BN <= 128 ? 2 : 1))
-conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const FpropParams p) {
-  constexpr int A_STAGE = 128 * 128;
-  constexpr int B_STAGE = BN * 128;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  // tile decode: column tile fastest so CTAs sharing an A tile are co-scheduled (A stays in L2)
-  const int n_tile = blockIdx.x % p.n_tiles_n;
-  int mt = blockIdx.x / p.n_tiles_n;
-  int t[4];
-#pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    t[d] = mt % p.ntiles[d];
-    mt /= p.ntiles[d];
-  }
-  const int n0 = n_tile * BN;
-  const int num_it = p.num_taps * p.kchunks;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    mbar_init(tmem_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t tx = (uint32_t)p.a_bytes + (uint32_t)B_STAGE;
-      for (int it = 0; it < num_it; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[s], tx);
-        const int tap = it / p.kchunks;
-        const int kc = it - tap * p.kchunks;
-        tma_load_5d(sA + s * A_STAGE, &tmA, &full[s], p.tap_delta[tap][0] + kc * 64,
-                    t[0] * p.a_tile_step[0] + p.tap_delta[tap][1], t[1] * p.a_tile_step[1] + p.tap_delta[tap][2],
-                    t[2] * p.a_tile_step[2] + p.tap_delta[tap][3], t[3] * p.a_tile_step[3] + p.tap_delta[tap][4]);
-        tma_load_2d(sB + s * B_STAGE, &tmB, &full[s], p.tap_bk[tap] + kc * 64, n0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_act(128, BN, 0, 0);
-      for (int it = 0; it < num_it; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&full[s], ph);
-        tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
-        const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-          const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-          umma_f16kind(tmem_base, ad, bd, idesc, (uint32_t)((it | k) != 0));
-        }
-        umma_commit(&empty[s]);
-      }
-      umma_commit(tmem_full);
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    int rr = r;
-    bool valid = true;
-    long long off = 0, roff = 0;
-    int coord[4];
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      const int i = rr % p.rows_box[d];
-      rr /= p.rows_box[d];
-      coord[d] = t[d] * p.rows_box[d] + i;
-      valid = valid && (coord[d] < p.odim[d]);
-      off += (long long)coord[d] * p.ostride[d];
-      roff += (long long)(coord[d] >> p.rshift[d]) * p.rstride[d];
-    }
-    valid = valid && (rr == 0);
-    const int gn_n = p.gn_sum ? coord[p.gn_dim] : 0;
-
-    mbar_wait(tmem_full, 0);
-    tc_fence_after_sync();
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      const int col0 = n0 + c;
-      if (col0 >= p.n_valid) break;  // uniform across the CTA
-      long long o = off + col0;
-      if (p.ogroup) {
-        const int g = col0 / p.ogroup;
-        o = off + p.ogroup_off[g] + (col0 - g * p.ogroup);
-      }
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.n_valid) f[j] += __ldg(p.bias + col0 + j);
-      }
-      if (p.gn_sum) {
-        // GroupNorm partial statistics on the fp32 accumulators (pre-rounding), one atomic per
-        // (warp, group).  Rows of one warp may straddle two images in flat mode: handled by
-        // reducing only over lanes that share lane 0's image and letting the rest add directly.
-        const int cpg = p.gn_cpg;
-        const int ngrp = cpg >= 32 ? 1 : 32 / cpg;
-        const int n_first = __shfl_sync(0xffffffffu, gn_n, 0);
-        const bool same = (gn_n == n_first);
-        const bool all_same = __all_sync(0xffffffffu, same || !valid);
-        for (int g = 0; g < ngrp; ++g) {
-          float s1 = 0.f, s2 = 0.f;
-          const int w = cpg >= 32 ? 32 : cpg;
-          if (valid) {
-            for (int j = 0; j < w; ++j) {
-              const float x = f[g * w + j];
-              s1 += x;
-              s2 += x * x;
-            }
-          }
-          const int grp = (col0 + g * w) / cpg;
-          if (all_same) {
-#pragma unroll
-            for (int m = 16; m > 0; m >>= 1) {
-              s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-              s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-            }
-            if (lane == 0 && col0 + g * w < p.n_valid) {
-              atomicAdd(p.gn_sum + ((long long)n_first * 32 + grp) * 2, s1);
-              atomicAdd(p.gn_sum + ((long long)n_first * 32 + grp) * 2 + 1, s2);
-            }
-          } else if (valid && col0 + g * w < p.n_valid) {
-            atomicAdd(p.gn_sum + ((long long)gn_n * 32 + grp) * 2, s1);
-            atomicAdd(p.gn_sum + ((long long)gn_n * 32 + grp) * 2 + 1, s2);
-          }
-        }
-      }
-      if (valid) {
-        if (p.res) {
-          const act_t* rp = p.res + roff + col0;
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            if (col0 + j8 * 8 < p.n_valid) {
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j8 * 8));
-              const act2_t* rh = reinterpret_cast<const act2_t*>(&rv);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 rf = act22float2(rh[k]);
-                f[j8 * 8 + 2 * k] += rf.x;
-                f[j8 * 8 + 2 * k + 1] += rf.y;
-              }
-            }
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (p.out_fp32) {
-          float* op = reinterpret_cast<float*>(p.out) + o;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            if (col0 + j4 * 4 < p.n_valid)
-              *reinterpret_cast<float4*>(op + j4 * 4) =
-                  make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
-          }
-        } else {
-          act_t* op = reinterpret_cast<act_t*>(p.out) + o;
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            if (col0 + j8 * 8 < p.n_valid) {
-              uint4 w;
-              w.x = pack_act2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-              w.y = pack_act2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-              w.z = pack_act2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-              w.w = pack_act2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-              *reinterpret_cast<uint4*>(op + j8 * 8) = w;
-            }
-          }
-        }
-      }
-    }
-    tc_fence_before_sync();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
-// =============================================================================================
 // wgrad: dW[m, n] += sum over pixel tiles of A[pix, m] * B[pix, n]; both operands MN-major SW128.
 // A = dY boxes (2 x 64 channels), B = X boxes (BN/64 x 64 channels), K = pixels (<= 64 per stage,
 // zero-padded to a multiple of 16).  Split over pixel tiles (grid.x), fp32 red.add epilogue.
@@ -421,31 +202,6 @@ int make_tensor_map_act(CUtensorMap* m, const void* base, int rank, const uint64
     return set_error(EOSVOS_ERR_CUDA, buf);
   }
   return 0;
-}
-
-template <int BN, int STAGES>
-static int launch_fprop_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, int m_tiles,
-                          cudaStream_t stream) {
-  constexpr int SMEM = 1024 + STAGES * (128 * 128 + BN * 128) + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_fprop)");
-    attr_done = true;
-  }
-  dim3 grid((unsigned)(m_tiles * p.n_tiles_n));
-  conv_fprop_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
-  return check_launch("conv_fprop_kernel");
-}
-
-int launch_fprop(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, int m_tiles,
-                 cudaStream_t stream) {
-  switch (bn) {
-    case 64: return launch_fprop_t<64, 4>(tmA, tmB, p, m_tiles, stream);
-    case 128: return launch_fprop_t<128, 3>(tmA, tmB, p, m_tiles, stream);
-    case 256: return launch_fprop_t<256, 4>(tmA, tmB, p, m_tiles, stream);
-  }
-  return set_error(EOSVOS_ERR_ARG, "launch_fprop: unsupported BN");
 }
 
 template <int BN, int STAGES>

@@ -18,6 +18,7 @@ struct FpropParams {
   int tap_bk[MAX_TAPS];           // per-tap B K-coordinate base
   int a_bytes;                    // bytes one A box deposits (rows * 128)
   int n_tiles_n;                  // column tiles
+  int m_tiles;                    // row tiles (product of ntiles[])
   // epilogue
   void* out;
   const float* bias;

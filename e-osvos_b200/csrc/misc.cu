@@ -448,3 +448,45 @@ extern "C" int eosvos_colsum(const void* dy, float* out, long long M, int C, flo
                                                         (int)rows_per_block, alpha);
   return check_launch("colsum_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------
+// multi-tensor permute + cast (fp32 -> act_t): all tensor-core operand layouts of one iteration in ONE launch.
+// table: int64 [T][14] = (src, dst, dims[4], sstride[4], dstride[4]); chunks: int32 [n][2] = (tensor, chunk)
+// ---------------------------------------------------------------------------------------------
+namespace eosvos {
+constexpr int PM_CHUNK = 8192;
+__global__ void __launch_bounds__(256)
+permute_cast_multi_kernel(const long long* __restrict__ table, const int* __restrict__ chunks) {
+  const int t = chunks[blockIdx.x * 2];
+  const long long start = (long long)chunks[blockIdx.x * 2 + 1] * PM_CHUNK;
+  const long long* e = table + (size_t)t * 14;
+  const float* __restrict__ src = reinterpret_cast<const float*>(e[0]);
+  act_t* __restrict__ dst = reinterpret_cast<act_t*>(e[1]);
+  const long long d1 = e[3], d2 = e[4], d3 = e[5];
+  const long long total = e[2] * d1 * d2 * d3;
+  long long end = start + PM_CHUNK;
+  if (end > total) end = total;
+  for (long long i = start + threadIdx.x; i < end; i += 256) {
+    long long r = i;
+    const long long i3 = r % d3;
+    r /= d3;
+    const long long i2 = r % d2;
+    r /= d2;
+    const long long i1 = r % d1;
+    const long long i0 = r / d1;
+    const float v = src[i0 * e[6] + i1 * e[7] + i2 * e[8] + i3 * e[9]];
+    dst[i0 * e[10] + i1 * e[11] + i2 * e[12] + i3 * e[13]] = float2act(v);
+  }
+}
+}  // namespace eosvos
+
+extern "C" int eosvos_permute_cast_multi_chunk_elems(void) { return eosvos::PM_CHUNK; }
+
+extern "C" int eosvos_permute_cast_multi(const long long* table_dev, const int* chunks_dev, int num_chunks,
+                                         eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (num_chunks == 0) return 0;
+  EOSVOS_REQUIRE(table_dev && chunks_dev, "permute_cast_multi: null table");
+  eosvos::permute_cast_multi_kernel<<<num_chunks, 256, 0, stream>>>(table_dev, chunks_dev);
+  return eosvos::check_launch("permute_cast_multi_kernel");
+}

@@ -16,8 +16,12 @@ GN_EPS = 1e-5
 ACT_DTYPE = torch.float16 if _lib.load().eosvos_act_dtype() == 1 else getattr(torch, "bfloat16")
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of torch's current stream on the current device (torch.cuda.current_stream() costs ~15 us)
+    return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
 
 
 def _ptr(t):
@@ -29,12 +33,48 @@ def _ptr(t):
 def _chk(t, dtype=None, name="tensor"):
     if not t.is_cuda:
         raise _lib.EosvosError(f"{name} must live on a CUDA device (no CPU path exists)")
-    if not t.is_contiguous():
-        raise _lib.EosvosError(f"{name} must be contiguous")
     if dtype is not None and t.dtype != dtype:
         raise _lib.EosvosError(f"{name} must be {dtype}, got {t.dtype}")
-    _lib.require_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    if not t.is_contiguous():
+        raise _lib.EosvosError(f"{name} must be contiguous")
+    idx = t.device.index
+    if idx not in _lib._checked_devices:
+        _lib.require_device(idx if idx is not None else torch.cuda.current_device())
+        _lib._checked_devices.add(idx)
     return t
+
+
+class ZeroPool:
+    """Hands out zero-initialised fp32 views carved from ONE zeroed block per iteration (instead of ~200
+    torch.zeros calls): accumulate-into outputs (split-K weight gradients, GroupNorm statistics, RoIAlign-bwd
+    maps).  A block is freed by reference counting once every view of it is gone, so views never alias."""
+
+    def __init__(self):
+        self.block = None
+        self.off = 0
+        self.used = 0
+        self.hint = 0
+
+    def reset(self):
+        self.hint = max(self.hint, self.used)
+        self.block, self.off, self.used = None, 0, 0
+
+    def take(self, shape, device):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        n_al = (n + 63) // 64 * 64          # keep every view 256-byte aligned
+        if self.block is None or self.block.device != device or self.off + n_al > self.block.numel():
+            size = max(self.hint - self.used, n_al, 1 << 20)
+            self.block = torch.zeros(size, device=device, dtype=torch.float32)
+            self.off = 0
+        v = self.block[self.off:self.off + n].view(shape)
+        self.off += n_al
+        self.used += n_al
+        return v
+
+
+zero_pool = ZeroPool()
 
 
 # ------------------------------------------------------------------------------------------- K1
@@ -85,7 +125,7 @@ def conv2d_wgrad(x, dy, ksize, *, stride=1, pad=0, alpha=1.0, bn_hint=0, split_h
     Cout = dy.shape[-1]
     KH, KW = ksize
     if out is None:
-        out = torch.zeros((Cout, Cin, KH, KW), device=x.device, dtype=torch.float32)
+        out = zero_pool.take((Cout, Cin, KH, KW), x.device)
     call("eosvos_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(out), N, H, W, Cin, Cout, KH, KW, stride, pad, alpha, bn_hint,
          split_hint, _stream())
     return out
@@ -134,7 +174,7 @@ def deconv2x2_wgrad(x, dy, *, alpha=1.0, bn_hint=0, split_hint=0):
     _chk(dy, ACT_DTYPE, "dy")
     N, h, w, Cin = x.shape
     Cout = dy.shape[-1]
-    dw = torch.zeros((Cin, Cout, 2, 2), device=x.device, dtype=torch.float32)
+    dw = zero_pool.take((Cin, Cout, 2, 2), x.device)
     call("eosvos_deconv2x2_wgrad", _ptr(x), _ptr(dy), _ptr(dw), N, h, w, Cin, Cout, alpha, bn_hint, split_hint, _stream())
     return dw
 
@@ -207,7 +247,7 @@ def roi_align_bwd(dout, level_shapes, scales, rois, P, sampling=2):
     sc = (ctypes.c_float * 4)(*[float(s) for s in scales])
     outs = []
     for i, shp in enumerate(level_shapes):
-        g = torch.zeros(shp, device=dout.device, dtype=torch.float32)
+        g = zero_pool.take(tuple(shp), dout.device)
         outs.append(g)
         ptrs[i] = g.data_ptr()
         Hs[i], Ws[i] = shp[1], shp[2]
@@ -278,27 +318,52 @@ def mask_to_bbox(target, K):
     return stats
 
 
+# ------------------------------------------------------------------------------------------- K5
+def nms_segments(boxes_sorted, seg_offsets, num_segments, max_seg, thresh):
+    """boxes [n,4] fp32 sorted by descending score inside each segment; seg_offsets int32 [S+1] (device).
+    Returns keep flags uint8 [n]."""
+    _chk(boxes_sorted, torch.float32, "boxes")
+    _chk(seg_offsets, torch.int32, "seg_offsets")
+    n = boxes_sorted.shape[0]
+    keep = torch.zeros((n,), device=boxes_sorted.device, dtype=torch.uint8)
+    if n == 0 or num_segments == 0:
+        return keep
+    nbytes = _lib.load().eosvos_nms_scratch_bytes(num_segments, max_seg)
+    scratch = torch.empty((nbytes,), device=boxes_sorted.device, dtype=torch.uint8)
+    call("eosvos_nms_segments", _ptr(boxes_sorted), _ptr(seg_offsets), num_segments, max_seg, float(thresh),
+         _ptr(scratch), _ptr(keep), _stream())
+    return keep
+
+
 # ------------------------------------------------------------------------------------------- K9
 class MetaUpdatePlan:
     """Pointer/chunk tables of one (params, grads, lrs, outs) binding, cached on the device."""
 
+    _chunk_cache = {}
+
     def __init__(self, params, grads, lrs, outs):
+        import numpy as np
         chunk = _lib.load().eosvos_meta_update_chunk_elems()
-        rows, chunks = [], []
+        dev = params[0].device
+        T = len(params)
+        rows = np.empty((T, 6), dtype=np.int64)
         for t, (p, g, lr, o) in enumerate(zip(params, grads, lrs, outs)):
             n = p.numel()
-            assert g.numel() == n and o.numel() == n, "meta_update: size mismatch"
-            assert n % lr.numel() == 0, "meta_update: learning-rate shape must divide the parameter"
-            for tt in (p, g, lr, o):
-                _chk(tt, torch.float32, "meta_update operand")
-            rows.append([p.data_ptr(), g.data_ptr(), lr.data_ptr(), o.data_ptr(), n, n // lr.numel()])
-            for c in range((n + chunk - 1) // chunk):
-                chunks.append([t, c])
-        dev = params[0].device
-        self.table = torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
-        self.chunks = torch.tensor(chunks, dtype=torch.int32).to(dev, non_blocking=True)
-        self.num_chunks = len(chunks)
-        self.key = tuple(r[0] for r in rows) + tuple(r[1] for r in rows) + tuple(r[3] for r in rows)
+            if g.numel() != n or o.numel() != n or n % lr.numel() != 0:
+                raise _lib.EosvosError("meta_update: parameter / gradient / learning-rate sizes do not match")
+            if not (p.is_cuda and g.is_cuda and lr.is_cuda and o.is_cuda) or p.dtype != torch.float32 or \
+                    g.dtype != torch.float32 or lr.dtype != torch.float32 or not (p.is_contiguous() and g.is_contiguous()):
+                raise _lib.EosvosError("meta_update operands must be contiguous fp32 CUDA tensors (no CPU path exists)")
+            rows[t] = (p.data_ptr(), g.data_ptr(), lr.data_ptr(), o.data_ptr(), n, n // lr.numel())
+        _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        key = (str(dev), tuple(int(n) for n in rows[:, 4]))
+        hit = MetaUpdatePlan._chunk_cache.get(key)
+        if hit is None:
+            chunks = [[t, c] for t in range(T) for c in range((int(rows[t, 4]) + chunk - 1) // chunk)]
+            hit = (torch.tensor(chunks, dtype=torch.int32).to(dev), len(chunks))
+            MetaUpdatePlan._chunk_cache = {key: hit}
+        self.chunks, self.num_chunks = hit
+        self.table = torch.from_numpy(rows).to(dev, non_blocking=True)
 
 
 def meta_update(plan, use_log=False):
@@ -324,6 +389,36 @@ def permute_cast(src, dst, dims, sstride, dstride):
     t = (ctypes.c_longlong * 4)(*dstride)
     call("eosvos_permute_cast", _ptr(src), _ptr(dst), d, s, t, _DT[src.dtype], _DT[dst.dtype], _stream())
     return dst
+
+
+_pm_chunk_cache = {}
+
+
+def permute_cast_multi(jobs):
+    """jobs: list of (src fp32 tensor, dst ACT tensor, dims[4], sstride[4], dstride[4]) -> one launch."""
+    import numpy as np
+    if not jobs:
+        return
+    chunk = _lib.load().eosvos_permute_cast_multi_chunk_elems()
+    tab = np.empty((len(jobs), 14), dtype=np.int64)
+    for t, (src, dst, dims, ss, ds) in enumerate(jobs):
+        tab[t, 0], tab[t, 1] = src.data_ptr(), dst.data_ptr()
+        tab[t, 2:6], tab[t, 6:10], tab[t, 10:14] = dims, ss, ds
+    dev = jobs[0][0].device
+    _chk(jobs[0][0], torch.float32, "permute_cast_multi source")
+    totals = tab[:, 2] * tab[:, 3] * tab[:, 4] * tab[:, 5]
+    key = (str(dev), totals.tobytes())
+    hit = _pm_chunk_cache.get(key)
+    if hit is None:                       # the chunk table only depends on the tensor sizes: build once
+        counts = (totals + chunk - 1) // chunk
+        tid = np.repeat(np.arange(len(jobs), dtype=np.int32), counts)
+        cid = np.concatenate([np.arange(c, dtype=np.int32) for c in counts]) if len(jobs) else np.zeros(0, np.int32)
+        hit = (torch.from_numpy(np.stack([tid, cid], 1).copy()).to(dev), int(counts.sum()))
+        if len(_pm_chunk_cache) > 8:
+            _pm_chunk_cache.clear()
+        _pm_chunk_cache[key] = hit
+    table = torch.from_numpy(tab).to(dev, non_blocking=True)
+    call("eosvos_permute_cast_multi", _ptr(table), _ptr(hit[0]), hit[1], _stream())
 
 
 def nchw_to_nhwc_bf16(x):
@@ -424,6 +519,6 @@ def colsum(dy2d, out=None, alpha=1.0):
     _chk(dy2d, ACT_DTYPE, "dy")
     M, C = dy2d.shape
     if out is None:
-        out = torch.zeros((C,), device=dy2d.device, dtype=torch.float32)
+        out = zero_pool.take((C,), dy2d.device)
     call("eosvos_colsum", _ptr(dy2d), _ptr(out), M, C, alpha, _stream())
     return out

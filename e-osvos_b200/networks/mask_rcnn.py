@@ -184,6 +184,27 @@ class MaskRCNN(_MaskRCNN):
                         "iscrowd": torch.zeros((num_objs,), dtype=torch.int64, device=device)})
         return out
 
+    def _prepare_operands(self):
+        """All 16-bit tensor-core operand layouts of the current parameters in ONE launch (cached per live tensor)."""
+        training = self.training
+        req = []
+        body = self.backbone.body
+        req.append((body.conv1.weight, "stem"))
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d) and m is not body.conv1 and m.weight.shape[0] >= 64:
+                req.append((m.weight, "f"))
+                if training:
+                    req.append((m.weight, "t"))
+        rh = self.roi_heads
+        C = self.backbone.out_channels
+        req.append((rh.box_head.fc6.weight, ("lf", C)))
+        req.append((rh.box_head.fc7.weight, ("lf", 0)))
+        if training:
+            req.append((rh.box_head.fc6.weight, ("lt", C)))
+            req.append((rh.box_head.fc7.weight, ("lt", 0)))
+        req.append((rh.mask_predictor.conv5_mask.weight, "dc"))
+        ops.prep_many(req)
+
     # ---- transform (tv transform.py:119-160, 25-84, 237-255) ------------------------------------
     def _resized_size(self, h, w):
         tr = self.transform
@@ -297,7 +318,7 @@ class MaskRCNN(_MaskRCNN):
             self.capture.update(objectness=objectness.detach(), deltas=pred_bbox_deltas.detach())
         anchors = self._anchors(image_shape, image_sizes, feat_shapes, feats[0].device)
         proposals = rpn.box_coder.decode(pred_bbox_deltas.detach(), anchors).view(N, -1, 4)
-        boxes, scores = rpn.filter_proposals(proposals, objectness, image_sizes, num_anchors_per_level)
+        boxes, scores = self._filter_proposals(proposals, objectness, image_sizes, num_anchors_per_level)
 
         mode = rpn._eval_augment_proposals_mode
         if not self.training and targets is not None and mode is not None:
@@ -335,6 +356,71 @@ class MaskRCNN(_MaskRCNN):
             losses = {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
         return boxes, losses
 
+    def _filter_proposals(self, proposals, objectness, image_sizes, num_anchors_per_level):
+        """tv rpn.py filter_proposals (called from reference mask_rcnn.py:249): per-level top-k, clip, drop small /
+        low-score boxes, per-level NMS, keep post_nms_top_n by score.  NMS runs as ONE segmented launch over all
+        (image, level) pairs (nms.cu); invalid boxes are zeroed in place (zero area: IoU 0, suppress nothing) so
+        that segments keep their static top-k sizes."""
+        rpn = self.rpn
+        N = proposals.shape[0]
+        device = proposals.device
+        objectness = objectness.detach().reshape(N, -1)
+        idx, sizes, offset = [], [], 0
+        for ob in objectness.split(num_anchors_per_level, 1):
+            k = min(rpn.pre_nms_top_n(), ob.shape[1])
+            idx.append(ob.topk(k, dim=1)[1] + offset)          # sorted by descending score inside the level
+            sizes.append(k)
+            offset += ob.shape[1]
+        top_n_idx = torch.cat(idx, dim=1)
+        batch_idx = torch.arange(N, device=device)[:, None]
+        prob = torch.sigmoid(objectness[batch_idx, top_n_idx])
+        props = proposals[batch_idx, top_n_idx]
+        Ktot = top_n_idx.shape[1]
+        key = (N, tuple(sizes), str(device))
+        if getattr(self, "_seg_cache_key", None) != key:
+            offs = [0]
+            for _ in range(N):
+                for k in sizes:
+                    offs.append(offs[-1] + k)
+            self._seg_cache = torch.tensor(offs, dtype=torch.int32, device=device)
+            self._seg_cache_key = key
+        hmax = torch.tensor([s[0] for s in image_sizes], device=device, dtype=props.dtype)[:, None]
+        wmax = torch.tensor([s[1] for s in image_sizes], device=device, dtype=props.dtype)[:, None]
+        x1 = torch.minimum(props[..., 0].clamp(min=0), wmax)
+        y1 = torch.minimum(props[..., 1].clamp(min=0), hmax)
+        x2 = torch.minimum(props[..., 2].clamp(min=0), wmax)
+        y2 = torch.minimum(props[..., 3].clamp(min=0), hmax)
+        valid = ((x2 - x1) >= rpn.min_size) & ((y2 - y1) >= rpn.min_size) & (prob >= rpn.score_thresh)
+        clipped = torch.stack([x1, y1, x2, y2], dim=-1)
+        nms_in = (clipped * valid[..., None]).reshape(N * Ktot, 4).contiguous()
+        flags = K.nms_segments(nms_in, self._seg_cache, N * len(sizes), max(sizes), rpn.nms_thresh)
+        flags = flags.view(N, Ktot).bool() & valid
+        ranked = torch.where(flags, prob, torch.full_like(prob, -1.0))
+        order = ranked.argsort(dim=1, descending=True, stable=True)
+        counts = flags.sum(dim=1).tolist()                        # one host sync for the batch
+        post = rpn.post_nms_top_n()
+        final_boxes, final_scores = [], []
+        for i in range(N):
+            keep = order[i, :min(counts[i], post)]
+            final_boxes.append(clipped[i, keep])
+            final_scores.append(prob[i, keep])
+        return final_boxes, final_scores
+
+    def _nms_by_label(self, boxes, scores, labels, thresh):
+        """batched_nms semantics (one NMS per label), result sorted by descending score."""
+        n = boxes.shape[0]
+        if n == 0:
+            return torch.zeros((0,), dtype=torch.int64, device=boxes.device)
+        o1 = scores.argsort(descending=True, stable=True)
+        o2 = labels[o1].argsort(stable=True)
+        order = o1[o2]                                            # grouped by label, descending score inside
+        nlab = self.num_classes
+        offs = torch.zeros(nlab + 1, dtype=torch.int32, device=boxes.device)
+        offs[1:] = torch.bincount(labels, minlength=nlab)[:nlab].cumsum(0).to(torch.int32)
+        flags = K.nms_segments(boxes[order].to(torch.float32).contiguous(), offs, nlab, n, thresh).bool()
+        kept = order[flags]
+        return kept[scores[kept].argsort(descending=True, stable=True)]
+
     # ---- RoI heads (reference mask_rcnn.py:95-214, 347-420) -------------------------------------
     _SCALES = (1 / 4, 1 / 8, 1 / 16, 1 / 32)
 
@@ -362,7 +448,7 @@ class MaskRCNN(_MaskRCNN):
             boxes, scores, labels = boxes[inds], scores[inds], labels[inds]
             keep = box_ops.remove_small_boxes(boxes, min_size=1e-2)
             boxes, scores, labels = boxes[keep], scores[keep], labels[keep]
-            keep = box_ops.batched_nms(boxes, scores, labels, rh.nms_thresh)
+            keep = self._nms_by_label(boxes, scores, labels, rh.nms_thresh)
             keep = keep[:rh.detections_per_img]
             all_boxes.append(boxes[keep])
             all_scores.append(scores[keep])
@@ -460,6 +546,8 @@ class MaskRCNN(_MaskRCNN):
         if self.training and targets is None:
             raise ValueError("targets should not be None in training mode")
         B, _, h, w = inputs.shape
+        K.zero_pool.reset()          # one zeroed block per forward(+backward) serves all accumulate-into outputs
+        self._prepare_operands()
         x8, targets_t, (oh, ow), (Hp, Wp) = self._transform(inputs, targets)
         image_sizes = [(oh, ow)] * B
         image_shape = (B, 3, Hp, Wp)

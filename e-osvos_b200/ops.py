@@ -55,70 +55,130 @@ def clear_prep_cache():
     _prep_cache.clear()
 
 
-def _permute_to(src, shape, dims, sstride, dtype=ACT):
-    out = torch.empty(shape, device=src.device, dtype=dtype)
-    dstride = [1, 1, 1, 1]
+def _contig_strides(dims):
+    ds = [1, 1, 1, 1]
     for i in (2, 1, 0):
-        dstride[i] = dstride[i + 1] * dims[i + 1]
-    K.permute_cast(src, out, dims, sstride, dstride)
-    return out
+        ds[i] = ds[i + 1] * dims[i + 1]
+    return ds
+
+
+# kind -> (w) -> list of (out_shape, dims, src strides, dst strides): the tensor-core operand layouts of a parameter
+def _spec_conv_f(w):
+    """fp32 [O,I,KH,KW] -> [O,KH,KW,I] (fprop B operand)."""
+    O, I, KH, KW = w.shape
+    T = KH * KW
+    d = (1, O, T, I)
+    return [((O, KH, KW, I), d, (0, I * T, 1, T), _contig_strides(d))]
+
+
+def _spec_conv_t(w):
+    """fp32 [O,I,KH,KW] -> [I,KH,KW,O] (dgrad B operand)."""
+    O, I, KH, KW = w.shape
+    T = KH * KW
+    d = (1, I, T, O)
+    return [((I, KH, KW, O), d, (0, T, 1, I * T), _contig_strides(d))]
+
+
+def _spec_linear_f(inner):
+    def f(w):
+        """fp32 [O,K] -> [O,1,1,K]; with inner=C the K axis is re-ordered (c, s) -> (s, c) (fc6 eats NHWC pooling)."""
+        O, Kd = w.shape
+        if inner:
+            C, S = inner, Kd // inner
+            d = (1, O, S, C)
+            return [((O, 1, 1, Kd), d, (0, Kd, 1, S), _contig_strides(d))]
+        d = (1, 1, O, Kd)
+        return [((O, 1, 1, Kd), d, (0, 0, Kd, 1), _contig_strides(d))]
+    return f
+
+
+def _spec_linear_t(inner):
+    def f(w):
+        """fp32 [O,K] -> [K,1,1,O] (dgrad operand), same K re-ordering."""
+        O, Kd = w.shape
+        if inner:
+            C, S = inner, Kd // inner
+            d = (1, S, C, O)
+            return [((Kd, 1, 1, O), d, (0, 1, S, Kd), _contig_strides(d))]
+        d = (1, 1, Kd, O)
+        return [((Kd, 1, 1, O), d, (0, 0, 1, Kd), _contig_strides(d))]
+    return f
+
+
+def _spec_deconv(w):
+    """fp32 [I,O,2,2] -> fwd operand [(dy,dx,o)][i] and dgrad operand [i][(dy,dx,o)]."""
+    I, O = w.shape[:2]
+    d1, d2 = (1, 4, O, I), (1, I, 4, O)
+    return [((4 * O, I), d1, (0, 1, 4, 4 * O), _contig_strides(d1)), ((I, 4 * O), d2, (0, 4 * O, 1, 4), _contig_strides(d2))]
+
+
+def _spec_stem(w):
+    """fp32 [O,3,7,7] -> [O,1,1,Kp] with k = t*3 + c, zero padded to a multiple of 64."""
+    O, I, KH, KW = w.shape
+    T = KH * KW
+    Kp = ((T * I + 63) // 64) * 64
+    return [((O, 1, 1, Kp), (1, O, T, I), (0, I * T, 1, T), (0, Kp, I, 1))]
+
+
+def _spec_for(kind):
+    if kind == "f":
+        return _spec_conv_f
+    if kind == "t":
+        return _spec_conv_t
+    if kind == "dc":
+        return _spec_deconv
+    if kind == "stem":
+        return _spec_stem
+    if kind[0] == "lf":
+        return _spec_linear_f(kind[1])
+    if kind[0] == "lt":
+        return _spec_linear_t(kind[1])
+    raise KeyError(kind)
+
+
+def prep_many(requests):
+    """requests: iterable of (parameter, kind).  Builds every missing operand layout with ONE kernel launch."""
+    jobs, pending = [], []
+    for w, kind in requests:
+        if _cache_get(w, kind) is not None:
+            continue
+        wd = w.detach()
+        if not wd.is_contiguous():
+            wd = wd.contiguous()
+        outs = []
+        for shape, dims, ss, ds in _spec_for(kind)(wd):
+            alloc = torch.zeros if kind == "stem" else torch.empty
+            out = alloc(shape, device=wd.device, dtype=ACT)
+            jobs.append((wd, out, dims, ss, ds))
+            outs.append(out)
+        pending.append((w, kind, outs[0] if len(outs) == 1 else tuple(outs)))
+    K.permute_cast_multi(jobs)
+    for w, kind, val in pending:
+        _cache_put(w, kind, val)
+
+
+def _prep_one(w, kind):
+    hit = _cache_get(w, kind)
+    if hit is None:
+        prep_many([(w, kind)])
+        hit = _cache_get(w, kind)
+    return hit
 
 
 def prep_conv_w(w):
-    """fp32 [O,I,KH,KW] -> bf16 [O,KH,KW,I] (fprop B operand)."""
-    hit = _cache_get(w, "f")
-    if hit is not None:
-        return hit
-    wd = w.detach().contiguous()
-    O, I, KH, KW = wd.shape
-    T = KH * KW
-    out = _permute_to(wd, (O, KH, KW, I), (1, O, T, I), (0, I * T, 1, T))
-    return _cache_put(w, "f", out)
+    return _prep_one(w, "f")
 
 
 def prep_conv_wt(w):
-    """fp32 [O,I,KH,KW] -> bf16 [I,KH,KW,O] (dgrad B operand)."""
-    hit = _cache_get(w, "t")
-    if hit is not None:
-        return hit
-    wd = w.detach().contiguous()
-    O, I, KH, KW = wd.shape
-    T = KH * KW
-    out = _permute_to(wd, (I, KH, KW, O), (1, I, T, O), (0, T, 1, I * T))
-    return _cache_put(w, "t", out)
+    return _prep_one(w, "t")
 
 
 def prep_linear_w(w, inner=0):
-    """fp32 [O, K] -> bf16 [O,1,1,K]; with inner=C the K axis is re-ordered (c, s) -> (s, c)
-    (fc6 consumes NHWC-pooled features)."""
-    kind = ("lf", inner)
-    hit = _cache_get(w, kind)
-    if hit is not None:
-        return hit
-    wd = w.detach().contiguous()
-    O, Kd = wd.shape
-    if inner:
-        C, S = inner, Kd // inner
-        out = _permute_to(wd, (O, 1, 1, Kd), (1, O, S, C), (0, Kd, 1, S))
-    else:
-        out = _permute_to(wd, (O, 1, 1, Kd), (1, 1, O, Kd), (0, 0, Kd, 1))
-    return _cache_put(w, kind, out)
+    return _prep_one(w, ("lf", inner))
 
 
 def prep_linear_wt(w, inner=0):
-    """fp32 [O, K] -> bf16 [K,1,1,O] (dgrad operand), same K re-ordering as prep_linear_w."""
-    kind = ("lt", inner)
-    hit = _cache_get(w, kind)
-    if hit is not None:
-        return hit
-    wd = w.detach().contiguous()
-    O, Kd = wd.shape
-    if inner:
-        C, S = inner, Kd // inner
-        out = _permute_to(wd, (Kd, 1, 1, O), (1, S, C, O), (0, 1, S, Kd))
-    else:
-        out = _permute_to(wd, (Kd, 1, 1, O), (1, 1, Kd, O), (0, 0, 1, Kd))
-    return _cache_put(w, kind, out)
+    return _prep_one(w, ("lt", inner))
 
 
 def _fused_head_w(ws, pad_to):
@@ -187,7 +247,7 @@ class ConvGnFn(torch.autograd.Function):
     def forward(ctx, x, w, gamma, beta, res, stride, pad, relu):
         wf = prep_conv_w(w)
         N = x.shape[0]
-        sums = torch.zeros((N, 32, 2), device=x.device, dtype=torch.float32)
+        sums = K.zero_pool.take((N, 32, 2), x.device)
         z = K.conv2d_fprop(x, wf, stride=stride, pad=pad, gn_sum=sums)
         g, b = gamma.detach(), beta.detach()
         y = K.gn_apply(z, sums, g, b, res, relu=relu)
@@ -220,17 +280,7 @@ def conv_gn(x, w, gamma, beta, res=None, stride=1, pad=0, relu=True):
 # stem: 7x7/2 conv (explicit im2col, K = 147 -> 192) -> GN -> ReLU.  No data gradient.
 # --------------------------------------------------------------------------------------------
 def _prep_stem_w(w):
-    hit = _cache_get(w, "stem")
-    if hit is not None:
-        return hit
-    wd = w.detach().contiguous()
-    O, I, KH, KW = wd.shape
-    T = KH * KW
-    Kp = ((T * I + 63) // 64) * 64
-    out = torch.zeros((O, 1, 1, Kp), device=wd.device, dtype=ACT)
-    # dst[o][t*I + c] = src[o][c][t]
-    K.permute_cast(wd, out, (1, O, T, I), (0, I * T, 1, T), (0, Kp, I, 1))
-    return _cache_put(w, "stem", out)
+    return _prep_one(w, "stem")
 
 
 class StemFn(torch.autograd.Function):
@@ -241,7 +291,7 @@ class StemFn(torch.autograd.Function):
         Kp = wf.shape[-1]
         N = x8.shape[0]
         col, Ho, Wo = K.im2col_stem(x8, KH, KW, 2, 3, Kp)
-        sums = torch.zeros((N, 32, 2), device=x8.device, dtype=torch.float32)
+        sums = K.zero_pool.take((N, 32, 2), x8.device)
         z = K.conv2d_fprop(col.view(N, 1, Ho * Wo, Kp), wf, gn_sum=sums).view(N, Ho, Wo, O)
         y = K.gn_apply(z, sums, gamma.detach(), beta.detach(), None, relu=True)
         ctx.save_for_backward(col, w, gamma, beta, z, sums)
@@ -256,7 +306,7 @@ class StemFn(torch.autograd.Function):
                                              alpha=_inv_scale())
         dw = None
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros_like(w, dtype=torch.float32)
+            dw = K.zero_pool.take(tuple(w.shape), w.device)
             T = KH * KW
             # column n = t*I + c  ->  torch offset c*T + t
             K.gemm_wgrad(col, dz.view(-1, O), dw, s_m=I * T, n_inner=I, s_n_inner=T, s_n_outer=1, alpha=_inv_scale())
@@ -329,7 +379,7 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = K.conv2d_dgrad(dy.view(1, 1, R, O), prep_linear_wt(w, inner), (1, R)).view(R, Kd)
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros((O, Kd), device=x.device, dtype=torch.float32)
+            dw = K.zero_pool.take((O, Kd), x.device)
             if inner:
                 K.gemm_wgrad(x, dy, dw, s_m=Kd, n_inner=inner, s_n_inner=Kd // inner, s_n_outer=1, alpha=_inv_scale())
             else:
@@ -378,7 +428,7 @@ class HeadFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.conv2d_dgrad(dyp.view(1, 1, rows, 64), wt, (1, rows)).view(rows, Kd)
-        dwf = torch.zeros((64, Kd), device=x.device, dtype=torch.float32)
+        dwf = K.zero_pool.take((64, Kd), x.device)
         K.gemm_wgrad(x, dyp, dwf, s_m=Kd, alpha=_inv_scale())
         dbf = dy.sum(0)
         dws, dbs = [], []
@@ -399,15 +449,7 @@ def fused_heads(x, ws, bs):
 # 2x2/2 transposed conv (+bias) (+ReLU)
 # --------------------------------------------------------------------------------------------
 def _prep_deconv(w):
-    hit = _cache_get(w, "dc")
-    if hit is not None:
-        return hit
-    wd = w.detach().contiguous()
-    I, O = wd.shape[:2]
-    # fwd operand [(dy,dx,o)][i]: src[i][o][g] ; dgrad operand [i][(dy,dx,o)]
-    wf = _permute_to(wd, (4 * O, I), (1, 4, O, I), (0, 1, 4, 4 * O))
-    wt = _permute_to(wd, (I, 4 * O), (1, I, 4, O), (0, 4 * O, 1, 4))
-    return _cache_put(w, "dc", (wf, wt))
+    return _prep_one(w, "dc")
 
 
 class Deconv2x2Fn(torch.autograd.Function):

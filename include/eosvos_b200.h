@@ -95,6 +95,12 @@ int eosvos_mask_paste_threshold(const float* logits, const int* det_of_chan, con
                                 int W, int M, int Cc, float thresh, eosvos_stream_t stream);
 int eosvos_mask_to_bbox(const float* target, int* stats, int B, int K, int H, int W, eosvos_stream_t stream);
 
+/* ---- K5: segmented NMS, one segment per (image, FPN level) or per image (reference: mask_rcnn.py:249 ->
+ *      tv rpn.py filter_proposals; mask_rcnn.py:392 -> torchvision::nms) */
+long long eosvos_nms_scratch_bytes(int num_segments, int max_seg);
+int eosvos_nms_segments(const float* boxes, const int* seg_off, int num_segments, int max_seg, float thresh,
+                        void* scratch, unsigned char* keep, eosvos_stream_t stream);
+
 /* ---- K9: MetaOptimizer update (reference: meta_optim.py:177-214, meta_model.py:78-80) */
 int eosvos_meta_update_chunk_elems(void);
 int eosvos_meta_update(const long long* table_dev, const int* chunks_dev, int num_chunks, int use_log,
@@ -107,6 +113,10 @@ int eosvos_radam_step(float* p, const float* g, float* m, float* v, long long n,
 /* ---- helpers around the kernels (reference: tv transform.py:119-160 etc., see csrc/misc.cu) */
 int eosvos_permute_cast(const void* src, void* dst, const long long* dims, const long long* sstride,
                         const long long* dstride, int src_dtype, int dst_dtype, eosvos_stream_t stream);
+/* all fp32 -> 16-bit operand layouts of one iteration in one launch; table int64 [T][14] =
+ * (src, dst, dims[4], src strides[4], dst strides[4]), chunks int32 [n][2] = (tensor, chunk index) */
+int eosvos_permute_cast_multi_chunk_elems(void);
+int eosvos_permute_cast_multi(const long long* table_dev, const int* chunks_dev, int num_chunks, eosvos_stream_t stream);
 int eosvos_transform(const float* img, void* out, int B, int h, int w, int oh, int ow, int Hp, int Wp, int Cs,
                      const float* mean3, const float* std3, eosvos_stream_t stream);
 int eosvos_mask_resize_nearest(const uint8_t* src, uint8_t* dst, int G, int h, int w, int oh, int ow,

@@ -366,3 +366,27 @@ def test_transform_and_stem():
     assert rel_err(nchw(u.float().cpu()), F.avg_pool2d(x.detach()[:, :, :22, :30], 2) * 4) < 4e-3
     c = k.colsum(xd.view(-1, 64))
     assert rel_err(c.cpu(), x.detach().sum((0, 2, 3))) < 1e-4
+
+
+def test_nms_segments_matches_torchvision():
+    """Segmented NMS == torchvision CPU nms run independently per segment (exact index sets)."""
+    import torchvision
+    g = torch.Generator().manual_seed(31)
+    sizes = [2000, 2000, 1500, 700, 63, 1, 0, 130]
+    boxes, offs = [], [0]
+    for n in sizes:
+        ctr = torch.rand(n, 2, generator=g) * torch.tensor([1333.0, 749.0])
+        wh = torch.exp(torch.rand(n, 2, generator=g) * 4.5) + 1
+        b = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+        if n:
+            b[::7] = b[:1].clone()                # clusters of identical boxes
+        boxes.append(b)
+        offs.append(offs[-1] + n)
+    allb = torch.cat(boxes).contiguous()
+    flags = K().nms_segments(allb.to(dev()), torch.tensor(offs, dtype=torch.int32, device=dev()), len(sizes), max(sizes),
+                             0.7).cpu().bool()
+    for i, n in enumerate(sizes):
+        scores = torch.arange(n, 0, -1, dtype=torch.float32)     # already sorted: descending score = position
+        ref = torchvision.ops.nms(boxes[i], scores, 0.7) if n else torch.zeros(0, dtype=torch.int64)
+        got = torch.nonzero(flags[offs[i]:offs[i + 1]]).flatten()
+        assert torch.equal(got, ref.sort()[0]), (i, n, got.numel(), ref.numel())

@@ -18,9 +18,13 @@ E.run_frames(model, iter(frames), tgt)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 torch.cuda.cudart().cudaProfilerStart()
-E.finetune(model, opt, lambda e: db[e % 4], int(os.environ.get("ITERS", "1")), 1, 2)
+ts = []
+def tick(e, l):
+    torch.cuda.synchronize(); ts.append(time.perf_counter())
+E.finetune(model, opt, lambda e: db[e % 4], int(os.environ.get("ITERS", "1")), 1, 2, on_iter=tick if os.environ.get("TICK") else None)
 torch.cuda.synchronize()
 t1 = time.perf_counter()
+if ts: print("per-iter ms:", [round(1e3 * (b - a), 1) for a, b in zip([t0] + ts[:-1], ts)])
 E.run_frames(model, iter(frames), tgt)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
