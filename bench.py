@@ -10,8 +10,9 @@ One STEP = one online-adaptation block of the e-OSVOS-100-OnA schedule on one 85
 MetaOptimizer update) followed by FRAMES_PER_STEP inference frames with target propagation -- the 10:3
 iteration:frame ratio of a 70-frame video under e-OSVOS-100-OnA (230 iterations, 69 frames).
 `value` = fine-tune iterations/s (device-resident inputs); `frames_per_s` = inference object-frames/s;
-`e2e` = the same block driven through the public API from pinned HOST buffers (H2D of every batch/frame,
-D2H of every loss/probability map inside the timed region).  With N > 1 every rank runs its own objects
+`e2e` = the same block driven through the public API from HOST buffers: first frame + every inference frame H2D from
+pinned memory, first-frame augmentation per iteration (random draws + label warp on the host, bicubic image warp on
+the GPU), every loss and probability map read back (D2H) inside the timed region.  With N > 1 every rank runs its own objects
 (weak scaling, no data-path collective); time = max over ranks.
 """
 import argparse
@@ -311,9 +312,17 @@ def main():
     def dev_frame(i):
         return dev_frames[i]
 
+    from eosvos_b200.util import augment
+    pin_frame0 = fr[0].contiguous().pin_memory()
+    gt0_np = gt0.numpy()
+    e2e_state = {}
+
     def host_batch(i):
-        a, b = pin_batches[i % len(pin_batches)]
-        return a.to(device, non_blocking=True), b.to(device, non_blocking=True)
+        # end to end: frame 0 goes H2D once per step (block); every iteration draws fresh random flips/rotations/
+        # scales (host, reference RNG order), warps the label on the host (nearest) and the image on the GPU (bicubic)
+        if i % ITERS_PER_STEP == 1 or "aug" not in e2e_state:
+            e2e_state["aug"] = augment.DeviceAugmenter(pin_frame0.to(device, non_blocking=True), gt0_np)
+        return e2e_state["aug"].batch(BATCH)
 
     def host_frame(i):
         return pin_frames[i].to(device, non_blocking=True)
@@ -362,7 +371,8 @@ def main():
     if rank == 0:
         n_it = args.steps * ITERS_PER_STEP * world
         n_fr = args.steps * FRAMES_PER_STEP * world
-        h2d = ITERS_PER_STEP * (batches[0][0].numel() + batches[0][1].numel()) * 4 + FRAMES_PER_STEP * fr[0:1].numel() * 4
+        h2d = (fr[0].numel() * 4 + ITERS_PER_STEP * (batches[0][1].numel() * 4 + BATCH * 28)
+               + FRAMES_PER_STEP * fr[0:1].numel() * 4)
         d2h = ITERS_PER_STEP * 4 + FRAMES_PER_STEP * H * W * 4
         line = {
             "metric": METRIC, "value": n_it / (ft_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -490,3 +490,68 @@ extern "C" int eosvos_permute_cast_multi(const long long* table_dev, const int* 
   eosvos::permute_cast_multi_kernel<<<num_chunks, 256, 0, stream>>>(table_dev, chunks_dev);
   return eosvos::check_launch("permute_cast_multi_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------
+// First-frame augmentation on the device: horizontal flip + rotate/scale about the centre with bicubic
+// (a = -0.75, constant-0 border) sampling -- the image half of the reference's RandomHorizontalFlip +
+// RandomScaleNRotate (src/data/custom_transforms.py:40-51,188-211; cv2.warpAffine INTER_CUBIC).  The label half
+// (nearest) and the random draws / rejection loop stay on the host (util/augment.py).  cv2 quantises source
+// coordinates to 1/32 px; this kernel uses exact float coordinates.
+// src [3][H][W] fp32, minv [B][6] (dst -> src affine), flip [B]; dst [B][3][H][W] fp32.
+// ---------------------------------------------------------------------------------------------
+namespace eosvos {
+__device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  w[0] = ((A * (t + 1.f) - 5.f * A) * (t + 1.f) + 8.f * A) * (t + 1.f) - 4.f * A;
+  w[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+  w[2] = ((A + 2.f) * (1.f - t) - (A + 3.f)) * (1.f - t) * (1.f - t) + 1.f;
+  w[3] = 1.f - w[0] - w[1] - w[2];
+}
+
+__global__ void __launch_bounds__(256)
+affine_warp_cubic_kernel(const float* __restrict__ src, const float* __restrict__ minv, const int* __restrict__ flip,
+                         float* __restrict__ dst, int B, int H, int W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W) return;
+  const int x = (int)(idx % W);
+  const int y = (int)((idx / W) % H);
+  const int b = (int)(idx / ((long long)W * H));
+  const float* m = minv + b * 6;
+  const float sx = m[0] * x + m[1] * y + m[2];
+  const float sy = m[3] * x + m[4] * y + m[5];
+  const int ix = (int)floorf(sx), iy = (int)floorf(sy);
+  float wx[4], wy[4];
+  cubic_w(sx - (float)ix, wx);
+  cubic_w(sy - (float)iy, wy);
+  const bool fl = flip[b] != 0;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int yy = iy - 1 + j;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int xx = ix - 1 + i;
+      if (xx < 0 || xx >= W) continue;
+      if (fl) xx = W - 1 - xx;
+      const float w = wy[j] * wx[i];
+      const size_t o = (size_t)yy * W + xx;
+      acc[0] += w * src[o];
+      acc[1] += w * src[(size_t)H * W + o];
+      acc[2] += w * src[2 * (size_t)H * W + o];
+    }
+  }
+  const size_t po = (size_t)y * W + x;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) dst[((size_t)b * 3 + c) * H * W + po] = acc[c];
+}
+}  // namespace eosvos
+
+extern "C" int eosvos_affine_warp_cubic(const float* src, const float* minv, const int* flip, float* dst, int B, int H,
+                                        int W, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(src && minv && flip && dst && B > 0, "affine_warp_cubic: bad arguments");
+  const long long total = (long long)B * H * W;
+  eosvos::affine_warp_cubic_kernel<<<eosvos::blocks_for(total), 256, 0, stream>>>(src, minv, flip, dst, B, H, W);
+  return eosvos::check_launch("affine_warp_cubic_kernel");
+}

@@ -421,6 +421,17 @@ def permute_cast_multi(jobs):
     call("eosvos_permute_cast_multi", _ptr(table), _ptr(hit[0]), hit[1], _stream())
 
 
+def affine_warp_cubic(src_chw, minv, flip, B):
+    """src [3,H,W] fp32, minv [B,6] fp32 (dst->src), flip [B] int32 -> [B,3,H,W] fp32 (bicubic, zero border)."""
+    _chk(src_chw, torch.float32, "src")
+    _chk(minv, torch.float32, "minv")
+    _chk(flip, torch.int32, "flip")
+    _, H, W = src_chw.shape
+    out = torch.empty((B, 3, H, W), device=src_chw.device, dtype=torch.float32)
+    call("eosvos_affine_warp_cubic", _ptr(src_chw), _ptr(minv), _ptr(flip), _ptr(out), B, H, W, _stream())
+    return out
+
+
 def nchw_to_nhwc_bf16(x):
     """fp32/bf16 [N,C,H,W] -> bf16 [N,H,W,C]."""
     N, C, H, W = x.shape

@@ -27,12 +27,14 @@ class _FusedUpdateFn(torch.autograd.Function):
         ps = [p.detach().contiguous() for p in params]
         gs = [g.detach().contiguous() for g in grads]
         ls = [l.detach().contiguous() for l in lrs]
-        total = sum(p.numel() for p in ps)
-        arena = torch.empty(total, device=ps[0].device, dtype=torch.float32)
-        outs, off = [], 0
+        # one arena for all updated tensors; every tensor starts on a 256-byte boundary so the kernel's float4 path
+        # applies to all of them (an unaligned view would fall back to scalar accesses)
+        offs, total = [], 0
         for p in ps:
-            outs.append(arena[off:off + p.numel()].view(p.shape))
-            off += p.numel()
+            offs.append(total)
+            total += (p.numel() + 63) // 64 * 64
+        arena = torch.empty(total, device=ps[0].device, dtype=torch.float32)
+        outs = [arena[o:o + p.numel()].view(p.shape) for o, p in zip(offs, ps)]
         K.meta_update(K.MetaUpdatePlan(ps, gs, ls, outs), use_log)
         ctx.use_log, ctx.n = use_log, n
         ctx.save_for_backward(*gs, *ls)

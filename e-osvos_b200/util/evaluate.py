@@ -75,7 +75,8 @@ def finetune(model, meta_optim, batch_fn, num_iters, seed, round_idx, reset_mode
 
 def evaluate_sequence(model, meta_optim, meta_optim_state_dict, frames, first_label, *, num_epochs_eval,
                       online_adapt_step=0, online_adapt_epochs=10, min_prop=0.5, batch_size=3, seed=1,
-                      random_train_transform=True, reset_model_mode='FIRST_STEP', device=None, timers=None):
+                      random_train_transform=True, reset_model_mode='FIRST_STEP', device=None, timers=None,
+                      device_augment=True):
     """frames: float32 [T,3,H,W] in [0,1] (host, ideally pinned); first_label: [H,W] object ids.
     Returns (pred uint8 [T,H,W], stats dict)."""
     device = device or next(model.parameters()).device
@@ -129,7 +130,12 @@ def evaluate_sequence(model, meta_optim, meta_optim_state_dict, frames, first_la
 
             iters = num_epochs_eval if k == 0 else online_adapt_epochs
 
-            if k == 0:
+            if k == 0 and random_train_transform and device_augment:
+                dev_aug = augment.DeviceAugmenter(to_dev(frames[0]), gt0_np)
+
+                def batch_fn(epoch):
+                    return dev_aug.batch(batch_size)
+            elif k == 0:
                 def batch_fn(epoch):
                     imgs, gts = [], []
                     for _ in range(batch_size):

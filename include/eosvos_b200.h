@@ -117,6 +117,9 @@ int eosvos_permute_cast(const void* src, void* dst, const long long* dims, const
  * (src, dst, dims[4], src strides[4], dst strides[4]), chunks int32 [n][2] = (tensor, chunk index) */
 int eosvos_permute_cast_multi_chunk_elems(void);
 int eosvos_permute_cast_multi(const long long* table_dev, const int* chunks_dev, int num_chunks, eosvos_stream_t stream);
+/* device half of the first-frame augmentation (reference: src/data/custom_transforms.py:40-51,188-211) */
+int eosvos_affine_warp_cubic(const float* src, const float* minv, const int* flip, float* dst, int B, int H, int W,
+                             eosvos_stream_t stream);
 int eosvos_transform(const float* img, void* out, int B, int h, int w, int oh, int ow, int Hp, int Wp, int Cs,
                      const float* mean3, const float* std3, eosvos_stream_t stream);
 int eosvos_mask_resize_nearest(const uint8_t* src, uint8_t* dst, int G, int h, int w, int oh, int ow,

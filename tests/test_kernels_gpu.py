@@ -390,3 +390,24 @@ def test_nms_segments_matches_torchvision():
         ref = torchvision.ops.nms(boxes[i], scores, 0.7) if n else torch.zeros(0, dtype=torch.int64)
         got = torch.nonzero(flags[offs[i]:offs[i + 1]]).flatten()
         assert torch.equal(got, ref.sort()[0]), (i, n, got.numel(), ref.numel())
+
+
+def test_device_augmentation_matches_cv2_family():
+    """GPU bicubic flip+rotate/scale vs cv2.warpAffine(INTER_CUBIC): same transform; cv2 snaps source coordinates
+    to a 1/32-px grid, so agreement is to ~1e-2 on a smooth image (mean abs < 2e-3), labels identical."""
+    import random
+    import numpy as np
+    from eosvos_b200.util import augment, synthetic
+    frames, labels = synthetic.make_video(3, 1, 240, 427, 1)
+    img = frames[0].astype(np.float32) / 255.0
+    gt = (labels[0] == 1).astype(np.float32)
+    random.seed(7)
+    ref = [augment.augment_first_frame(img, gt) for _ in range(3)]
+    random.seed(7)
+    aug = augment.DeviceAugmenter(torch.from_numpy(img.transpose(2, 0, 1).copy()).to(dev()), gt)
+    x, g = aug.batch(3)
+    for b in range(3):
+        ri = torch.from_numpy(np.ascontiguousarray(ref[b][0].transpose(2, 0, 1)))
+        assert torch.equal(g[b, 0].cpu(), torch.from_numpy(np.ascontiguousarray(ref[b][1])))
+        d = (x[b].cpu() - ri).abs()
+        assert d.mean().item() < 2e-3 and d.max().item() < 0.25, (d.mean().item(), d.max().item())
