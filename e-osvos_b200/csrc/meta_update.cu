@@ -74,14 +74,15 @@ meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ 
 //   p -= wd*lr*p ; p -= step_size * m / (sqrt(v) + eps)   [n_sma >= 5]   or   p -= step_size * m
 __global__ void __launch_bounds__(256)
 radam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             long long n, float gscale, float clip, float beta1, float beta2, float eps, float lr, float wd,
-             float step_size, int rectified, float clamp_lo, float clamp_hi, int do_clamp) {
+             long long n, float gscale, float clip, float beta1, float beta2, float omb1, float omb2, float eps, float lr,
+             float wd, float step_size, int rectified, float clamp_lo, float clamp_hi, int do_clamp) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float gg = g[i] * gscale;
   if (clip > 0.f) gg = fminf(fmaxf(gg, -clip), clip);
-  const float mm = beta1 * m[i] + (1.f - beta1) * gg;
-  const float vv = beta2 * v[i] + (1.f - beta2) * gg * gg;
+  // omb = 1 - beta rounded from double on the host, as the reference's Python scalars are (radam.py:60-61)
+  const float mm = __fadd_rn(__fmul_rn(beta1, m[i]), __fmul_rn(omb1, gg));
+  const float vv = __fadd_rn(__fmul_rn(beta2, v[i]), __fmul_rn(__fmul_rn(omb2, gg), gg));
   m[i] = mm;
   v[i] = vv;
   float pp = p[i];
@@ -110,13 +111,14 @@ extern "C" int eosvos_meta_update(const long long* table_dev, const int* chunks_
 }
 
 extern "C" int eosvos_radam_step(float* p, const float* g, float* m, float* v, long long n, float gscale, float clip,
-                                 float beta1, float beta2, float eps, float lr, float wd, float step_size,
-                                 int rectified, float clamp_lo, float clamp_hi, int do_clamp,
+                                 float beta1, float beta2, float omb1, float omb2, float eps, float lr, float wd,
+                                 float step_size, int rectified, float clamp_lo, float clamp_hi, int do_clamp,
                                  eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (n == 0) return 0;
   EOSVOS_REQUIRE(p && g && m && v, "radam_step: null pointer");
-  radam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, g, m, v, n, gscale, clip, beta1, beta2, eps, lr, wd,
-                                                               step_size, rectified, clamp_lo, clamp_hi, do_clamp);
+  radam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, g, m, v, n, gscale, clip, beta1, beta2, omb1, omb2, eps,
+                                                               lr, wd, step_size, rectified, clamp_lo, clamp_hi,
+                                                               do_clamp);
   return check_launch("radam_kernel");
 }

@@ -375,7 +375,7 @@ def radam_step(p, g, m, v, *, gscale, clip, beta1, beta2, eps, lr, wd, step_size
         _chk(t, torch.float32, "radam operand")
     lo, hi, do = (clamp[0], clamp[1], 1) if clamp is not None else (0.0, 0.0, 0)
     call("eosvos_radam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), gscale, clip if clip else 0.0, beta1,
-         beta2, eps, lr, wd, step_size, 1 if rectified else 0, lo, hi, do, _stream())
+         beta2, 1 - beta1, 1 - beta2, eps, lr, wd, step_size, 1 if rectified else 0, lo, hi, do, _stream())
 
 
 # ------------------------------------------------------------------------------------------- misc

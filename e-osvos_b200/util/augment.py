@@ -56,13 +56,17 @@ class DeviceAugmenter:
         for b in range(batch_size):
             do_flip = random.random() < 0.5
             gt = cv2.flip(self.gt, flipCode=1) if do_flip else self.gt
-            num_labels = len(np.unique(gt))
+
+            def n_ids(a):     # == len(np.unique(a)) for integer-valued label maps, without the sort
+                return int(np.count_nonzero(np.bincount(a.astype(np.uint8).ravel(), minlength=256)))
+
+            num_labels = n_ids(gt)
             while True:
                 rot = (rots[1] - rots[0]) * random.random() - (rots[1] - rots[0]) / 2
                 sc = (scales[1] - scales[0]) * random.random() - (scales[1] - scales[0]) / 2 + 1
                 M = cv2.getRotationMatrix2D((w / 2, h / 2), rot, sc)
                 aug_gt = cv2.warpAffine(gt, M, (w, h), flags=cv2.INTER_NEAREST)
-                if not num_labels > 1 or len(np.unique(aug_gt)) == num_labels:
+                if not num_labels > 1 or n_ids(aug_gt) == num_labels:
                     break
             minv[b] = cv2.invertAffineTransform(M).reshape(6)
             flips[b] = int(do_flip)

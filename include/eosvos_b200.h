@@ -107,8 +107,9 @@ int eosvos_meta_update(const long long* table_dev, const int* chunks_dev, int nu
                        eosvos_stream_t stream);
 /* ---- K10: outer RAdam step of meta-training (reference: radam.py:28-94, train_meta.py:361-373) */
 int eosvos_radam_step(float* p, const float* g, float* m, float* v, long long n, float gscale, float clip, float beta1,
-                      float beta2, float eps, float lr, float wd, float step_size, int rectified, float clamp_lo,
-                      float clamp_hi, int do_clamp, eosvos_stream_t stream);
+                      float beta2, float one_minus_beta1, float one_minus_beta2, float eps, float lr, float wd,
+                      float step_size, int rectified, float clamp_lo, float clamp_hi, int do_clamp,
+                      eosvos_stream_t stream);
 
 /* ---- helpers around the kernels (reference: tv transform.py:119-160 etc., see csrc/misc.cu) */
 int eosvos_permute_cast(const void* src, void* dst, const long long* dims, const long long* sstride,

@@ -286,3 +286,51 @@ def jaccard(pred, gt):
     pred, gt = pred.bool(), gt.bool()
     union = (pred | gt).sum().item()
     return 1.0 if union == 0 else (pred & gt).sum().item() / union
+
+
+def oracle_meta_gradients(model, lrs, train_batch, meta_batch, num_epochs=5):
+    """First-order BPTT of reference src/util/meta_run.py:124-214 in plain torch: theta_{k+1} = theta_k - lr * g_k with
+    g_k detached (meta_optim.py:202-207, second_order False), meta loss after the last step, gradients w.r.t. theta_0
+    and the learning rates.  `model` must hold leaf parameters theta_0; `lrs` leaf tensors (requires_grad)."""
+    slots = [(n_m, module, n_p) for n_m, module in model.named_modules()
+             for n_p, p in module._parameters.items() if p is not None and p.requires_grad]
+    theta0 = [module._parameters[n_p] for _, module, n_p in slots]
+    cur = theta0
+    try:
+        for _ in range(num_epochs):
+            model.train()
+            loss, _ = model(*train_batch)
+            grads = torch.autograd.grad(loss, cur)
+            cur = [p - g.detach() * lr for p, g, lr in zip(cur, grads, lrs)]
+            for (_, module, n_p), t in zip(slots, cur):
+                module._parameters[n_p] = t
+        meta_loss, _ = model(*meta_batch)
+        out = torch.autograd.grad(meta_loss, list(theta0) + list(lrs), allow_unused=True)
+    finally:
+        for (_, module, n_p), t in zip(slots, theta0):
+            module._parameters[n_p] = t
+    n = len(theta0)
+    return meta_loss.detach(), out[:n], out[n:]
+
+
+def radam_reference(p, g, m, v, step, lr, wd, betas=(0.9, 0.999), eps=1e-8):
+    """reference src/util/radam.py:28-94 for one tensor (degenerated_to_sgd=True)."""
+    import math
+    beta1, beta2 = betas
+    v = v * beta2 + (1 - beta2) * g * g
+    m = m * beta1 + (1 - beta1) * g
+    beta2_t = beta2 ** step
+    n_max = 2 / (1 - beta2) - 1
+    n_sma = n_max - 2 * step * beta2_t / (1 - beta2_t)
+    p = p.clone()
+    if n_sma >= 5:
+        ss = math.sqrt((1 - beta2_t) * (n_sma - 4) / (n_max - 4) * (n_sma - 2) / n_sma * n_max / (n_max - 2)) / (1 - beta1 ** step)
+        if wd != 0:
+            p = p + (-wd * lr) * p
+        p = p + (-ss * lr) * m / (v.sqrt() + eps)
+    else:
+        ss = 1.0 / (1 - beta1 ** step)
+        if wd != 0:
+            p = p + (-wd * lr) * p
+        p = p + (-ss * lr) * m
+    return p, m, v
