@@ -132,6 +132,7 @@ static int run_fprop(const AView& av, const int extent[4], const int conv_stride
   p.gn_sum = ep.gn_sum;
   p.gn_cpg = ep.gn_cpg;
   p.gn_dim = ep.gn_dim;
+  p.gn_nimg = ep.gn_sum ? ep.odim[ep.gn_dim] : 0;
   if (ep.gn_sum) EOSVOS_REQUIRE((ep.gn_cpg & (ep.gn_cpg - 1)) == 0, "fprop: GroupNorm channels per group must be a power of two");
   if (ep.ogroup) EOSVOS_REQUIRE(ep.ogroup % bn == 0, "fprop: output group must be a multiple of the column tile");
 

@@ -23,23 +23,10 @@ struct FpropCfg {
   static constexpr int SMEM = 1024 + STAGES * (128 * 128 + BN * 128) + 256;
 };
 
-__device__ __forceinline__ void gn_flush(float* gn_sum, int n_img, int n_first, int grp, float s1, float s2, bool all_same,
-                                         bool valid, int lane) {
-  if (all_same) {
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-    }
-    if (lane == 0) {
-      atomicAdd(gn_sum + ((long long)n_first * 32 + grp) * 2, s1);
-      atomicAdd(gn_sum + ((long long)n_first * 32 + grp) * 2 + 1, s2);
-    }
-  } else if (valid) {
-    atomicAdd(gn_sum + ((long long)n_img * 32 + grp) * 2, s1);
-    atomicAdd(gn_sum + ((long long)n_img * 32 + grp) * 2 + 1, s2);
-  }
-}
+// GroupNorm partial statistics are accumulated per CTA in shared memory across ALL of its tiles and flushed with
+// one global atomic per (image, group) at the end: per-tile global atomics on the 64 * N hot addresses serialise
+// in L2 (measured: 1.07 ms instead of ~60 us for the stem GEMM).
+constexpr int GN_MAXN = 8;   // images kept in the shared accumulator; larger batches fall back to global atomics
 
 template <int BN>
 __global__ void __launch_bounds__(192, FpropCfg<BN>::CTAS_PER_SM)
@@ -59,6 +46,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull = empty + STAGES;    // [2]
   uint64_t* tempty = tfull + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  __shared__ float gn_acc_s[GN_MAXN * 32 * 2];
+  float* gn_acc = (p.gn_sum && p.gn_nimg <= GN_MAXN) ? gn_acc_s : nullptr;
+  if (gn_acc)
+    for (int i = threadIdx.x; i < p.gn_nimg * 64; i += blockDim.x) gn_acc_s[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -196,20 +187,61 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (col0 + j < p.n_valid) f[j] += __ldg(p.bias + col0 + j);
         }
         if (p.gn_sum) {
-          // GroupNorm partial statistics on the fp32 accumulators (pre-rounding).  cpg is a power of two;
-          // a group boundary falls after column j when (j + 1) is a multiple of cpg (or at the chunk end).
-          const int cmask = p.gn_cpg - 1;
-          float s1 = 0.f, s2 = 0.f;
+          // GroupNorm partial statistics on the fp32 accumulators (pre-rounding).  The warp holds a 32-row x
+          // 32-column block (lane = row).  A butterfly "transpose-reduce" (16+8+4+2+1 shuffles) leaves lane l with
+          // the sum over all 32 rows of column l; lanes of one group are then combined (cpg is a power of two) and
+          // one lane per group adds into the CTA's shared accumulator.
+          if (all_same) {
+            float a1[32], a2[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = valid ? f[j] : 0.f;
-            s1 += x;
-            s2 += x * x;
-            if ((((j + 1) & cmask) == 0) || j == 31) {
-              if (col0 + j < p.n_valid)
-                gn_flush(p.gn_sum, gn_n, n_first, (col0 + j) / p.gn_cpg, s1, s2, all_same, valid, lane);
-              s1 = 0.f;
-              s2 = 0.f;
+            for (int j = 0; j < 32; ++j) {
+              const float x = valid ? f[j] : 0.f;
+              a1[j] = x;
+              a2[j] = x * x;
+            }
+#pragma unroll
+            for (int offx = 16, n = 32; offx >= 1; offx >>= 1, n >>= 1) {
+              const bool upper = (lane & offx) != 0;
+#pragma unroll
+              for (int i = 0; i < n / 2; ++i) {
+                const float s1 = upper ? a1[i] : a1[i + n / 2];
+                const float k1 = upper ? a1[i + n / 2] : a1[i];
+                a1[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, offx);
+                const float s2 = upper ? a2[i] : a2[i + n / 2];
+                const float k2 = upper ? a2[i + n / 2] : a2[i];
+                a2[i] = k2 + __shfl_xor_sync(0xffffffffu, s2, offx);
+              }
+            }
+            float c1 = a1[0], c2 = a2[0];            // column (col0 + lane): sums over the warp's 32 rows
+            const int gl = p.gn_cpg < 32 ? p.gn_cpg : 32;   // lanes per group inside this chunk
+            for (int m = 1; m < gl; m <<= 1) {
+              c1 += __shfl_xor_sync(0xffffffffu, c1, m);
+              c2 += __shfl_xor_sync(0xffffffffu, c2, m);
+            }
+            if ((lane & (gl - 1)) == 0 && col0 + lane < p.n_valid && (c1 != 0.f || c2 != 0.f)) {
+              const int grp = (col0 + lane) / p.gn_cpg;
+              float* d = gn_acc ? gn_acc + (n_first * 32 + grp) * 2 : p.gn_sum + ((long long)n_first * 32 + grp) * 2;
+              atomicAdd(d, c1);
+              atomicAdd(d + 1, c2);
+            }
+          } else {
+            // rows of this warp straddle two images (flat tiles only): slow per-lane path
+            const int cmask = p.gn_cpg - 1;
+            float s1 = 0.f, s2 = 0.f;
+            for (int j = 0; j < 32; ++j) {
+              const float x = valid ? f[j] : 0.f;
+              s1 += x;
+              s2 += x * x;
+              if ((((j + 1) & cmask) == 0) || j == 31) {
+                if (valid && col0 + j < p.n_valid) {
+                  const int grp = (col0 + j) / p.gn_cpg;
+                  float* d = gn_acc ? gn_acc + (gn_n * 32 + grp) * 2 : p.gn_sum + ((long long)gn_n * 32 + grp) * 2;
+                  atomicAdd(d, s1);
+                  atomicAdd(d + 1, s2);
+                }
+                s1 = 0.f;
+                s2 = 0.f;
+              }
             }
           }
         }
@@ -262,6 +294,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+    if (gn_acc) {
+      // all four epilogue warps are done with every tile: publish this CTA's partial statistics
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = (warp - 2) * 32 + lane; i < p.gn_nimg * 64; i += 128) {
+        const float v = gn_acc_s[i];
+        if (v != 0.f) atomicAdd(p.gn_sum + i, v);
+      }
     }
   }
   tc_fence_before_sync();

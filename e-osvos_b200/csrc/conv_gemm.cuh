@@ -33,6 +33,7 @@ struct FpropParams {
   float* gn_sum;                  // optional GroupNorm partial statistics: [gn_n][32][2] fp32 (sum, sumsq)
   int gn_cpg;                     // channels per group
   int gn_dim;                     // which tiled dim (0..3) indexes the image n
+  int gn_nimg;                    // number of images (rows of gn_sum)
 };
 
 // dW[m, n] (+)= sum_pixels A[pixel, m] * B[pixel, n]   (both MN-major), split over pixel tiles.

@@ -60,6 +60,10 @@ class ZeroPool:
         self.block, self.off, self.used = None, 0, 0
 
     def take(self, shape, device):
+        if torch.cuda.is_current_stream_capturing():
+            # inside CUDA-graph capture every buffer must come from the graph's private pool (fixed address,
+            # memset recorded as a graph node)
+            return torch.zeros(tuple(int(s) for s in shape), device=device, dtype=torch.float32)
         n = 1
         for s in shape:
             n *= int(s)

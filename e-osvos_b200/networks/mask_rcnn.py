@@ -103,6 +103,12 @@ class MaskRCNN(_MaskRCNN):
         # test hooks (tests/test_model_gpu.py): bypass RPN proposals / capture stage outputs
         self.fixed_proposals = None
         self.capture = None
+        # CUDA-graph the fixed-shape trunk (ResNet body + FPN, forward and backward): ~110 autograd Functions and
+        # ~600 launches per iteration replay as two graphs with no host work (EOSVOS_CUDA_GRAPHS=0 disables)
+        import os
+        self.use_cuda_graphs = os.environ.get("EOSVOS_CUDA_GRAPHS", "1") != "0"
+        self._graphs = {}
+        self._trunk_slots = None
 
     # ---- reference API (mask_rcnn.py:523-570) ------------------------------------------------
     def replace_batch_with_group_norms(self):
@@ -189,8 +195,13 @@ class MaskRCNN(_MaskRCNN):
         training = self.training
         req = []
         body = self.backbone.body
-        req.append((body.conv1.weight, "stem"))
+        graphed = self.use_cuda_graphs and self.capture is None
+        if not graphed:
+            req.append((body.conv1.weight, "stem"))
+        trunk = set(id(m) for m in self.backbone.modules()) if graphed else set()
         for m in self.modules():
+            if id(m) in trunk:
+                continue          # the graphed trunk builds its operands inside the graph from its static inputs
             if isinstance(m, nn.Conv2d) and m is not body.conv1 and m.weight.shape[0] >= 64:
                 req.append((m.weight, "f"))
                 if training:
@@ -260,7 +271,38 @@ class MaskRCNN(_MaskRCNN):
             identity = x
         return ops.conv_gn(out, blk.conv3.weight, *self._norm_args(blk.bn3), identity, 1, 0, True)
 
+    def _trunk_functional(self, x8, *theta):
+        """The trunk as a pure function of tensors (what torch.cuda.make_graphed_callables captures)."""
+        slots = self._trunk_slots
+        saved = [m._parameters[n] for m, n in slots]
+        for (m, n), t in zip(slots, theta):
+            m._parameters[n] = t
+        try:
+            return tuple(self._backbone_eager(x8))
+        finally:
+            for (m, n), t in zip(slots, saved):
+                m._parameters[n] = t
+
     def _backbone(self, x8):
+        if not self.use_cuda_graphs or self.capture is not None:
+            return self._backbone_eager(x8)
+        if self._trunk_slots is None:
+            self._trunk_slots = [(m, n) for _, m in self.backbone.named_modules()
+                                 for n, p in m._parameters.items() if p is not None and p.requires_grad]
+        theta = [m._parameters[n] for m, n in self._trunk_slots]
+        grad_mode = torch.is_grad_enabled() and self.training
+        key = (tuple(x8.shape), grad_mode, x8.device.index)
+        fn = self._graphs.get(key)
+        if fn is None:
+            sample = [x8.detach().clone()] + [t.detach().clone().requires_grad_(grad_mode) for t in theta]
+            with torch.enable_grad() if grad_mode else torch.no_grad():
+                fn = torch.cuda.make_graphed_callables(self._trunk_functional, tuple(sample))
+            if len(self._graphs) >= 4:          # bounded: graphs pin their activation pools
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = fn
+        return list(fn(x8, *theta))
+
+    def _backbone_eager(self, x8):
         body = self.backbone.body
         x = ops.stem(x8, body.conv1.weight, *self._norm_args(body.bn1))
         x = ops.maxpool3x3s2(x)

@@ -157,7 +157,22 @@ def prep_many(requests):
         _cache_put(w, kind, val)
 
 
+def _prep_direct(w, kind):
+    """Capture-safe variant: per-tensor launches with by-value parameters (no host tables, no caching)."""
+    wd = w.detach()
+    if not wd.is_contiguous():
+        wd = wd.contiguous()
+    outs = []
+    for shape, dims, ss, ds in _spec_for(kind)(wd):
+        out = (torch.zeros if kind == "stem" else torch.empty)(shape, device=wd.device, dtype=ACT)
+        K.permute_cast(wd, out, dims, ss, ds)
+        outs.append(out)
+    return outs[0] if len(outs) == 1 else tuple(outs)
+
+
 def _prep_one(w, kind):
+    if torch.cuda.is_current_stream_capturing():
+        return _prep_direct(w, kind)
     hit = _cache_get(w, kind)
     if hit is None:
         prep_many([(w, kind)])
@@ -247,8 +262,15 @@ class ConvGnFn(torch.autograd.Function):
     def forward(ctx, x, w, gamma, beta, res, stride, pad, relu):
         wf = prep_conv_w(w)
         N = x.shape[0]
-        sums = K.zero_pool.take((N, 32, 2), x.device)
-        z = K.conv2d_fprop(x, wf, stride=stride, pad=pad, gn_sum=sums)
+        # statistics ride in the conv epilogue when the K loop is long enough to hide them (>= 4 K blocks);
+        # short-K layers (e.g. 1x1 64->256) are epilogue-bound already, there a separate pass over the (mostly
+        # L2-resident) output is cheaper
+        if w.shape[1] * w.shape[2] * w.shape[3] >= 256:
+            sums = K.zero_pool.take((N, 32, 2), x.device)
+            z = K.conv2d_fprop(x, wf, stride=stride, pad=pad, gn_sum=sums)
+        else:
+            z = K.conv2d_fprop(x, wf, stride=stride, pad=pad)
+            sums = K.gn_stats(z)
         g, b = gamma.detach(), beta.detach()
         y = K.gn_apply(z, sums, g, b, res, relu=relu)
         mode = 0 if not relu else (2 if res is not None else 1)
