@@ -12,7 +12,8 @@ iteration:frame ratio of a 70-frame video under e-OSVOS-100-OnA (230 iterations,
 `value` = fine-tune iterations/s (device-resident inputs); `frames_per_s` = inference object-frames/s;
 `e2e` = the same block driven through the public API from HOST buffers: first frame + every inference frame H2D from
 pinned memory, first-frame augmentation per iteration (random draws + label warp on the host, bicubic image warp on
-the GPU), every loss and probability map read back (D2H) inside the timed region.  With N > 1 every rank runs its own objects
+the GPU; the host half is prefetched by a background thread), every loss and probability map read back (D2H) inside
+the timed region.  With N > 1 every rank runs its own objects
 (weak scaling, no data-path collective); time = max over ranks.
 """
 import argparse
@@ -321,8 +322,11 @@ def main():
         # end to end: frame 0 goes H2D once per step (block); every iteration draws fresh random flips/rotations/
         # scales (host, reference RNG order), warps the label on the host (nearest) and the image on the GPU (bicubic)
         if i % ITERS_PER_STEP == 1 or "aug" not in e2e_state:
-            e2e_state["aug"] = augment.DeviceAugmenter(pin_frame0.to(device, non_blocking=True), gt0_np)
-        return e2e_state["aug"].batch(BATCH)
+            if "aug" in e2e_state:
+                e2e_state["aug"].close()
+            e2e_state["aug"] = augment.PrefetchingAugmenter(pin_frame0.to(device, non_blocking=True), gt0_np, BATCH,
+                                                            lambda e: 1 + e)
+        return e2e_state["aug"].get(i)
 
     def host_frame(i):
         return pin_frames[i].to(device, non_blocking=True)

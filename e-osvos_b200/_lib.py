@@ -101,8 +101,18 @@ def call(name, *args):
     return rc
 
 
+_replayed = 0
+
+
+def add_replayed_launches(n):
+    """Kernels of this library executed through a CUDA-graph replay (not visible to the C-side counter)."""
+    global _replayed
+    _replayed += int(n)
+
+
 def launch_count():
-    return int(load().eosvos_launch_count())
+    """Kernel launches issued by the library so far: direct launches + kernels replayed inside CUDA graphs."""
+    return int(load().eosvos_launch_count()) + _replayed
 
 
 _checked_devices = set()

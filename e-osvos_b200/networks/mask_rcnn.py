@@ -102,6 +102,7 @@ class MaskRCNN(_MaskRCNN):
         self._anchor_cache = {}
         # test hooks (tests/test_model_gpu.py): bypass RPN proposals / capture stage outputs
         self.fixed_proposals = None
+        self.fixed_detections = None
         self.capture = None
         # CUDA-graph the fixed-shape trunk (ResNet body + FPN, forward and backward): ~110 autograd Functions and
         # ~600 launches per iteration replay as two graphs with no host work (EOSVOS_CUDA_GRAPHS=0 disables)
@@ -295,12 +296,18 @@ class MaskRCNN(_MaskRCNN):
         fn = self._graphs.get(key)
         if fn is None:
             sample = [x8.detach().clone()] + [t.detach().clone().requires_grad_(grad_mode) for t in theta]
+            from .. import _lib
+            c0 = _lib.launch_count()
             with torch.enable_grad() if grad_mode else torch.no_grad():
-                fn = torch.cuda.make_graphed_callables(self._trunk_functional, tuple(sample))
+                graphed = torch.cuda.make_graphed_callables(self._trunk_functional, tuple(sample))
+            per_call = (_lib.launch_count() - c0) // 4      # 3 eager warm-up runs + 1 capture of the same kernels
+            fn = (graphed, per_call)
             if len(self._graphs) >= 4:          # bounded: graphs pin their activation pools
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = fn
-        return list(fn(x8, *theta))
+        from .. import _lib
+        _lib.add_replayed_launches(fn[1])
+        return list(fn[0](x8, *theta))
 
     def _backbone_eager(self, x8):
         body = self.backbone.body
@@ -541,6 +548,10 @@ class MaskRCNN(_MaskRCNN):
             boxes, scores, labels = self._postprocess_detections(class_logits, box_regression, proposals, image_sizes)
             for i in range(len(boxes)):
                 result.append(dict(boxes=boxes[i], labels=labels[i], scores=scores[i]))
+            if self.capture is not None:
+                self.capture.update(detections=[{k: v.detach().clone() for k, v in r.items()} for r in result])
+            if self.fixed_detections is not None:      # test hook: mask branch on given detections
+                result = [{k: v.to(feats[0].device).clone() for k, v in d.items()} for d in self.fixed_detections]
             mask_proposals = [p["boxes"] for p in result]
 
         n_mask = sum(p.shape[0] for p in mask_proposals)

@@ -46,24 +46,27 @@ class DeviceAugmenter:
         self.gt = np.ascontiguousarray(gt_hw, dtype=np.float32)
         self.h, self.w = self.gt.shape
 
-    def batch(self, batch_size, rots=(-30, 30), scales=(.75, 1.25)):
-        import torch
-        from .. import kernels as K
+    def host_part(self, batch_size, rng=random, rots=(-30, 30), scales=(.75, 1.25), out=None):
+        """Random draws (reference order: flip, then rot/scale with the rejection loop) + label warp on the host.
+        Returns (minv [B,6] f32, flips [B] i32, gts [B,1,H,W] f32) as numpy views (of `out` when given)."""
         h, w = self.h, self.w
-        minv = np.empty((batch_size, 6), np.float32)
-        flips = np.empty((batch_size,), np.int32)
-        gts = np.empty((batch_size, 1, h, w), np.float32)
+        if out is None:
+            minv = np.empty((batch_size, 6), np.float32)
+            flips = np.empty((batch_size,), np.int32)
+            gts = np.empty((batch_size, 1, h, w), np.float32)
+        else:
+            minv, flips, gts = out
+
+        def n_ids(a):     # == len(np.unique(a)) for integer-valued label maps, without the sort
+            return int(np.count_nonzero(np.bincount(a.astype(np.uint8).ravel(), minlength=256)))
+
         for b in range(batch_size):
-            do_flip = random.random() < 0.5
+            do_flip = rng.random() < 0.5
             gt = cv2.flip(self.gt, flipCode=1) if do_flip else self.gt
-
-            def n_ids(a):     # == len(np.unique(a)) for integer-valued label maps, without the sort
-                return int(np.count_nonzero(np.bincount(a.astype(np.uint8).ravel(), minlength=256)))
-
             num_labels = n_ids(gt)
             while True:
-                rot = (rots[1] - rots[0]) * random.random() - (rots[1] - rots[0]) / 2
-                sc = (scales[1] - scales[0]) * random.random() - (scales[1] - scales[0]) / 2 + 1
+                rot = (rots[1] - rots[0]) * rng.random() - (rots[1] - rots[0]) / 2
+                sc = (scales[1] - scales[0]) * rng.random() - (scales[1] - scales[0]) / 2 + 1
                 M = cv2.getRotationMatrix2D((w / 2, h / 2), rot, sc)
                 aug_gt = cv2.warpAffine(gt, M, (w, h), flags=cv2.INTER_NEAREST)
                 if not num_labels > 1 or n_ids(aug_gt) == num_labels:
@@ -71,8 +74,58 @@ class DeviceAugmenter:
             minv[b] = cv2.invertAffineTransform(M).reshape(6)
             flips[b] = int(do_flip)
             gts[b, 0] = aug_gt
+        return minv, flips, gts
+
+    def device_part(self, minv, flips, gts):
+        import torch
+        from .. import kernels as K
         dev = self.src.device
-        minv_d = torch.from_numpy(minv).to(dev, non_blocking=True)
-        flip_d = torch.from_numpy(flips).to(dev, non_blocking=True)
-        gts_d = torch.from_numpy(gts).to(dev, non_blocking=True)
-        return K.affine_warp_cubic(self.src, minv_d, flip_d, batch_size), gts_d
+        as_t = (lambda a: a) if isinstance(minv, torch.Tensor) else torch.from_numpy
+        minv_d = as_t(minv).to(dev, non_blocking=True)
+        flip_d = as_t(flips).to(dev, non_blocking=True)
+        gts_d = as_t(gts).to(dev, non_blocking=True)
+        return K.affine_warp_cubic(self.src, minv_d, flip_d, minv_d.shape[0]), gts_d
+
+    def batch(self, batch_size, rots=(-30, 30), scales=(.75, 1.25)):
+        return self.device_part(*self.host_part(batch_size, random, rots, scales))
+
+
+class PrefetchingAugmenter:
+    """DeviceAugmenter whose host half (random draws + nearest label warp, cv2 releases the GIL) runs in a
+    background thread a few iterations ahead, into a ring of pinned buffers, while the GPU works.  Every epoch uses
+    its own random.Random(seed_for_epoch(epoch)) -- the same stream the reference gets from
+    set_random_seeds(seed + epoch + round) (src/util/evaluate.py:221-222) followed by the dataset's transforms."""
+
+    def __init__(self, frame0_chw_device, gt_hw, batch_size, seed_for_epoch, depth=3):
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        self.aug = DeviceAugmenter(frame0_chw_device, gt_hw)
+        self.batch_size, self.seed_for_epoch, self.depth = batch_size, seed_for_epoch, depth
+        h, w = self.aug.h, self.aug.w
+        self.ring = [(torch.empty((batch_size, 6), dtype=torch.float32).pin_memory(),
+                      torch.empty((batch_size,), dtype=torch.int32).pin_memory(),
+                      torch.empty((batch_size, 1, h, w), dtype=torch.float32).pin_memory()) for _ in range(depth + 1)]
+        self.pool = ThreadPoolExecutor(max_workers=1)
+        self.futures = {}
+        self.next_slot = 0
+
+    def _submit(self, epoch):
+        slot = self.ring[self.next_slot % len(self.ring)]
+        self.next_slot += 1
+
+        def work():
+            self.aug.host_part(self.batch_size, random.Random(self.seed_for_epoch(epoch)),
+                               out=tuple(t.numpy() for t in slot))
+            return slot
+
+        self.futures[epoch] = self.pool.submit(work)
+
+    def get(self, epoch):
+        for e in range(epoch, epoch + self.depth):
+            if e not in self.futures:
+                self._submit(e)
+        slot = self.futures.pop(epoch).result()
+        return self.aug.device_part(*slot)
+
+    def close(self):
+        self.pool.shutdown(wait=False, cancel_futures=True)

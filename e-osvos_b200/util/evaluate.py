@@ -131,10 +131,11 @@ def evaluate_sequence(model, meta_optim, meta_optim_state_dict, frames, first_la
             iters = num_epochs_eval if k == 0 else online_adapt_epochs
 
             if k == 0 and random_train_transform and device_augment:
-                dev_aug = augment.DeviceAugmenter(to_dev(frames[0]), gt0_np)
+                dev_aug = augment.PrefetchingAugmenter(to_dev(frames[0]), gt0_np, batch_size,
+                                                       lambda e, k=k: seed + e + k)
 
                 def batch_fn(epoch):
-                    return dev_aug.batch(batch_size)
+                    return dev_aug.get(epoch)
             elif k == 0:
                 def batch_fn(epoch):
                     imgs, gts = [], []

@@ -158,6 +158,7 @@ class OracleMaskRCNN(TvMaskRCNN):
                 pos_idx.append(matched_idxs[i][pos])
         else:
             result = self.detections_stage(class_logits, box_regression, proposals, image_shapes)
+            self.last_detections = [{k: v.detach().clone() for k, v in r.items()} for r in result]
             mask_props = [r["boxes"] for r in result]
         mf = rh.mask_roi_pool(features, mask_props, image_shapes)
         if mf.shape[0] > 0:
