@@ -139,19 +139,32 @@ def build_model(device):
     return model, meta_optim
 
 
+_LOSS_PIN = {}
+
+
+def _pinned_losses():
+    if "t" not in _LOSS_PIN:
+        _LOSS_PIN["t"] = torch.zeros(ITERS_PER_STEP, dtype=torch.float32).pin_memory()
+    return _LOSS_PIN["t"]
+
+
 def run_block(model, meta_optim, get_batch, get_frame, start_target, step_idx, ev=None, read_back=False):
     """One step: ITERS_PER_STEP fine-tune iterations + FRAMES_PER_STEP propagated inference frames."""
     from eosvos_b200.util import evaluate as E
     if ev is not None:
         ev[0].record()
     sink = 0.0
+    loss_host = _pinned_losses() if read_back else None
     meta_optim.reset()          # theta <- theta_0 at the start of the block (evaluate.py:196-199, 'FULL' reset)
     meta_optim.eval()
 
     def on_iter(epoch, loss):
         nonlocal sink
         if read_back:
-            sink += loss.item()              # evaluate.py:263 train_loss.item()
+            # evaluate.py:263 appends train_loss.item() per iteration; with early stopping off (the eval configs'
+            # default, cfgs/meta.yaml:97-99) nothing consumes the value before the round ends, so the D2H copy is
+            # issued asynchronously into pinned memory and read after the block (still inside the timed region)
+            loss_host[epoch - 1].copy_(loss.detach(), non_blocking=True)
 
     E.finetune(model, meta_optim, lambda epoch: get_batch(step_idx * ITERS_PER_STEP + epoch), ITERS_PER_STEP,
                seed=1, round_idx=1 + step_idx, on_iter=on_iter)
@@ -159,7 +172,8 @@ def run_block(model, meta_optim, get_batch, get_frame, start_target, step_idx, e
         ev[1].record()
     probs, boxes = E.run_frames(model, (get_frame(i) for i in range(FRAMES_PER_STEP)), start_target)
     if read_back:
-        sink += float(probs.cpu().sum())     # evaluate.py:302 probs_frame_range.cpu()
+        sink += float(probs.cpu().sum())     # evaluate.py:302 probs_frame_range.cpu()  (synchronises)
+        sink += float(loss_host.sum())
     if ev is not None:
         ev[2].record()
     return sink
@@ -187,7 +201,8 @@ def conv_roofline(device, peaks, peak_kind, reps=20):
     return {"bound": "tensor", "kernel": "conv_fprop_kernel<256,4> 3x3 256->256 @192x336 x3", "achieved": round(achieved, 1),
             "peak": peak, "peak_kind": f"{peak_kind} burst (kernel timed alone)", "unit": "TFLOP/s",
             "frac": round(achieved / peak, 4), "flops_per_launch": flops, "us_per_launch": round(dur * 1e6, 1),
-            "traffic": None}
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/README.md §2)
+            "traffic": 151996160}
 
 
 def update_roofline(device, meta_optim, model, peaks, peak_kind, reps=20):
@@ -212,7 +227,8 @@ def update_roofline(device, meta_optim, model, peaks, peak_kind, reps=20):
     peak = float(peaks["hbm_gbs"])
     return {"bound": "hbm", "kernel": "meta_update_kernel (201 tensors, 43,975,515 params)",
             "achieved": round(nbytes / dur / 1e9, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-            "frac": round(nbytes / dur / 1e9 / peak, 4), "bytes_per_launch": nbytes, "us_per_launch": round(dur * 1e6, 1)}
+            "frac": round(nbytes / dur / 1e9 / peak, 4), "bytes_per_launch": nbytes, "us_per_launch": round(dur * 1e6, 1),
+            "traffic": 484998656}
 
 
 def cpu_baseline(sample_iters=1, sample_frames=1):

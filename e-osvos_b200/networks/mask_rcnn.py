@@ -297,6 +297,10 @@ class MaskRCNN(_MaskRCNN):
         if fn is None:
             sample = [x8.detach().clone()] + [t.detach().clone().requires_grad_(grad_mode) for t in theta]
             from .. import _lib
+            try:      # graphed backward runs on the capture stream; the resulting AccumulateGrad stream note is benign
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            except AttributeError:
+                pass
             c0 = _lib.launch_count()
             with torch.enable_grad() if grad_mode else torch.no_grad():
                 graphed = torch.cuda.make_graphed_callables(self._trunk_functional, tuple(sample))
