@@ -44,6 +44,44 @@ def _chk(t, dtype=None, name="tensor"):
     return t
 
 
+class PinnedStager:
+    """Small host->device uploads (pointer tables, boxes, ids) through a ring of PINNED staging buffers with
+    non_blocking copies.  A plain `torch.tensor(..., device='cuda')` / `.to(device)` from pageable memory makes the
+    driver synchronise the stream before the copy -- i.e. the host would wait for all queued GPU work."""
+
+    def __init__(self, slot_bytes=1 << 16, slots=16):
+        self.slot_bytes, self.slots = slot_bytes, slots
+        self.ring = None
+        self.events = [None] * slots
+        self.i = 0
+
+    def put(self, array, device):
+        """array: numpy array or CPU tensor -> device tensor of the same dtype / shape."""
+        src = torch.from_numpy(array) if not isinstance(array, torch.Tensor) else array
+        src = src.contiguous()
+        nbytes = src.numel() * src.element_size()
+        if nbytes == 0:
+            return torch.empty(src.shape, dtype=src.dtype, device=device)
+        if nbytes > self.slot_bytes:
+            return src.pin_memory().to(device, non_blocking=True)
+        if self.ring is None:
+            self.ring = torch.empty((self.slots, self.slot_bytes), dtype=torch.uint8).pin_memory()
+        j = self.i % self.slots
+        self.i += 1
+        if self.events[j] is not None:
+            self.events[j].synchronize()          # the copy that last used this slot (16 uploads ago) is long done
+        stage = self.ring[j, :nbytes].view(src.dtype).view(src.shape)
+        stage.copy_(src)
+        out = stage.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.events[j] = ev
+        return out
+
+
+stager = PinnedStager()
+
+
 class ZeroPool:
     """Hands out zero-initialised fp32 views carved from ONE zeroed block per iteration (instead of ~200
     torch.zeros calls): accumulate-into outputs (split-K weight gradients, GroupNorm statistics, RoIAlign-bwd
@@ -364,10 +402,10 @@ class MetaUpdatePlan:
         hit = MetaUpdatePlan._chunk_cache.get(key)
         if hit is None:
             chunks = [[t, c] for t in range(T) for c in range((int(rows[t, 4]) + chunk - 1) // chunk)]
-            hit = (torch.tensor(chunks, dtype=torch.int32).to(dev), len(chunks))
+            hit = (torch.tensor(chunks, dtype=torch.int32).to(dev), len(chunks))      # once per shape signature
             MetaUpdatePlan._chunk_cache = {key: hit}
         self.chunks, self.num_chunks = hit
-        self.table = torch.from_numpy(rows).to(dev, non_blocking=True)
+        self.table = stager.put(rows, dev)
 
 
 def meta_update(plan, use_log=False):
@@ -421,7 +459,7 @@ def permute_cast_multi(jobs):
         if len(_pm_chunk_cache) > 8:
             _pm_chunk_cache.clear()
         _pm_chunk_cache[key] = hit
-    table = torch.from_numpy(tab).to(dev, non_blocking=True)
+    table = stager.put(tab, dev)
     call("eosvos_permute_cast_multi", _ptr(table), _ptr(hit[0]), hit[1], _stream())
 
 

@@ -110,6 +110,7 @@ class MaskRCNN(_MaskRCNN):
         self.use_cuda_graphs = os.environ.get("EOSVOS_CUDA_GRAPHS", "1") != "0"
         self._graphs = {}
         self._trunk_slots = None
+        self._side_stream = None
 
     # ---- reference API (mask_rcnn.py:523-570) ------------------------------------------------
     def replace_batch_with_group_norms(self):
@@ -156,11 +157,21 @@ class MaskRCNN(_MaskRCNN):
         B = targets.shape[0]
         Kc = max(self.num_classes - 1, 1)
         t32 = targets.to(torch.float32).contiguous()
-        stats_d = K.mask_to_bbox(t32, Kc)
-        ign_d = (t32 == 255.0).flatten(1).any(dim=1).to(torch.int32)
-        packed = torch.cat([stats_d.flatten(), ign_d]).cpu()   # ONE small D2H per forward (the reference does several)
-        stats = packed[:B * Kc * 5].view(B, Kc, 5)
-        ign = packed[B * Kc * 5:]
+        pre = getattr(targets, "_eosvos_target_stats", None)
+        if pre is not None and not flip_label and tuple(pre[0].shape) == (B, Kc, 5):
+            # fast path: the producer of `targets` already knows the per-id boxes / counts on the HOST (the
+            # augmentation thread, or the previous frame's fused tail kernel via run_frames) -> no kernel, no sync
+            stats, ign = pre
+        else:
+            stats_d = K.mask_to_bbox(t32, Kc)
+            ign_d = (t32 == 255.0).flatten(1).any(dim=1).to(torch.int32)
+            packed = torch.cat([stats_d.flatten(), ign_d]).cpu()   # ONE small D2H (the reference does several)
+            stats = packed[:B * Kc * 5].view(B, Kc, 5)
+            ign = packed[B * Kc * 5:]
+            try:        # static batches (OnA rounds re-use the same tensors every iteration) pay the sync once
+                targets._eosvos_target_stats = (stats, ign)
+            except Exception:
+                pass
         out = []
         for b in range(B):
             mask = t32[b]                            # [1,H,W]
@@ -168,7 +179,7 @@ class MaskRCNN(_MaskRCNN):
             ids = [k + 1 for k in range(Kc) if int(stats[b, k, 4]) > 0]
             num_objs = len(ids)
             assert num_objs >= 1, f"num_objs: {num_objs}"
-            obj_ids = torch.tensor(ids, dtype=torch.float32, device=device)
+            obj_ids = K.stager.put(torch.tensor(ids, dtype=torch.float32), device)
             masks = mask == obj_ids[:, None, None]
             has_ignore = bool(int(ign[b]))
             if has_ignore:
@@ -186,8 +197,9 @@ class MaskRCNN(_MaskRCNN):
             if flip_label:
                 masks = 1 - masks
             area = (boxes[:, 3] - boxes[:, 1]) * (boxes[:, 2] - boxes[:, 0])
-            out.append({"boxes": boxes.to(device), "labels": labels, "masks": masks,
-                        "image_id": torch.tensor([0], device=device), "area": area.to(device),
+            out.append({"boxes": K.stager.put(boxes, device), "boxes_cpu": boxes, "labels": labels, "masks": masks,
+                        "image_id": torch.zeros((1,), dtype=torch.int64, device=device),
+                        "area": K.stager.put(area, device),
                         "iscrowd": torch.zeros((num_objs,), dtype=torch.int64, device=device)})
         return out
 
@@ -237,15 +249,16 @@ class MaskRCNN(_MaskRCNN):
         Hp, Wp = (oh + div - 1) // div * div, (ow + div - 1) // div * div
         x8 = K.transform(inputs.to(torch.float32).contiguous(), oh, ow, Hp, Wp, tr.image_mean, tr.image_std, Cs=8)
         if targets is not None:
-            rh = torch.tensor(oh, dtype=torch.float32, device=inputs.device) / torch.tensor(
-                h, dtype=torch.float32, device=inputs.device)
-            rw = torch.tensor(ow, dtype=torch.float32, device=inputs.device) / torch.tensor(
-                w, dtype=torch.float32, device=inputs.device)
+            # tv resize_boxes computes the ratios as fp32 tensors; fp32(oh)/fp32(h) is reproduced on the host
+            rh = float(torch.tensor(oh, dtype=torch.float32) / torch.tensor(h, dtype=torch.float32))
+            rw = float(torch.tensor(ow, dtype=torch.float32) / torch.tensor(w, dtype=torch.float32))
             new = []
             for t in targets:
                 t = dict(t)
                 xmin, ymin, xmax, ymax = t["boxes"].unbind(1)
                 t["boxes"] = torch.stack((xmin * rw, ymin * rh, xmax * rw, ymax * rh), dim=1)
+                cx0, cy0, cx1, cy1 = t["boxes_cpu"].unbind(1)
+                t["boxes_cpu"] = torch.stack((cx0 * rw, cy0 * rh, cx1 * rw, cy1 * rh), dim=1)
                 if self.training:
                     t["masks"] = K.mask_resize_nearest(t["masks"].contiguous(), oh, ow)
                 new.append(t)
@@ -354,6 +367,31 @@ class MaskRCNN(_MaskRCNN):
         head = rpn.head
         conv = head.conv[0][0] if isinstance(head.conv, nn.Sequential) else head.conv
         N = feats[0].shape[0]
+        early = None
+        if self.training:
+            # Anchor labelling + sampling depend only on the anchors and the ground truth, not on the network: run
+            # them on a side stream now, so their host syncs (nonzero) do not wait for the trunk that is still
+            # executing on the main stream.  RNG order is unchanged (RPN sampler before RoI sampler).
+            fs = [(f.shape[1], f.shape[2]) for f in feats]
+            anchors = self._anchors(image_shape, image_sizes, fs, feats[0].device)
+            main = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=feats[0].device)
+            with torch.cuda.stream(self._side_stream):
+                # the ground-truth boxes are uploaded again on THIS stream (from their host copy), so nothing here
+                # is ordered behind the main stream's queue
+                side_targets = [{"boxes": K.stager.put(t["boxes_cpu"], feats[0].device)} for t in targets]
+                labels, matched_gt_boxes = rpn.assign_targets_to_anchors(anchors, side_targets)
+                regression_targets = rpn.box_coder.encode(matched_gt_boxes, anchors)
+                pos, neg = rpn.fg_bg_sampler(labels)
+                pos = torch.where(torch.cat(pos, dim=0))[0]
+                neg = torch.where(torch.cat(neg, dim=0))[0]
+                early = (torch.cat(labels, dim=0), torch.cat(regression_targets, dim=0), pos, neg)
+                done = torch.cuda.Event()
+                done.record(self._side_stream)
+            for t in early:
+                t.record_stream(main)
+            early = early + (done,)
         obj, dlt, feat_shapes = [], [], []
         for f in feats:
             _, H, W, C = f.shape
@@ -370,7 +408,7 @@ class MaskRCNN(_MaskRCNN):
         if self.capture is not None:
             self.capture.update(objectness=objectness.detach(), deltas=pred_bbox_deltas.detach())
         anchors = self._anchors(image_shape, image_sizes, feat_shapes, feats[0].device)
-        proposals = rpn.box_coder.decode(pred_bbox_deltas.detach(), anchors).view(N, -1, 4)
+        proposals = self._decode(pred_bbox_deltas.detach(), anchors, rpn.box_coder).view(N, -1, 4)
         boxes, scores = self._filter_proposals(proposals, objectness, image_sizes, num_anchors_per_level)
 
         mode = rpn._eval_augment_proposals_mode
@@ -382,7 +420,7 @@ class MaskRCNN(_MaskRCNN):
             num_box_augs = post // 2 if mode == 'EXTEND' else post
             img_height, img_width = image_shape[-2:]
             for i, target in enumerate(targets):
-                tb = target['boxes'].cpu()
+                tb = target['boxes_cpu']
                 target_boxes = []
                 for box in tb:
                     bw, bh = box[2] - box[0], box[3] - box[1]
@@ -392,7 +430,7 @@ class MaskRCNN(_MaskRCNN):
                     y_maxs = box[3] + torch.rand((num_box_augs,)) * bh * random_share
                     target_boxes.append(torch.stack([x_mins.clamp(0, img_width), y_mins.clamp(0, img_height),
                                                      x_maxs.clamp(0, img_width), y_maxs.clamp(0, img_height)], dim=1))
-                target_boxes = torch.cat(target_boxes, dim=0).to(scores[0].device)
+                target_boxes = K.stager.put(torch.cat(target_boxes, dim=0), scores[0].device)
                 if mode == 'EXTEND':
                     boxes[i] = torch.cat([boxes[i][:post // 2], target_boxes], dim=0)
                 elif mode == 'REPLACE':
@@ -402,12 +440,39 @@ class MaskRCNN(_MaskRCNN):
 
         losses = {}
         if self.training:
-            labels, matched_gt_boxes = rpn.assign_targets_to_anchors(anchors, targets)
-            regression_targets = rpn.box_coder.encode(matched_gt_boxes, anchors)
-            loss_objectness, loss_rpn_box_reg = rpn.compute_loss(objectness, pred_bbox_deltas, labels,
-                                                                 regression_targets)
+            # tv rpn.py compute_loss with the indices sampled above
+            labels_c, reg_c, pos, neg, done = early
+            torch.cuda.current_stream().wait_event(done)
+            sampled = torch.cat([pos, neg], dim=0)
+            loss_rpn_box_reg = F.smooth_l1_loss(pred_bbox_deltas[pos], reg_c[pos], beta=1 / 9,
+                                                reduction="sum") / (sampled.numel())
+            loss_objectness = F.binary_cross_entropy_with_logits(objectness.flatten()[sampled], labels_c[sampled])
             losses = {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
         return boxes, losses
+
+    @staticmethod
+    def _decode(rel_codes, anchors, coder):
+        """tv _utils.py BoxCoder.decode / decode_single restated with Python scalars (torchvision builds its 0.5
+        constants with torch.tensor(..., device=cuda): a blocking H2D copy, i.e. a full stream sync per call)."""
+        boxes = torch.cat(anchors, dim=0).to(rel_codes.dtype)
+        wx, wy, ww, wh = coder.weights
+        widths = boxes[:, 2] - boxes[:, 0]
+        heights = boxes[:, 3] - boxes[:, 1]
+        ctr_x = boxes[:, 0] + 0.5 * widths
+        ctr_y = boxes[:, 1] + 0.5 * heights
+        dx = rel_codes[:, 0::4] / wx
+        dy = rel_codes[:, 1::4] / wy
+        dw = torch.clamp(rel_codes[:, 2::4] / ww, max=coder.bbox_xform_clip)
+        dh = torch.clamp(rel_codes[:, 3::4] / wh, max=coder.bbox_xform_clip)
+        pred_ctr_x = dx * widths[:, None] + ctr_x[:, None]
+        pred_ctr_y = dy * heights[:, None] + ctr_y[:, None]
+        pred_w = torch.exp(dw) * widths[:, None]
+        pred_h = torch.exp(dh) * heights[:, None]
+        c_to_c_h = 0.5 * pred_h
+        c_to_c_w = 0.5 * pred_w
+        out = torch.stack((pred_ctr_x - c_to_c_w, pred_ctr_y - c_to_c_h, pred_ctr_x + c_to_c_w,
+                           pred_ctr_y + c_to_c_h), dim=2).flatten(1)
+        return out.reshape(rel_codes.shape[0], -1, 4)
 
     def _filter_proposals(self, proposals, objectness, image_sizes, num_anchors_per_level):
         """tv rpn.py filter_proposals (called from reference mask_rcnn.py:249): per-level top-k, clip, drop small /
@@ -437,8 +502,8 @@ class MaskRCNN(_MaskRCNN):
                     offs.append(offs[-1] + k)
             self._seg_cache = torch.tensor(offs, dtype=torch.int32, device=device)
             self._seg_cache_key = key
-        hmax = torch.tensor([s[0] for s in image_sizes], device=device, dtype=props.dtype)[:, None]
-        wmax = torch.tensor([s[1] for s in image_sizes], device=device, dtype=props.dtype)[:, None]
+        hw = K.stager.put(torch.tensor([[s[0], s[1]] for s in image_sizes], dtype=props.dtype), device)
+        hmax, wmax = hw[:, 0:1], hw[:, 1:2]
         x1 = torch.minimum(props[..., 0].clamp(min=0), wmax)
         y1 = torch.minimum(props[..., 1].clamp(min=0), hmax)
         x2 = torch.minimum(props[..., 2].clamp(min=0), wmax)
@@ -606,6 +671,7 @@ class MaskRCNN(_MaskRCNN):
         K.zero_pool.reset()          # one zeroed block per forward(+backward) serves all accumulate-into outputs
         self._prepare_operands()
         x8, targets_t, (oh, ow), (Hp, Wp) = self._transform(inputs, targets)
+
         image_sizes = [(oh, ow)] * B
         image_shape = (B, 3, Hp, Wp)
 
@@ -630,8 +696,8 @@ class MaskRCNN(_MaskRCNN):
         # eval: first detection of every class -> dense probability map + box (mask_rcnn.py:732-775),
         # boxes rescaled to the input frame (tv transform.py:257-278), paste/threshold fused on device
         Kc = self.num_classes - 1
-        rh_ = torch.tensor(h, dtype=torch.float32, device=device) / torch.tensor(oh, dtype=torch.float32, device=device)
-        rw_ = torch.tensor(w, dtype=torch.float32, device=device) / torch.tensor(ow, dtype=torch.float32, device=device)
+        rh_ = float(torch.tensor(h, dtype=torch.float32) / torch.tensor(oh, dtype=torch.float32))
+        rw_ = float(torch.tensor(w, dtype=torch.float32) / torch.tensor(ow, dtype=torch.float32))
         det_boxes, det_labels, chan, off = [], [], [], 0
         cls_ids = torch.arange(1, self.num_classes, device=device)
         for det in detections:

@@ -76,7 +76,25 @@ class DeviceAugmenter:
             gts[b, 0] = aug_gt
         return minv, flips, gts
 
-    def device_part(self, minv, flips, gts):
+    @staticmethod
+    def target_stats(gts, num_ids=1):
+        """Per-sample, per-id (xmin, ymin, xmax, ymax, count) of label maps [B,1,H,W] -- what
+        MaskRCNN._build_targets would otherwise derive on the device and read back (a stream sync)."""
+        import torch
+        B = gts.shape[0]
+        st = np.empty((B, num_ids, 5), np.int32)
+        for b in range(B):
+            for k in range(num_ids):
+                m = (gts[b, 0] == (k + 1)).astype(np.uint8)
+                n = cv2.countNonZero(m)
+                if n == 0:
+                    st[b, k] = (2147483647, 2147483647, -1, -1, 0)
+                else:
+                    x, y, w, h = cv2.boundingRect(m)
+                    st[b, k] = (x, y, x + w - 1, y + h - 1, n)
+        return torch.from_numpy(st), torch.zeros(B, dtype=torch.int32)
+
+    def device_part(self, minv, flips, gts, stats=None):
         import torch
         from .. import kernels as K
         dev = self.src.device
@@ -84,10 +102,13 @@ class DeviceAugmenter:
         minv_d = as_t(minv).to(dev, non_blocking=True)
         flip_d = as_t(flips).to(dev, non_blocking=True)
         gts_d = as_t(gts).to(dev, non_blocking=True)
+        if stats is not None:
+            gts_d._eosvos_target_stats = stats       # host-side boxes/counts: lets forward() skip a stream sync
         return K.affine_warp_cubic(self.src, minv_d, flip_d, minv_d.shape[0]), gts_d
 
     def batch(self, batch_size, rots=(-30, 30), scales=(.75, 1.25)):
-        return self.device_part(*self.host_part(batch_size, random, rots, scales))
+        minv, flips, gts = self.host_part(batch_size, random, rots, scales)
+        return self.device_part(minv, flips, gts, self.target_stats(gts))
 
 
 class PrefetchingAugmenter:
@@ -116,7 +137,7 @@ class PrefetchingAugmenter:
         def work():
             self.aug.host_part(self.batch_size, random.Random(self.seed_for_epoch(epoch)),
                                out=tuple(t.numpy() for t in slot))
-            return slot
+            return slot + (self.aug.target_stats(slot[2].numpy()),)
 
         self.futures[epoch] = self.pool.submit(work)
 

@@ -44,11 +44,15 @@ def run_frames(model, frames_dev, start_target):
                 # threshold / argmax + pixel count come out of the fused tail kernel (no extra passes)
                 nxt, stats = model.last_propagated_target, model.last_target_stats
                 model.rpn._eval_augment_proposals_mode = mode
-                if int(stats[..., 4].sum().item()) == 0:
+                stats_cpu = stats.cpu()                      # the ONE host sync per frame (helper_func.py:124)
+                if int(stats_cpu[..., 4].sum()) == 0:
                     model.rpn._eval_augment_proposals_mode = 'EXTEND'
                     targets = start_target
                 else:
                     targets = nxt
+                    # boxes / counts of the propagated target are already on the host: the next forward skips its
+                    # own mask->box kernel and read-back
+                    targets._eosvos_target_stats = (stats_cpu, torch.zeros(stats_cpu.shape[0], dtype=torch.int32))
             probs_all.append(probs)
             boxes_all.append(boxes)
     return torch.cat(probs_all), torch.cat(boxes_all)
