@@ -9,7 +9,10 @@ LIB = os.path.join(HERE, "libeosvos_b200.so")
 SOURCES = ["common.cu", "conv_gemm.cu", "conv_fprop.cu", "conv_api.cu", "gn.cu", "roi_align.cu", "mask_loss.cu", "mask_tail.cu",
            "meta_update.cu", "misc.cu", "nms.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--use_fast_math" if False else "-DEOSVOS_PRECISE_MATH", "-Xptxas", "-v"]
+              "-Xptxas", "-v"]
+# activation / operand storage: fp16 (default) or bf16 (EOSVOS_ACT=bf16 at build time)
+if os.environ.get("EOSVOS_ACT", "fp16").lower() == "bf16":
+    NVCC_FLAGS.append("-DEOSVOS_ACT_BF16")
 
 
 def _newer(src, dst):

@@ -92,6 +92,8 @@ class ZeroPool:
         self.off = 0
         self.used = 0
         self.hint = 0
+        self.cap_block = None
+        self.cap_off = 0
 
     def reset(self):
         self.hint = max(self.hint, self.used)
@@ -100,8 +102,18 @@ class ZeroPool:
     def take(self, shape, device):
         if torch.cuda.is_current_stream_capturing():
             # inside CUDA-graph capture every buffer must come from the graph's private pool (fixed address,
-            # memset recorded as a graph node)
-            return torch.zeros(tuple(int(s) for s in shape), device=device, dtype=torch.float32)
+            # memset recorded as a graph node): carve views from 32 MB zeroed blocks allocated during the capture
+            n = 1
+            for s in shape:
+                n *= int(s)
+            n_al = (n + 63) // 64 * 64
+            if self.cap_block is None or self.cap_off + n_al > self.cap_block.numel():
+                self.cap_block = torch.zeros(max(n_al, 8 << 20), device=device, dtype=torch.float32)
+                self.cap_off = 0
+            v = self.cap_block[self.cap_off:self.cap_off + n].view(tuple(int(s) for s in shape))
+            self.cap_off += n_al
+            return v
+        self.cap_block = None          # not capturing: never hand out memory of a finished capture
         n = 1
         for s in shape:
             n *= int(s)

@@ -103,15 +103,28 @@ def test_bptt_chain_exact_on_small_model():
 
 
 def test_meta_gradients_vs_oracle():
-    """First-order BPTT through 2 fine-tune steps + meta frame.  Gradients of a random-init net only agree
-    statistically under 16-bit noise: cosine similarity of the flat meta-gradients >= 0.3, meta loss
-    within 25 % (the chain itself is checked exactly in test_bptt_chain_exact_on_small_model)."""
+    """First-order BPTT through 2 fine-tune steps + meta frame on the full model.  To keep the comparison about
+    arithmetic (not about which RoIs a noisy NMS lets through), both sides get the same fixed proposal set in every
+    forward and the same sampler permutations.  Gradients of a random-init net still only agree statistically under
+    16-bit noise (ReLU gates flip): cosine similarity of the flat meta-gradients >= 0.5 (measured
+    0.75 .. 0.9), meta loss within 15 % (measured 3 .. 9 %).  The BPTT chain itself is checked exactly in test_bptt_chain_exact_on_small_model."""
     from unittest import mock
     from tests.test_model_gpu import build_pair, det_randperm, frame
     from eosvos_b200.util import meta_train
     model, opt, oracle, oopt, dev, _ = build_pair("BCE")
     img, tgt = frame()
     img2, tgt2 = frame(seed=12)
+    g = torch.Generator().manual_seed(77)
+    ctr = torch.rand(600, 2, generator=g) * torch.tensor([266.0, 150.0])
+    wh = torch.rand(600, 2, generator=g) * torch.tensor([120.0, 80.0]) + 4
+    props = torch.cat([ctr - wh / 2, ctr + wh / 2], 1).clamp(min=0)
+    props[:, 2].clamp_(max=266.0)
+    props[:, 3].clamp_(max=150.0)
+    jit = torch.rand(200, 4, generator=g) * 16 - 8          # boxes around the object so that positives exist
+    gtbox = torch.tensor([79.8, 45.0, 186.2, 109.4])
+    props = torch.cat([props, (gtbox[None] + jit).clamp(min=0)], 0)
+    oracle.fixed_proposals = [props]
+    model.fixed_proposals = [props]
     oracle.train_without_dropout()
     olrs = [l.clone().requires_grad_(True) for l in oopt.lrs]
     with mock.patch("torch.randperm", det_randperm(5)), mock.patch.object(meta_train, "set_random_seeds", lambda s: None):
@@ -122,17 +135,19 @@ def test_meta_gradients_vs_oracle():
         torch.manual_seed(21)
         _, ml = meta_train.task_meta_gradients(model, opt, (img.to(dev), tgt.to(dev)), (img2.to(dev), tgt2.to(dev)),
                                                num_epochs=2, bptt_epochs=2)
-    assert abs(ml.item() - oml.item()) <= 0.25 * abs(oml.item())   # two noisy SGD steps + own RoI sampling apart
+    model.fixed_proposals = None
+    assert abs(ml.item() - oml.item()) <= 0.15 * abs(oml.item()), (ml.item(), oml.item())
     names = [n for n, _ in opt.named_parameters()]
     gl = torch.cat([p.grad.flatten().cpu() for n, p in opt.named_parameters() if n.startswith("log_init_lr")])
     gt = torch.cat([p.grad.flatten().cpu() for n, p in opt.named_parameters() if n.startswith("model_init")])
-    ol = torch.cat([torch.zeros_like(l).flatten() if g is None else g.flatten() for g, l in zip(odl, olrs)])
-    ot = torch.cat([g.flatten() for g in odt])
+    ol = torch.cat([torch.zeros_like(l).flatten() if g_ is None else g_.flatten() for g_, l in zip(odl, olrs)])
+    ot = torch.cat([g_.flatten() for g_ in odt])
     assert len(names) == 402 and gl.numel() == ol.numel() and gt.numel() == ot.numel()
+    assert torch.isfinite(gl).all() and torch.isfinite(gt).all()
     cos_t = torch.nn.functional.cosine_similarity(gt, ot, dim=0).item()
     cos_l = torch.nn.functional.cosine_similarity(gl, ol, dim=0).item()
-    print("meta-gradient cosine: theta0", cos_t, "lambda", cos_l)
-    assert cos_t >= 0.3 and cos_l >= 0.3      # measured 0.6 .. 0.95 run to run
+    print("meta loss", ml.item(), oml.item(), "meta-gradient cosine: theta0", cos_t, "lambda", cos_l)
+    assert cos_t >= 0.5 and cos_l >= 0.5
     # outer step runs and changes the parameters
     radam = meta_train.FusedRAdam(opt)
     before = [p.detach().clone() for _, p in opt.named_parameters()]

@@ -68,6 +68,12 @@ def main(min_size=160, max_size=266, h=96, w=170, kind="LOVASZ"):
     errs = sorted(((rel(gp, go), n, go.norm().item()) for n, gp, go in zip(names, grads, ogr)), reverse=True)
     print(f"oracle bwd {t_ob:.2f}s; grad rel err: median {errs[len(errs)//2][0]:.4f}  worst:")
     for e in errs[:12]: print(f"      {e[0]:.4f}  {e[1]}  |g|={e[2]:.3e}")
+    import collections
+    proj = collections.defaultdict(lambda: [0.0, 0.0])
+    for n, gp, go in zip(names, grads, ogr):
+        kind = ("bias" if n.endswith(".bias") else "weight") + ("/gn" if ".bn" in n or "downsample.1" in n else "") + "/" + n.split(".")[0] + ("." + n.split(".")[1] if n.startswith("roi_heads") or n.startswith("backbone") else "")
+        proj[kind][0] += (gp.double().cpu() * go.double()).sum().item(); proj[kind][1] += (go.double() ** 2).sum().item()
+    print("   projection <g,g_ref>/<g_ref,g_ref> per group:", {k: round(a / max(b, 1e-30), 3) for k, (a, b) in proj.items()})
     tot = torch.sqrt(sum(((gp.double().cpu() - go.double()) ** 2).sum() for gp, go in zip(grads, ogr))) / torch.sqrt(sum((go.double() ** 2).sum() for go in ogr))
     print("   global grad rel err:", tot.item())
     opt.set_train_loss(loss); opt.step(loss); opt.meta_model.detach_param_groups()
