@@ -55,8 +55,8 @@ SIGNATURES = {
     "eosvos_transform": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "eosvos_mask_resize_nearest": [_P, _P, _I, _I, _I, _I, _I, _P],
     "eosvos_im2col_stem": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "eosvos_maxpool_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "eosvos_maxpool_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "eosvos_maxpool_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "eosvos_maxpool_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "eosvos_subsample2": [_P, _P, _I, _I, _I, _I, _I, _P],
     "eosvos_sum2x2": [_P, _P, _I, _I, _I, _I, _P],
     "eosvos_relu_bwd": [_P, _P, _P, _L, _P],

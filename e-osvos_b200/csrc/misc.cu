@@ -134,12 +134,12 @@ im2col_stem_kernel(const act_t* __restrict__ x, act_t* __restrict__ col, int N, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// max-pool k x k / stride s / pad p, NHWC bf16.  Backward re-derives the arg-max (first maximum
-// in window scan order, as ATen) so no index tensor is stored.
+// max-pool k x k / stride s / pad p, NHWC 16-bit.  Forward also records, per output element, which window
+// position (kh*k + kw, first maximum in scan order, as ATen) won; backward gathers from those indices.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, int N, int H, int W, int C,
-                   int Ho, int Wo, int ksz, int stride, int pad) {
+maxpool_fwd_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, uint8_t* __restrict__ arg, int N, int H, int W,
+                   int C, int Ho, int Wo, int ksz, int stride, int pad) {
   const int cv = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * Ho * Wo * cv) return;
@@ -149,8 +149,12 @@ maxpool_fwd_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, int N, in
   const int ho = (int)((t / Wo) % Ho);
   const int n = (int)(t / ((long long)Wo * Ho));
   float m[8];
+  uint8_t am[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) m[k] = -3.0e38f;
+  for (int k = 0; k < 8; ++k) {
+    m[k] = -3.0e38f;
+    am[k] = 255;
+  }
   for (int kh = 0; kh < ksz; ++kh) {
     const int hi = ho * stride - pad + kh;
     if (hi < 0 || hi >= H) continue;
@@ -160,17 +164,27 @@ maxpool_fwd_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, int N, in
       float f[8];
       ld8f(x + (((size_t)n * H + hi) * W + wi) * C + (size_t)c8 * 8, f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+      for (int k = 0; k < 8; ++k) {
+        if (f[k] > m[k]) {
+          m[k] = f[k];
+          am[k] = (uint8_t)(kh * ksz + kw);
+        }
+      }
     }
   }
   st8f(y + (size_t)idx * 8, m);
+  if (arg) {
+    uint2 pk;
+    pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | ((uint32_t)am[3] << 24);
+    pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | ((uint32_t)am[7] << 24);
+    *reinterpret_cast<uint2*>(arg + (size_t)idx * 8) = pk;
+  }
 }
 
-// dx[hi,wi] = sum over windows containing (hi,wi) whose first arg-max is (hi,wi) of dy[window]
+// dx[hi,wi] = sum over windows whose recorded arg-max is (hi,wi) of dy[window]
 __global__ void __launch_bounds__(256)
-maxpool_bwd_kernel(const act_t* __restrict__ x, const act_t* __restrict__ y,
-                   const act_t* __restrict__ dy, act_t* __restrict__ dx, int N, int H, int W, int C,
-                   int Ho, int Wo, int ksz, int stride, int pad) {
+maxpool_bwd_kernel(const uint8_t* __restrict__ arg, const act_t* __restrict__ dy, act_t* __restrict__ dx, int N, int H,
+                   int W, int C, int Ho, int Wo, int ksz, int stride, int pad) {
   const int cv = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * H * W * cv) return;
@@ -179,38 +193,23 @@ maxpool_bwd_kernel(const act_t* __restrict__ x, const act_t* __restrict__ y,
   const int wi = (int)(t % W);
   const int hi = (int)((t / W) % H);
   const int n = (int)(t / ((long long)W * H));
-  float xv[8], acc[8];
-  ld8f(x + (size_t)idx * 8, xv);
+  float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  // windows (ho, wo) with ho*stride - pad <= hi < ho*stride - pad + ksz
   const int ho_lo = max(0, (hi + pad - ksz + stride) / stride), ho_hi = min(Ho - 1, (hi + pad) / stride);
   const int wo_lo = max(0, (wi + pad - ksz + stride) / stride), wo_hi = min(Wo - 1, (wi + pad) / stride);
   for (int ho = ho_lo; ho <= ho_hi; ++ho)
     for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-      float yv[8], dv[8];
+      const int pos = (hi - (ho * stride - pad)) * ksz + (wi - (wo * stride - pad));   // my position in that window
       const size_t o = (((size_t)n * Ho + ho) * Wo + wo) * C + (size_t)c8 * 8;
-      ld8f(y + o, yv);
+      const uint2 pk = *reinterpret_cast<const uint2*>(arg + o);
+      float dv[8];
       ld8f(dy + o, dv);
-      // is (hi,wi) the FIRST position in this window holding the max?
-      bool first[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) first[k] = (xv[k] == yv[k]);
-      for (int kh = 0; kh < ksz; ++kh) {
-        const int h2 = ho * stride - pad + kh;
-        if (h2 < 0 || h2 >= H) continue;
-        for (int kw = 0; kw < ksz; ++kw) {
-          const int w2 = wo * stride - pad + kw;
-          if (w2 < 0 || w2 >= W) continue;
-          if (h2 > hi || (h2 == hi && w2 >= wi)) continue;  // only earlier positions
-          float f[8];
-          ld8f(x + (((size_t)n * H + h2) * W + w2) * C + (size_t)c8 * 8, f);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) first[k] = first[k] && !(f[k] == yv[k]);
-        }
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t a = ((k < 4 ? pk.x : pk.y) >> (8 * (k & 3))) & 0xffu;
+        acc[k] += (a == (uint32_t)pos) ? dv[k] : 0.f;
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += first[k] ? dv[k] : 0.f;
     }
   st8f(dx + (size_t)idx * 8, acc);
 }
@@ -380,26 +379,23 @@ extern "C" int eosvos_im2col_stem(const void* x, void* col, int N, int H, int W,
   return check_launch("im2col_stem_kernel");
 }
 
-extern "C" int eosvos_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int ksz, int stride, int pad,
-                                  eosvos_stream_t stream_) {
+extern "C" int eosvos_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int N, int H, int W, int C, int ksz,
+                                  int stride, int pad, eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EOSVOS_REQUIRE(x && y && C % 8 == 0, "maxpool_fwd: bad arguments");
   const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
   maxpool_fwd_kernel<<<blocks_for((long long)N * Ho * Wo * (C >> 3)), 256, 0, stream>>>(
-      reinterpret_cast<const act_t*>(x), reinterpret_cast<act_t*>(y), N, H, W, C, Ho, Wo, ksz, stride,
-      pad);
+      reinterpret_cast<const act_t*>(x), reinterpret_cast<act_t*>(y), argmax, N, H, W, C, Ho, Wo, ksz, stride, pad);
   return check_launch("maxpool_fwd_kernel");
 }
 
-extern "C" int eosvos_maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, int N, int H, int W, int C,
-                                  int ksz, int stride, int pad, eosvos_stream_t stream_) {
+extern "C" int eosvos_maxpool_bwd(const uint8_t* argmax, const void* dy, void* dx, int N, int H, int W, int C, int ksz,
+                                  int stride, int pad, eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  EOSVOS_REQUIRE(x && y && dy && dx && C % 8 == 0, "maxpool_bwd: bad arguments");
+  EOSVOS_REQUIRE(argmax && dy && dx && C % 8 == 0, "maxpool_bwd: bad arguments");
   const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
   maxpool_bwd_kernel<<<blocks_for((long long)N * H * W * (C >> 3)), 256, 0, stream>>>(
-      reinterpret_cast<const act_t*>(x), reinterpret_cast<const act_t*>(y),
-      reinterpret_cast<const act_t*>(dy), reinterpret_cast<act_t*>(dx), N, H, W, C, Ho, Wo, ksz, stride,
-      pad);
+      argmax, reinterpret_cast<const act_t*>(dy), reinterpret_cast<act_t*>(dx), N, H, W, C, Ho, Wo, ksz, stride, pad);
   return check_launch("maxpool_bwd_kernel");
 }
 

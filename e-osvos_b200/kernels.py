@@ -530,21 +530,23 @@ def im2col_stem(x, KH=7, KW=7, stride=2, pad=3, Kp=192):
     return col, Ho, Wo
 
 
-def maxpool_fwd(x, ksz=3, stride=2, pad=1):
+def maxpool_fwd(x, ksz=3, stride=2, pad=1, want_argmax=True):
+    """-> (y, argmax uint8 [N,Ho,Wo,C]: winning window position kh*ksz+kw, first maximum in scan order)."""
     _chk(x, ACT_DTYPE, "x")
     N, H, W, C = x.shape
     Ho = (H + 2 * pad - ksz) // stride + 1
     Wo = (W + 2 * pad - ksz) // stride + 1
     y = torch.empty((N, Ho, Wo, C), device=x.device, dtype=ACT_DTYPE)
-    call("eosvos_maxpool_fwd", _ptr(x), _ptr(y), N, H, W, C, ksz, stride, pad, _stream())
-    return y
+    arg = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.uint8) if want_argmax else None
+    call("eosvos_maxpool_fwd", _ptr(x), _ptr(y), _ptr(arg), N, H, W, C, ksz, stride, pad, _stream())
+    return y, arg
 
 
-def maxpool_bwd(x, y, dy, ksz=3, stride=2, pad=1):
-    N, H, W, C = x.shape
-    dx = torch.empty_like(x)
-    call("eosvos_maxpool_bwd", _ptr(x), _ptr(y), _ptr(_chk(dy, ACT_DTYPE)), _ptr(dx), N, H, W, C, ksz, stride,
-         pad, _stream())
+def maxpool_bwd(arg, dy, in_shape, ksz=3, stride=2, pad=1):
+    N, H, W, C = in_shape
+    dx = torch.empty(in_shape, device=dy.device, dtype=ACT_DTYPE)
+    call("eosvos_maxpool_bwd", _ptr(_chk(arg, torch.uint8, "argmax")), _ptr(_chk(dy, ACT_DTYPE)), _ptr(dx), N, H, W, C,
+         ksz, stride, pad, _stream())
     return dx
 
 

@@ -111,6 +111,8 @@ class MaskRCNN(_MaskRCNN):
         self._graphs = {}
         self._trunk_slots = None
         self._side_stream = None
+        self._prefetched = {}
+        self._pf_slot = 0
 
     # ---- reference API (mask_rcnn.py:523-570) ------------------------------------------------
     def replace_batch_with_group_norms(self):
@@ -136,6 +138,8 @@ class MaskRCNN(_MaskRCNN):
 
     def train(self, mode=True):
         super(MaskRCNN, self).train(mode)
+        if mode and getattr(self, "_prefetched", None):
+            self._prefetched.clear()            # look-ahead features are only valid for the weights they ran on
         if not self._train_encoder:
             self.backbone.eval()
         if not self._accum_batch_norm_stats:
@@ -241,13 +245,16 @@ class MaskRCNN(_MaskRCNN):
         import math
         return int(math.floor(float(h) * scale)), int(math.floor(float(w) * scale))
 
-    def _transform(self, inputs, targets):
+    def _transform(self, inputs, targets, pre=None):
         tr = self.transform
         B, _, h, w = inputs.shape
-        oh, ow = self._resized_size(h, w)
-        div = int(tr.size_divisible)
-        Hp, Wp = (oh + div - 1) // div * div, (ow + div - 1) // div * div
-        x8 = K.transform(inputs.to(torch.float32).contiguous(), oh, ow, Hp, Wp, tr.image_mean, tr.image_std, Cs=8)
+        if pre is not None:
+            x8, (oh, ow), (Hp, Wp) = pre
+        else:
+            oh, ow = self._resized_size(h, w)
+            div = int(tr.size_divisible)
+            Hp, Wp = (oh + div - 1) // div * div, (ow + div - 1) // div * div
+            x8 = K.transform(inputs.to(torch.float32).contiguous(), oh, ow, Hp, Wp, tr.image_mean, tr.image_std, Cs=8)
         if targets is not None:
             # tv resize_boxes computes the ratios as fp32 tensors; fp32(oh)/fp32(h) is reproduced on the host
             rh = float(torch.tensor(oh, dtype=torch.float32) / torch.tensor(h, dtype=torch.float32))
@@ -297,7 +304,24 @@ class MaskRCNN(_MaskRCNN):
             for (m, n), t in zip(slots, saved):
                 m._parameters[n] = t
 
-    def _backbone(self, x8):
+    @torch.no_grad()
+    def prefetch_backbone(self, inputs):
+        """Inference look-ahead: transform + trunk of a FUTURE frame, enqueued now.  The trunk of frame f+1 does not
+        depend on frame f's result (only the proposal augmentation and the heads do, reference
+        helper_func.py:100-126), so run_frames issues it before blocking on frame f's detections and the GPU works
+        through the host-side section.  Two alternating graph instances keep frame f's features intact."""
+        if self.training or not self.use_cuda_graphs or self.capture is not None:
+            return
+        B, _, h, w = inputs.shape
+        x8, _, sizes, padded = self._transform(inputs, None)
+        slot = self._pf_slot
+        self._pf_slot ^= 1
+        feats = self._backbone(x8, slot=slot)
+        if len(self._prefetched) >= 2:
+            self._prefetched.clear()
+        self._prefetched[id(inputs)] = (inputs, x8, sizes, padded, feats)
+
+    def _backbone(self, x8, slot=0):
         if not self.use_cuda_graphs or self.capture is not None:
             return self._backbone_eager(x8)
         if self._trunk_slots is None:
@@ -305,7 +329,7 @@ class MaskRCNN(_MaskRCNN):
                                  for n, p in m._parameters.items() if p is not None and p.requires_grad]
         theta = [m._parameters[n] for m, n in self._trunk_slots]
         grad_mode = torch.is_grad_enabled() and self.training
-        key = (tuple(x8.shape), grad_mode, x8.device.index)
+        key = (tuple(x8.shape), grad_mode, x8.device.index, slot)
         fn = self._graphs.get(key)
         if fn is None:
             sample = [x8.detach().clone()] + [t.detach().clone().requires_grad_(grad_mode) for t in theta]
@@ -319,7 +343,7 @@ class MaskRCNN(_MaskRCNN):
                 graphed = torch.cuda.make_graphed_callables(self._trunk_functional, tuple(sample))
             per_call = (_lib.launch_count() - c0) // 4      # 3 eager warm-up runs + 1 capture of the same kernels
             fn = (graphed, per_call)
-            if len(self._graphs) >= 4:          # bounded: graphs pin their activation pools
+            if len(self._graphs) >= 6:          # bounded: graphs pin their activation pools
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = fn
         from .. import _lib
@@ -670,14 +694,20 @@ class MaskRCNN(_MaskRCNN):
         B, _, h, w = inputs.shape
         K.zero_pool.reset()          # one zeroed block per forward(+backward) serves all accumulate-into outputs
         self._prepare_operands()
-        x8, targets_t, (oh, ow), (Hp, Wp) = self._transform(inputs, targets)
+        pre = None
+        if self._prefetched:
+            pf = self._prefetched.pop(id(inputs), None)
+            if pf is not None and pf[0] is inputs and not self.training:
+                pre = (pf[1], pf[2], pf[3])
+                pre_feats = pf[4]
+        x8, targets_t, (oh, ow), (Hp, Wp) = self._transform(inputs, targets, pre)
 
         image_sizes = [(oh, ow)] * B
         image_shape = (B, 3, Hp, Wp)
 
         grad_ctx = torch.enable_grad() if self.training else torch.no_grad()
         with grad_ctx:
-            feats = self._backbone(x8)
+            feats = pre_feats if pre is not None else self._backbone(x8)
             proposals, rpn_losses = self._rpn(feats, image_shape, image_sizes, targets_t)
             if self.fixed_proposals is not None:
                 proposals = [p.to(device).clone() for p in self.fixed_proposals]

@@ -342,15 +342,16 @@ def stem(x8, w, gamma, beta):
 class MaxPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        y = K.maxpool_fwd(x, 3, 2, 1)
-        ctx.save_for_backward(x, y)
+        y, arg = K.maxpool_fwd(x, 3, 2, 1)
+        ctx.save_for_backward(arg)
+        ctx.in_shape = tuple(x.shape)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, y = ctx.saved_tensors
-        return K.maxpool_bwd(x, y, dy.contiguous(), 3, 2, 1)
+        (arg,) = ctx.saved_tensors
+        return K.maxpool_bwd(arg, dy.contiguous(), ctx.in_shape, 3, 2, 1)
 
 
 def maxpool3x3s2(x):

@@ -36,9 +36,20 @@ def run_frames(model, frames_dev, start_target):
         else:
             targets = start_target.clone()
     probs_all, boxes_all = [], []
+    it = iter(frames_dev)
+    nxt_inputs = next(it, None)
+    prefetch = getattr(model, "prefetch_backbone", None)
     with torch.no_grad():
-        for inputs in frames_dev:
+        model.eval()
+        if nxt_inputs is not None and prefetch is not None:
+            prefetch(nxt_inputs)
+        while nxt_inputs is not None:
+            inputs, nxt_inputs = nxt_inputs, next(it, None)
             model.eval()
+            if prefetch is not None and nxt_inputs is not None:
+                # look-ahead: the trunk of the NEXT frame is independent of this frame's result; enqueue it behind
+                # this frame's trunk so the GPU stays busy while the host filters proposals / waits for detections
+                prefetch(nxt_inputs)
             probs, boxes = model(inputs, targets)
             if mode is not None:
                 # threshold / argmax + pixel count come out of the fused tail kernel (no extra passes)

@@ -127,10 +127,10 @@ int eosvos_mask_resize_nearest(const uint8_t* src, uint8_t* dst, int G, int h, i
                                eosvos_stream_t stream);
 int eosvos_im2col_stem(const void* x, void* col, int N, int H, int W, int Cs, int KH, int KW, int stride, int pad,
                        int Kp, eosvos_stream_t stream);
-int eosvos_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int ksz, int stride, int pad,
+int eosvos_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int N, int H, int W, int C, int ksz, int stride, int pad,
                        eosvos_stream_t stream);
-int eosvos_maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, int N, int H, int W, int C, int ksz,
-                       int stride, int pad, eosvos_stream_t stream);
+int eosvos_maxpool_bwd(const uint8_t* argmax, const void* dy, void* dx, int N, int H, int W, int C, int ksz, int stride,
+                       int pad, eosvos_stream_t stream);
 int eosvos_subsample2(const void* x, void* y, int N, int H, int W, int C, int backward, eosvos_stream_t stream);
 int eosvos_sum2x2(const void* dfine, void* dcoarse, int N, int Hc, int Wc, int C, eosvos_stream_t stream);
 int eosvos_relu_bwd(const void* dy, const void* y, void* out, long long numel, eosvos_stream_t stream);

@@ -354,11 +354,11 @@ def test_transform_and_stem():
     x = bf(torch.randn(2, 64, 23, 31, generator=g)).float().requires_grad_(True)
     yp = F.max_pool2d(x, 3, 2, 1)
     xd = bf(nhwc(x.detach())).to(dev())
-    yd = k.maxpool_fwd(xd)
+    yd, arg = k.maxpool_fwd(xd)
     assert torch.equal(nchw(yd.float().cpu()), yp.detach())
     dy = bf(torch.randn(yp.shape, generator=g)).float()
     (rx,) = torch.autograd.grad(yp, x, dy)
-    dx = k.maxpool_bwd(xd, yd, bf(nhwc(dy)).to(dev()))
+    dx = k.maxpool_bwd(arg, bf(nhwc(dy)).to(dev()), tuple(xd.shape))
     assert rel_err(nchw(dx.float().cpu()), rx) < 4e-3
     s = k.subsample2(xd)
     assert torch.equal(nchw(s.float().cpu()), F.max_pool2d(x.detach(), 1, 2, 0))
