@@ -452,7 +452,7 @@ static int run_wgrad(const AView& a_view, const AView& b_view, const int extent[
 
 extern "C" int eosvos_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
                                    int KH, int KW, int stride, int pad, float alpha, int bn_hint, int split_hint,
-                                   eosvos_stream_t stream_) {
+                                   int dw_layout, eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EOSVOS_REQUIRE(x && dy && dw, "conv2d_wgrad: null pointer");
   EOSVOS_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "conv2d_wgrad: channels must be multiples of 8");
@@ -483,6 +483,9 @@ extern "C" int eosvos_conv2d_wgrad(const void* x, const void* dy, float* dw, int
   AView b = nhwc_view(x, N, H, W, Cin, stride);
   const int ext[4] = {Wo, Ho, N, 1};
   const int bs[4] = {stride, stride, 1, 1};
+  if (dw_layout == 1)   // [Cout][tap][Cin]
+    return run_wgrad(a, b, ext, bs, 0, 1, nt, tda, tdb, Cout, Cin, dw, (long long)T * Cin, (long long)Cin, 0, 1, 0,
+                     alpha, bn_hint, split_hint, stream);
   return run_wgrad(a, b, ext, bs, 0, 1, nt, tda, tdb, Cout, Cin, dw, (long long)T * Cin, 1, 0, (long long)T, 0,
                    alpha, bn_hint, split_hint, stream);
 }

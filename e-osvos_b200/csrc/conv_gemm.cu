@@ -129,19 +129,35 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tmem_full, 0);
       tc_fence_after_sync();
       float* dst = p.dw + (long long)m * p.dw_m_stride + (long long)tap * p.dw_tap_stride;
+      // columns contiguous in the destination (1x1 convs, Linear, channels-last filter gradients): one 16-byte
+      // vector RED per 4 columns instead of 4 scalar ones -- the scattered scalar REDs, not the MMAs, bound the
+      // short-reduction layers (layer3/4: 6..24 k-blocks per CTA against 32768 REDs)
+      const bool vec = p.n_inner_stride == 1 && p.n_inner >= p.n_valid && (p.n_valid & 3) == 0 &&
+                       (((p.dw_m_stride | p.dw_tap_stride) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dw) & 15) == 0);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= p.n_valid) break;  // uniform
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
         tmem_ld_wait();
         if (m < p.m_valid) {
+          if (vec) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c + j;
-            if (n < p.n_valid) {
-              const int no = n / p.n_inner;
-              atomicAdd(dst + (long long)no * p.n_outer_stride + (long long)(n - no * p.n_inner) * p.n_inner_stride,
-                        __uint_as_float(v[j]) * p.alpha);
+            for (int j = 0; j < 32; j += 4) {
+              const int n = n0 + c + j;
+              if (n < p.n_valid)
+                red_add_v4(dst + n, __uint_as_float(v[j]) * p.alpha, __uint_as_float(v[j + 1]) * p.alpha,
+                           __uint_as_float(v[j + 2]) * p.alpha, __uint_as_float(v[j + 3]) * p.alpha);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + c + j;
+              if (n < p.n_valid) {
+                const int no = n / p.n_inner;
+                atomicAdd(dst + (long long)no * p.n_outer_stride + (long long)(n - no * p.n_inner) * p.n_inner_stride,
+                          __uint_as_float(v[j]) * p.alpha);
+              }
             }
           }
         }

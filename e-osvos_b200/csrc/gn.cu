@@ -88,12 +88,32 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const act_t* __res
 
 // ---------------------------------------------------------------------------------------------
 // apply: y = relu?( (x - mean) * rstd * gamma + beta  (+ res) )
+//
+// All three streaming kernels below keep GN_UNROLL independent 16-byte loads per operand in flight per thread
+// (HBM latency x bandwidth needs ~45 KB in flight per SM) and fold the per-channel constants into one multiply-add
+// so the register budget allows 4 CTAs of 256 threads per SM.  The apply kernels walk the tensor in REVERSE block
+// order: the producer (conv epilogue / reduce pass) touched the high addresses last, so those are still in L2.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GN_THREADS)
+constexpr int GN_UNROLL = 4;
+
+__device__ __forceinline__ uint4 ldg16(const act_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const act2_t* h = reinterpret_cast<const act2_t*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = act22float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+
+template <bool RES>
+__global__ void __launch_bounds__(GN_THREADS, 3)
 gn_apply_kernel(const act_t* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const act_t* __restrict__ res, act_t* __restrict__ y,
                 int HW, int C, int chunk_pixels, float eps, int relu) {
-  const int n = blockIdx.y;
+  const int n = gridDim.y - 1 - blockIdx.y;
+  const int bx = gridDim.x - 1 - blockIdx.x;
   const int cv = C >> 3;
   const int my_cv = threadIdx.x % cv;
   const int pix_per_pass = GN_THREADS / cv;
@@ -110,17 +130,18 @@ gn_apply_kernel(const act_t* __restrict__ x, const float* __restrict__ sums, con
     a[k] = rstd * gamma[c];
     b[k] = beta[c] - mean * a[k];
   }
-  const int p0 = blockIdx.x * chunk_pixels;
+  const int p0 = bx * chunk_pixels;
   const int p1 = min(HW, p0 + chunk_pixels);
   const size_t base = (size_t)n * HW * C + (size_t)my_cv * 8;
-  for (int p = p0 + threadIdx.x / cv; p < p1; p += pix_per_pass) {
+  const size_t step = (size_t)pix_per_pass * C;
+  auto one = [&](const uint4& xv, const uint4& rv, size_t o) {
     float f[8];
-    load8(x + base + (size_t)p * C, f);
+    unpack8(xv, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = f[k] * a[k] + b[k];
-    if (res) {
+    if (RES) {
       float r[8];
-      load8(res + base + (size_t)p * C, r);
+      unpack8(rv, r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] += r[k];
     }
@@ -128,19 +149,38 @@ gn_apply_kernel(const act_t* __restrict__ x, const float* __restrict__ sums, con
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
     }
-    store8(y + base + (size_t)p * C, f);
+    store8(y + o, f);
+  };
+  int p = p0 + threadIdx.x / cv;
+  size_t o = base + (size_t)p * C;
+  for (; p + (GN_UNROLL - 1) * pix_per_pass < p1; p += GN_UNROLL * pix_per_pass, o += GN_UNROLL * step) {
+    uint4 xv[GN_UNROLL], rv[GN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      xv[u] = ldg16(x + o + u * step);
+      if (RES) rv[u] = ldg16(res + o + u * step);
+    }
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) one(xv[u], rv[u], o + u * step);
+  }
+  for (; p < p1; p += pix_per_pass, o += step) {
+    const uint4 xv = ldg16(x + o);
+    uint4 rv = xv;
+    if (RES) rv = ldg16(res + o);
+    one(xv, rv, o);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward pass 1: per (n, c): S1 = sum dy_eff, S2 = sum dy_eff * xhat  ->  part[n][c][2]
-//   mask_mode 0: dy_eff = dy;  1: dy_eff = dy * (xhat*gamma+beta > 0);  2: dy_eff = dy * (yout > 0)
+//   MODE 0: dy_eff = dy;  1: dy_eff = dy * (xhat*gamma+beta > 0);  2: dy_eff = dy * (yout > 0)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GN_THREADS)
+template <int MODE>
+__global__ void __launch_bounds__(GN_THREADS, MODE == 1 ? 2 : 3)
 gn_bwd_reduce_kernel(const act_t* __restrict__ x, const float* __restrict__ sums,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      const act_t* __restrict__ dy, const act_t* __restrict__ yout,
-                     float* __restrict__ part, int HW, int C, int chunk_pixels, float eps, int mask_mode) {
+                     float* __restrict__ part, int HW, int C, int chunk_pixels, float eps) {
   extern __shared__ float smp[];  // [C][2]
   const int n = blockIdx.y;
   const int cv = C >> 3;
@@ -149,16 +189,18 @@ gn_bwd_reduce_kernel(const act_t* __restrict__ x, const float* __restrict__ sums
   const int cpg = C / GN_GROUPS;
   const float inv_m = 1.f / ((float)cpg * (float)HW);
   for (int i = threadIdx.x; i < C * 2; i += GN_THREADS) smp[i] = 0.f;
-  float mean[8], rstd[8], ga[8], be[8];
+  // mask test (MODE 1): x*a + b > 0;   S2 accumulates dy_eff * (x - mean), scaled by rstd once at the end
+  float mean[8], a[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = my_cv * 8 + k;
     const int g = c / cpg;
     mean[k] = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
-    const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean[k] * mean[k], 0.f);
-    rstd[k] = rsqrtf(var + eps);
-    ga[k] = gamma[c];
-    be[k] = beta[c];
+    if (MODE == 1) {
+      const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean[k] * mean[k], 0.f);
+      a[k] = rsqrtf(var + eps) * gamma[c];
+      b[k] = beta[c] - mean[k] * a[k];
+    }
   }
   __syncthreads();
   float s1[8], s2[8];
@@ -167,40 +209,70 @@ gn_bwd_reduce_kernel(const act_t* __restrict__ x, const float* __restrict__ sums
   const int p0 = blockIdx.x * chunk_pixels;
   const int p1 = min(HW, p0 + chunk_pixels);
   const size_t base = (size_t)n * HW * C + (size_t)my_cv * 8;
-  for (int p = p0 + threadIdx.x / cv; p < p1; p += pix_per_pass) {
+  const size_t step = (size_t)pix_per_pass * C;
+  auto one = [&](const uint4& xv, const uint4& dv, const uint4& yv) {
     float f[8], d[8];
-    load8(x + base + (size_t)p * C, f);
-    load8(dy + base + (size_t)p * C, d);
-    float yo[8];
-    if (mask_mode == 2) load8(yout + base + (size_t)p * C, yo);
+    unpack8(xv, f);
+    unpack8(dv, d);
+    if (MODE == 2) {
+      float yo[8];
+      unpack8(yv, yo);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] = (yo[k] > 0.f) ? d[k] : 0.f;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float xh = (f[k] - mean[k]) * rstd[k];
       float de = d[k];
-      if (mask_mode == 1) de = (xh * ga[k] + be[k] > 0.f) ? de : 0.f;
-      if (mask_mode == 2) de = (yo[k] > 0.f) ? de : 0.f;
+      if (MODE == 1) de = (f[k] * a[k] + b[k] > 0.f) ? de : 0.f;
       s1[k] += de;
-      s2[k] += de * xh;
+      s2[k] += de * (f[k] - mean[k]);
     }
+  };
+  int p = p0 + threadIdx.x / cv;
+  size_t o = base + (size_t)p * C;
+  for (; p + (GN_UNROLL - 1) * pix_per_pass < p1; p += GN_UNROLL * pix_per_pass, o += GN_UNROLL * step) {
+    uint4 xv[GN_UNROLL], dv[GN_UNROLL], yv[GN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      xv[u] = ldg16(x + o + u * step);
+      dv[u] = ldg16(dy + o + u * step);
+      if (MODE == 2) yv[u] = ldg16(yout + o + u * step);
+    }
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) one(xv[u], dv[u], yv[u]);
+  }
+  for (; p < p1; p += pix_per_pass, o += step) {
+    const uint4 xv = ldg16(x + o), dv = ldg16(dy + o);
+    uint4 yv = xv;
+    if (MODE == 2) yv = ldg16(yout + o);
+    one(xv, dv, yv);
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    atomicAdd(&smp[(my_cv * 8 + k) * 2], s1[k]);
-    atomicAdd(&smp[(my_cv * 8 + k) * 2 + 1], s2[k]);
+    const int c = my_cv * 8 + k;
+    const int g = c / cpg;
+    const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean[k] * mean[k], 0.f);
+    atomicAdd(&smp[c * 2], s1[k]);
+    atomicAdd(&smp[c * 2 + 1], s2[k] * rsqrtf(var + eps));
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 2; i += GN_THREADS) atomicAdd(&part[(size_t)n * C * 2 + i], smp[i]);
+  for (int i = threadIdx.x; i < C * 2; i += GN_THREADS) {
+    const float v = smp[i];
+    if (v != 0.f) atomicAdd(&part[(size_t)n * C * 2 + i], v);
+  }
 }
 
-// backward pass 2: dx = rstd * (gamma*dy_eff - (A_g + xhat*B_g)/m);  optional d_res = dy_eff
-__global__ void __launch_bounds__(GN_THREADS)
+// backward pass 2: dx = rstd * (gamma*dy_eff - (A_g + xhat*B_g)/m) = dy_eff*k1 + x*k2 + k3;  optional d_res = dy_eff
+template <int MODE, bool DRES>
+__global__ void __launch_bounds__(GN_THREADS, 3)
 gn_bwd_apply_kernel(const act_t* __restrict__ x, const float* __restrict__ sums,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
                     const act_t* __restrict__ dy, const act_t* __restrict__ yout,
                     const float* __restrict__ part, act_t* __restrict__ dx, act_t* __restrict__ dres,
-                    int HW, int C, int chunk_pixels, float eps, int mask_mode) {
+                    int HW, int C, int chunk_pixels, float eps) {
   __shared__ float gA[GN_GROUPS], gB[GN_GROUPS];
-  const int n = blockIdx.y;
+  const int n = gridDim.y - 1 - blockIdx.y;
+  const int bx = gridDim.x - 1 - blockIdx.x;
   const int cv = C >> 3;
   const int my_cv = threadIdx.x % cv;
   const int pix_per_pass = GN_THREADS / cv;
@@ -216,39 +288,60 @@ gn_bwd_apply_kernel(const act_t* __restrict__ x, const float* __restrict__ sums,
     gB[threadIdx.x] = B * inv_m;
   }
   __syncthreads();
-  float mean[8], rstd[8], ga[8], be[8], cA[8], cB[8];
+  float k1[8], k2[8], k3[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = my_cv * 8 + k;
     const int g = c / cpg;
-    mean[k] = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
-    const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean[k] * mean[k], 0.f);
-    rstd[k] = rsqrtf(var + eps);
-    ga[k] = gamma[c];
-    be[k] = beta[c];
-    cA[k] = gA[g];
-    cB[k] = gB[g];
+    const float mean = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
+    const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    k1[k] = rstd * gamma[c];
+    k2[k] = -rstd * rstd * gB[g];
+    k3[k] = -rstd * gA[g] - mean * k2[k];
+    if (MODE == 1) b[k] = beta[c] - mean * k1[k];
   }
-  const int p0 = blockIdx.x * chunk_pixels;
+  const int p0 = bx * chunk_pixels;
   const int p1 = min(HW, p0 + chunk_pixels);
   const size_t base = (size_t)n * HW * C + (size_t)my_cv * 8;
-  for (int p = p0 + threadIdx.x / cv; p < p1; p += pix_per_pass) {
-    float f[8], d[8], yo[8];
-    load8(x + base + (size_t)p * C, f);
-    load8(dy + base + (size_t)p * C, d);
-    if (mask_mode == 2) load8(yout + base + (size_t)p * C, yo);
-    float o[8];
+  const size_t step = (size_t)pix_per_pass * C;
+  auto one = [&](const uint4& xv, const uint4& dv, const uint4& yv, size_t o) {
+    float f[8], d[8];
+    unpack8(xv, f);
+    unpack8(dv, d);
+    if (MODE == 2) {
+      float yo[8];
+      unpack8(yv, yo);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] = (yo[k] > 0.f) ? d[k] : 0.f;
+    }
+    float r[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float xh = (f[k] - mean[k]) * rstd[k];
-      float de = d[k];
-      if (mask_mode == 1) de = (xh * ga[k] + be[k] > 0.f) ? de : 0.f;
-      if (mask_mode == 2) de = (yo[k] > 0.f) ? de : 0.f;
-      d[k] = de;
-      o[k] = rstd[k] * (ga[k] * de - cA[k] - xh * cB[k]);
+      if (MODE == 1) d[k] = (f[k] * k1[k] + b[k] > 0.f) ? d[k] : 0.f;
+      r[k] = d[k] * k1[k] + (f[k] * k2[k] + k3[k]);
     }
-    store8(dx + base + (size_t)p * C, o);
-    if (dres) store8(dres + base + (size_t)p * C, d);
+    store8(dx + o, r);
+    if (DRES) store8(dres + o, d);
+  };
+  int p = p0 + threadIdx.x / cv;
+  size_t o = base + (size_t)p * C;
+  for (; p + (GN_UNROLL - 1) * pix_per_pass < p1; p += GN_UNROLL * pix_per_pass, o += GN_UNROLL * step) {
+    uint4 xv[GN_UNROLL], dv[GN_UNROLL], yv[GN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      xv[u] = ldg16(x + o + u * step);
+      dv[u] = ldg16(dy + o + u * step);
+      if (MODE == 2) yv[u] = ldg16(yout + o + u * step);
+    }
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) one(xv[u], dv[u], yv[u], o + u * step);
+  }
+  for (; p < p1; p += pix_per_pass, o += step) {
+    const uint4 xv = ldg16(x + o), dv = ldg16(dy + o);
+    uint4 yv = xv;
+    if (MODE == 2) yv = ldg16(yout + o);
+    one(xv, dv, yv, o);
   }
 }
 
@@ -267,9 +360,9 @@ __global__ void gn_bwd_param_kernel(const float* __restrict__ part, float* __res
 }
 
 static int gn_chunk(int HW, int N, int C, int* chunks) {
-  // ~4 CTAs per SM overall; each CTA covers >= one pass of pixels
-  const int pix_per_pass = GN_THREADS / (C >> 3);
-  int want = (4 * num_sms() + N - 1) / N;
+  // ~3 resident CTAs per SM overall, two waves; each CTA covers whole unrolled passes of pixels
+  const int pix_per_pass = GN_THREADS / (C >> 3) * GN_UNROLL;
+  int want = (6 * num_sms() + N - 1) / N;
   int chunk = (HW + want - 1) / want;
   chunk = ((chunk + pix_per_pass - 1) / pix_per_pass) * pix_per_pass;
   if (chunk < pix_per_pass) chunk = pix_per_pass;
@@ -306,9 +399,14 @@ extern "C" int eosvos_gn_apply(const void* x, const float* sums, const float* ga
   EOSVOS_TRY(gn_check(N, HW, C));
   int chunks;
   const int chunk = gn_chunk(HW, N, C, &chunks);
-  gn_apply_kernel<<<dim3(chunks, N), GN_THREADS, 0, stream>>>(
-      reinterpret_cast<const act_t*>(x), sums, gamma, beta, reinterpret_cast<const act_t*>(res),
-      reinterpret_cast<act_t*>(y), HW, C, chunk, eps, relu);
+  if (res)
+    gn_apply_kernel<true><<<dim3(chunks, N), GN_THREADS, 0, stream>>>(
+        reinterpret_cast<const act_t*>(x), sums, gamma, beta, reinterpret_cast<const act_t*>(res),
+        reinterpret_cast<act_t*>(y), HW, C, chunk, eps, relu);
+  else
+    gn_apply_kernel<false><<<dim3(chunks, N), GN_THREADS, 0, stream>>>(
+        reinterpret_cast<const act_t*>(x), sums, gamma, beta, nullptr, reinterpret_cast<act_t*>(y), HW, C, chunk, eps,
+        relu);
   return check_launch("gn_apply_kernel");
 }
 
@@ -327,14 +425,28 @@ extern "C" int eosvos_gn_backward(const void* x, const float* sums, const float*
   const act_t* xb = reinterpret_cast<const act_t*>(x);
   const act_t* dyb = reinterpret_cast<const act_t*>(dy);
   const act_t* yb = reinterpret_cast<const act_t*>(yout);
-  gn_bwd_reduce_kernel<<<dim3(chunks, N), GN_THREADS, (size_t)C * 2 * sizeof(float), stream>>>(
-      xb, sums, gamma, beta, dyb, yb, part, HW, C, chunk, eps, mask_mode);
-  EOSVOS_TRY(check_launch("gn_bwd_reduce_kernel"));
-  gn_bwd_apply_kernel<<<dim3(chunks, N), GN_THREADS, 0, stream>>>(xb, sums, gamma, beta, dyb, yb, part,
-                                                                  reinterpret_cast<act_t*>(dx),
-                                                                  reinterpret_cast<act_t*>(dres), HW, C, chunk,
-                                                                  eps, mask_mode);
-  EOSVOS_TRY(check_launch("gn_bwd_apply_kernel"));
+  EOSVOS_REQUIRE(mask_mode >= 0 && mask_mode <= 2, "groupnorm backward: mask_mode must be 0, 1 or 2");
+  const dim3 grid(chunks, N);
+  const size_t sm = (size_t)C * 2 * sizeof(float);
+  act_t* dxb = reinterpret_cast<act_t*>(dx);
+  act_t* drb = reinterpret_cast<act_t*>(dres);
+#define GN_BWD(MODE)                                                                                                  \
+  do {                                                                                                                \
+    gn_bwd_reduce_kernel<MODE><<<grid, GN_THREADS, sm, stream>>>(xb, sums, gamma, beta, dyb, yb, part, HW, C, chunk,  \
+                                                                 eps);                                                \
+    EOSVOS_TRY(check_launch("gn_bwd_reduce_kernel"));                                                                 \
+    if (drb)                                                                                                          \
+      gn_bwd_apply_kernel<MODE, true><<<grid, GN_THREADS, 0, stream>>>(xb, sums, gamma, beta, dyb, yb, part, dxb,     \
+                                                                       drb, HW, C, chunk, eps);                       \
+    else                                                                                                              \
+      gn_bwd_apply_kernel<MODE, false><<<grid, GN_THREADS, 0, stream>>>(xb, sums, gamma, beta, dyb, yb, part, dxb,    \
+                                                                        nullptr, HW, C, chunk, eps);                  \
+    EOSVOS_TRY(check_launch("gn_bwd_apply_kernel"));                                                                  \
+  } while (0)
+  if (mask_mode == 0) GN_BWD(0);
+  else if (mask_mode == 1) GN_BWD(1);
+  else GN_BWD(2);
+#undef GN_BWD
   gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, dgamma, dbeta, N, C, alpha);
   return check_launch("gn_bwd_param_kernel");
 }

@@ -14,20 +14,41 @@ namespace eosvos {
 constexpr int MU_THREADS = 256;
 constexpr int MU_CHUNK = 8192;  // elements per CTA
 
-// table: int64 [T][6] = (p, g, lr, out, numel, row_len) ; chunks: int32 [n][2] = (tensor, start / 4... in elements)
+// table: int64 [T][8] = (p, g, lr, out, numel, row_len, g_taps, g_cin) ; chunks: int32 [n][2] = (tensor, chunk index)
+// g_taps > 1: the gradient of a [Cout][Cin][taps] filter is stored as [Cout][taps][Cin] (channels_last, what the wgrad
+// kernel's vector-RED epilogue produces); element i = (co, ci, t) of p pairs with g[(co * taps + t) * Cin + ci].  The
+// permuted reads stay inside one filter's Cin*taps window, so they are served by L1 / L2, not HBM.
 __global__ void __launch_bounds__(MU_THREADS)
 meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ chunks, int use_log) {
   const int t = chunks[blockIdx.x * 2];
   const long long start = (long long)chunks[blockIdx.x * 2 + 1] * (long long)MU_CHUNK;
-  const long long* e = table + (size_t)t * 6;
-  const float* __restrict__ p = reinterpret_cast<const float*>(e[0]);
+  const long long* e = table + (size_t)t * 8;
+  const float* p = reinterpret_cast<const float*>(e[0]);     // may alias `out` (in-place update, same index)
   const float* __restrict__ g = reinterpret_cast<const float*>(e[1]);
   const float* __restrict__ lr = reinterpret_cast<const float*>(e[2]);
-  float* __restrict__ out = reinterpret_cast<float*>(e[3]);
+  float* out = reinterpret_cast<float*>(e[3]);
   const long long numel = e[4];
   const long long row_len = e[5];
+  const int g_taps = (int)e[6];
+  const int g_cin = (int)e[7];
   long long n = numel - start;
   if (n > MU_CHUNK) n = MU_CHUNK;
+  if (g_taps > 1) {
+    // 32-bit index arithmetic: a single filter tensor has < 2^31 elements
+    const unsigned filt = (unsigned)g_taps * (unsigned)g_cin;
+    const unsigned rl = (unsigned)row_len;
+    const unsigned end = (unsigned)(start + n);
+    for (unsigned i = (unsigned)start + threadIdx.x; i < end; i += MU_THREADS) {
+      const unsigned co = i / filt;
+      const unsigned rem = i - co * filt;
+      const unsigned ci = rem / (unsigned)g_taps;
+      const unsigned tp = rem - ci * (unsigned)g_taps;
+      float lv = __ldg(lr + i / rl);
+      if (use_log) lv = expf(lv);
+      out[i] = __fsub_rn(p[i], __fmul_rn(__ldg(g + (size_t)co * filt + tp * (unsigned)g_cin + ci), lv));
+    }
+    return;
+  }
   const bool aligned = (((e[0] | e[1] | e[3]) & 15) == 0);
   if (aligned) {
     const long long nv = n >> 2;

@@ -146,4 +146,9 @@ __device__ __forceinline__ uint32_t pack_act2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// 128-bit vector reduction (sm_90+): one RED instruction for 4 consecutive fp32 values
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 }  // namespace eosvos

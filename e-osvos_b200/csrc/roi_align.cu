@@ -8,6 +8,7 @@
 #include "common.h"
 #include "../../include/eosvos_b200.h"
 #include "act.cuh"
+#include "ptx.cuh"
 
 namespace eosvos {
 
@@ -60,10 +61,6 @@ __device__ __forceinline__ Bilin bilin_setup(float y, float x, int H, int W) {
   return b;
 }
 
-// 128-bit vector reduction (sm_90+): one RED instruction for 4 consecutive fp32 channels
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 __device__ __forceinline__ void ld8(const act_t* p, float (&f)[8]) {
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));

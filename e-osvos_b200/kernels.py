@@ -171,17 +171,31 @@ def conv2d_dgrad(dy, wt, in_hw, *, stride=1, pad=0, out_fp32=False, bn_hint=0):
     return dx
 
 
-def conv2d_wgrad(x, dy, ksize, *, stride=1, pad=0, alpha=1.0, bn_hint=0, split_hint=0, out=None):
-    """x [N,H,W,Cin], dy [N,Ho,Wo,Cout] bf16 -> dw fp32 [Cout,Cin,KH,KW] (torch layout)."""
+def conv2d_wgrad(x, dy, ksize, *, stride=1, pad=0, alpha=1.0, bn_hint=0, split_hint=0, out=None, channels_last=None):
+    """x [N,H,W,Cin], dy [N,Ho,Wo,Cout] 16-bit -> dw fp32, logical shape [Cout,Cin,KH,KW].
+    channels_last (default for KH*KW > 1 when `out` is not given): memory order [Cout][KH][KW][Cin] = torch's
+    channels_last strides, which lets the kernel reduce with 16-byte vector REDs; the MetaOptimizer update reads that
+    layout directly (MetaUpdatePlan)."""
     _chk(x, ACT_DTYPE, "x")
     _chk(dy, ACT_DTYPE, "dy")
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     KH, KW = ksize
     if out is None:
-        out = zero_pool.take((Cout, Cin, KH, KW), x.device)
+        if channels_last is None:
+            channels_last = KH * KW > 1
+        if channels_last:
+            out = zero_pool.take((Cout, KH, KW, Cin), x.device).permute(0, 3, 1, 2)
+        else:
+            out = zero_pool.take((Cout, Cin, KH, KW), x.device)
+    else:
+        cl = out.dim() == 4 and KH * KW > 1 and out.is_contiguous(memory_format=torch.channels_last)
+        if channels_last is None:
+            channels_last = cl and not out.is_contiguous()
+        if (channels_last and not cl) or (not channels_last and not out.is_contiguous()):
+            raise _lib.EosvosError("conv2d_wgrad: `out` strides do not match the requested gradient layout")
     call("eosvos_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(out), N, H, W, Cin, Cout, KH, KW, stride, pad, alpha, bn_hint,
-         split_hint, _stream())
+         split_hint, 1 if channels_last else 0, _stream())
     return out
 
 
@@ -400,15 +414,21 @@ class MetaUpdatePlan:
         chunk = _lib.load().eosvos_meta_update_chunk_elems()
         dev = params[0].device
         T = len(params)
-        rows = np.empty((T, 6), dtype=np.int64)
+        rows = np.empty((T, 8), dtype=np.int64)
         for t, (p, g, lr, o) in enumerate(zip(params, grads, lrs, outs)):
             n = p.numel()
             if g.numel() != n or o.numel() != n or n % lr.numel() != 0:
                 raise _lib.EosvosError("meta_update: parameter / gradient / learning-rate sizes do not match")
+            # gradients of KxK filters arrive in channels_last memory order [Cout][K*K][Cin] (conv2d_wgrad)
+            taps, cin = 1, 1
+            if not g.is_contiguous() and g.dim() == 4 and g.is_contiguous(memory_format=torch.channels_last):
+                taps, cin = g.shape[2] * g.shape[3], g.shape[1]
+            elif not g.is_contiguous():
+                raise _lib.EosvosError("meta_update: gradient must be contiguous or channels_last")
             if not (p.is_cuda and g.is_cuda and lr.is_cuda and o.is_cuda) or p.dtype != torch.float32 or \
-                    g.dtype != torch.float32 or lr.dtype != torch.float32 or not (p.is_contiguous() and g.is_contiguous()):
+                    g.dtype != torch.float32 or lr.dtype != torch.float32 or not p.is_contiguous():
                 raise _lib.EosvosError("meta_update operands must be contiguous fp32 CUDA tensors (no CPU path exists)")
-            rows[t] = (p.data_ptr(), g.data_ptr(), lr.data_ptr(), o.data_ptr(), n, n // lr.numel())
+            rows[t] = (p.data_ptr(), g.data_ptr(), lr.data_ptr(), o.data_ptr(), n, n // lr.numel(), taps, cin)
         _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
         key = (str(dev), tuple(int(n) for n in rows[:, 4]))
         hit = MetaUpdatePlan._chunk_cache.get(key)

@@ -22,18 +22,24 @@ class _FusedUpdateFn(torch.autograd.Function):
     """outs_i = p_i - lr_i * g_i for every tensor i in one launch."""
 
     @staticmethod
-    def forward(ctx, use_log, n, *tensors):
+    def forward(ctx, use_log, n, home, *tensors):
         params, grads, lrs = tensors[:n], tensors[n:2 * n], tensors[2 * n:]
         ps = [p.detach().contiguous() for p in params]
-        gs = [g.detach().contiguous() for g in grads]
+        gs = [g.detach() if (g.is_contiguous() or (g.dim() == 4 and g.is_contiguous(memory_format=torch.channels_last)))
+              else g.detach().contiguous() for g in grads]
         ls = [l.detach().contiguous() for l in lrs]
         # one arena for all updated tensors; every tensor starts on a 256-byte boundary so the kernel's float4 path
-        # applies to all of them (an unaligned view would fall back to scalar accesses)
-        offs, total = [], 0
-        for p in ps:
-            offs.append(total)
-            total += (p.numel() + 63) // 64 * 64
-        arena = torch.empty(total, device=ps[0].device, dtype=torch.float32)
+        # applies to all of them (an unaligned view would fall back to scalar accesses).  `home` = the model's own
+        # stable arena (MaskRCNN.theta_home): the update then lands where the graphed trunk reads its parameters,
+        # in place from the second step on (element i is read and written by the same thread).
+        if home is not None:
+            arena, offs = home
+        else:
+            offs, total = [], 0
+            for p in ps:
+                offs.append(total)
+                total += (p.numel() + 63) // 64 * 64
+            arena = torch.empty(total, device=ps[0].device, dtype=torch.float32)
         outs = [arena[o:o + p.numel()].view(p.shape) for o, p in zip(offs, ps)]
         K.meta_update(K.MetaUpdatePlan(ps, gs, ls, outs), use_log)
         ctx.use_log, ctx.n = use_log, n
@@ -54,7 +60,7 @@ class _FusedUpdateFn(torch.autograd.Function):
                 dls.append(None)
                 continue
             dps.append(d)
-            if ctx.needs_input_grad[2 + 2 * n + i]:
+            if ctx.needs_input_grad[3 + 2 * n + i]:
                 prod = -(d * gs[i])
                 red = [k for k in range(prod.dim()) if ls[i].shape[k] == 1 and prod.shape[k] != 1] \
                     if ls[i].dim() == prod.dim() else None
@@ -67,7 +73,7 @@ class _FusedUpdateFn(torch.autograd.Function):
                 dls.append(dl)
             else:
                 dls.append(None)
-        return (None, None, *dps, *([None] * n), *dls)
+        return (None, None, None, *dps, *([None] * n), *dls)
 
 
 class MetaOptimizer(nn.Module):
@@ -208,6 +214,13 @@ class MetaOptimizer(nn.Module):
         lrs = [l if l.device == dev else l.to(dev) for l in lrs]
         grads = [g if g.device == dev else g.to(dev) for g in grads]
         n = len(params)
-        new_params = _FusedUpdateFn.apply(bool(self._use_log_init_lr), n, *params, *grads, *lrs)
+        home = None
+        theta_home = getattr(self.meta_model.model, "theta_home", None)
+        if callable(theta_home):
+            arena, offs, shapes, index = theta_home()
+            idx = [index.get((id(module), n_p)) for _, module, n_p, _ in groups]
+            if arena.device == dev and all(i is not None and shapes[i] == tuple(p.shape) for i, p in zip(idx, params)):
+                home = (arena, [offs[i] for i in idx])
+        new_params = _FusedUpdateFn.apply(bool(self._use_log_init_lr), n, home, *params, *grads, *lrs)
         self.meta_model.set_param_groups(new_params)
         self.state["num_steps"] += 1

@@ -113,6 +113,7 @@ class MaskRCNN(_MaskRCNN):
         self._side_stream = None
         self._prefetched = {}
         self._pf_slot = 0
+        self._theta_home = None
 
     # ---- reference API (mask_rcnn.py:523-570) ------------------------------------------------
     def replace_batch_with_group_norms(self):
@@ -292,6 +293,27 @@ class MaskRCNN(_MaskRCNN):
             identity = x
         return ops.conv_gn(out, blk.conv3.weight, *self._norm_args(blk.bn3), identity, 1, 0, True)
 
+    def theta_home(self):
+        """Stable HBM home of every fine-tuned parameter: ONE fp32 arena, each tensor on a 256-byte boundary, in
+        MetaModel.param_groups() order.  MetaOptimizer.step writes the updated parameters here (in place from the
+        second step on), and the graphed trunk uses these very addresses as its static inputs, so a fine-tune
+        iteration no longer copies 161 trunk tensors into the graph (the reference re-allocates every parameter
+        on every step, meta_model.py:78-80).  -> (arena, offsets, shapes, {(id(module), name): index})"""
+        dev = self.backbone.body.conv1.weight.device
+        if self._theta_home is None or self._theta_home[0].device != dev:
+            slots = [(m, n) for _, m in self.named_modules()
+                     for n, p in m._parameters.items() if p is not None and p.requires_grad]
+            offs, shapes, total = [], [], 0
+            for m, n in slots:
+                p = m._parameters[n]
+                offs.append(total)
+                shapes.append(tuple(p.shape))
+                total += (p.numel() + 63) // 64 * 64
+            arena = torch.empty(total, device=dev, dtype=torch.float32)
+            self._theta_home = (arena, offs, shapes, {(id(m), n): i for i, (m, n) in enumerate(slots)})
+            self._graphs.clear()
+        return self._theta_home
+
     def _trunk_functional(self, x8, *theta):
         """The trunk as a pure function of tensors (what torch.cuda.make_graphed_callables captures)."""
         slots = self._trunk_slots
@@ -332,7 +354,19 @@ class MaskRCNN(_MaskRCNN):
         key = (tuple(x8.shape), grad_mode, x8.device.index, slot)
         fn = self._graphs.get(key)
         if fn is None:
-            sample = [x8.detach().clone()] + [t.detach().clone().requires_grad_(grad_mode) for t in theta]
+            # static parameter inputs = the parameters' home addresses (no per-call copy once they live there)
+            arena, offs, shapes, index = self.theta_home()
+            sample = [x8.detach().clone()]
+            with torch.no_grad():
+                for (m, n), t in zip(self._trunk_slots, theta):
+                    i = index.get((id(m), n))
+                    if i is None or shapes[i] != tuple(t.shape):
+                        sample.append(t.detach().clone().requires_grad_(grad_mode))
+                        continue
+                    h = arena[offs[i]:offs[i] + t.numel()].view(shapes[i])
+                    if h.data_ptr() != t.data_ptr():
+                        h.copy_(t)
+                    sample.append(h.requires_grad_(grad_mode))
             from .. import _lib
             try:      # graphed backward runs on the capture stream; the resulting AccumulateGrad stream note is benign
                 torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)

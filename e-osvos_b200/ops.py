@@ -402,10 +402,16 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = K.conv2d_dgrad(dy.view(1, 1, R, O), prep_linear_wt(w, inner), (1, R)).view(R, Kd)
         if ctx.needs_input_grad[1]:
-            dw = K.zero_pool.take((O, Kd), x.device)
             if inner:
-                K.gemm_wgrad(x, dy, dw, s_m=Kd, n_inner=inner, s_n_inner=Kd // inner, s_n_outer=1, alpha=_inv_scale())
+                # x columns are (position, channel)-ordered, the weight is (channel, position)-ordered: reduce in x's
+                # order (contiguous columns -> vector REDs), then one transposing copy into torch's order
+                tmp = K.zero_pool.take((O, Kd), x.device)
+                K.gemm_wgrad(x, dy, tmp, s_m=Kd, alpha=_inv_scale())
+                dw = torch.empty((O, Kd), device=x.device, dtype=torch.float32)
+                pos = Kd // inner
+                K.permute_cast(tmp, dw, (O, inner, pos, 1), (Kd, 1, inner, 0), (Kd, pos, 1, 0))
             else:
+                dw = K.zero_pool.take((O, Kd), x.device)
                 K.gemm_wgrad(x, dy, dw, s_m=Kd, alpha=_inv_scale())
         if has_bias and ctx.needs_input_grad[2]:
             db = K.colsum(dy, alpha=_inv_scale())

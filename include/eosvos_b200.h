@@ -49,9 +49,12 @@ int eosvos_conv2d_fprop(const void* x, const void* w, const float* bias, const v
 /* dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], wt[Cin,KH,KW,Cout]) */
 int eosvos_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout, int KH,
                         int KW, int stride, int pad, int flags, int bn_hint, eosvos_stream_t stream);
-/* dw[Cout,Cin,KH,KW] (fp32, torch layout) += x (*) dy ; the caller zeroes dw */
+/* dw (fp32) += alpha * x (*) dy ; the caller zeroes dw.  dw_layout 0: memory order [Cout][Cin][KH][KW] (torch
+ * contiguous); 1: [Cout][KH][KW][Cin] (torch channels_last strides of the same logical [Cout,Cin,KH,KW] tensor:
+ * the input channel is innermost, so the epilogue issues 16-byte vector reductions) */
 int eosvos_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int KH,
-                        int KW, int stride, int pad, float alpha, int bn_hint, int split_hint, eosvos_stream_t stream);
+                        int KW, int stride, int pad, float alpha, int bn_hint, int split_hint, int dw_layout,
+                        eosvos_stream_t stream);
 /* dw[m * s_m + (n / n_inner) * s_n_outer + (n % n_inner) * s_n_inner] += sum_r dy[r][m] * x[r][n]
  * (Linear / stem-im2col weight gradients with an arbitrary destination layout) */
 int eosvos_gemm_wgrad(const void* x, const void* dy, float* dw, long long rows, int n_cols, int m_cols,

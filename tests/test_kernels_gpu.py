@@ -143,8 +143,16 @@ def test_conv2d_wgrad(case):
     g = torch.Generator().manual_seed(11)
     dy = bf(torch.randn(y.shape, generator=g)).float()
     (ref,) = torch.autograd.grad(y, w, dy)
-    dw = K().conv2d_wgrad(bf(nhwc(x)).to(dev()), bf(nhwc(dy)).to(dev()), (k, k), stride=s, pad=p)
+    xd, dyd = bf(nhwc(x)).to(dev()), bf(nhwc(dy)).to(dev())
+    dw = K().conv2d_wgrad(xd, dyd, (k, k), stride=s, pad=p)
+    assert dw.shape == ref.shape
+    if k > 1:   # KxK filters: channels_last memory order (vector-RED epilogue), same logical tensor
+        assert dw.is_contiguous(memory_format=torch.channels_last) and not dw.is_contiguous()
     assert rel_err(dw.cpu(), ref) < 1e-4, (case, rel_err(dw.cpu(), ref))
+    # torch-contiguous destination (scalar-RED epilogue) on request
+    dw2 = K().conv2d_wgrad(xd, dyd, (k, k), stride=s, pad=p, channels_last=False)
+    assert dw2.is_contiguous()
+    assert rel_err(dw2.cpu(), ref) < 1e-4, (case, rel_err(dw2.cpu(), ref))
 
 
 def test_gemm_wgrad_layouts():
@@ -325,7 +333,14 @@ def test_meta_update_bit_exact():
         dl = [x.to(dev()) for x in lr_in]
         do = [torch.empty_like(p) for p in dp]
         k.meta_update(k.MetaUpdatePlan(dp, dg, dl, do), use_log)
-        for o, r in zip(do, ref):
+        # same update with the KxK filter gradients in channels_last memory order (what conv2d_wgrad emits) and
+        # written IN PLACE over the parameters (what MetaOptimizer.step does from the second step on)
+        dg_cl = [x.contiguous(memory_format=torch.channels_last) if x.dim() == 4 else x for x in dg]
+        assert not dg_cl[6].is_contiguous()
+        dp2 = [p.clone() for p in dp]
+        k.meta_update(k.MetaUpdatePlan(dp2, dg_cl, dl, dp2), use_log)
+        for o, o2, r in zip(do, dp2, ref):
+            assert torch.equal(o, o2)
             if use_log:  # expf on device vs CPU differs in the last ulp of lr
                 assert torch.allclose(o.cpu(), r, rtol=1e-6, atol=1e-9)
             else:        # bit exact: same fp32 multiply and subtract
