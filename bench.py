@@ -180,8 +180,9 @@ def run_block(model, meta_optim, get_batch, get_frame, start_target, step_idx, e
 
 
 def conv_roofline(device, peaks, peak_kind, reps=20):
-    """Live CUDA-event timing of the dominant kernel: conv_fprop_kernel<256> on the 3x3 256->256 convolution at
-    the P2 level (192x336) at batch 3 -- the FPN output conv and the RPN head conv, forward and (as dgrad) backward."""
+    """Live CUDA-event timing of the dominant kernel: conv_fprop_pair_kernel (cta_group::2, 256x256 tiles) on the 3x3
+    256->256 convolution at the P2 level (192x336) at batch 3 -- the FPN output conv and the RPN head conv, forward and
+    (as dgrad) backward."""
     from eosvos_b200 import kernels as K
     x = torch.randn(BATCH, 192, 336, 256, device=device).to(K.ACT_DTYPE)
     w = (torch.randn(256, 3, 3, 256, device=device) * 0.02).to(K.ACT_DTYPE)
@@ -198,7 +199,7 @@ def conv_roofline(device, peaks, peak_kind, reps=20):
     dur = e0.elapsed_time(e1) / reps * 1e-3
     achieved = flops / dur / 1e12
     peak = float(peaks["bf16_tflops"]) if "bf16_tflops" in peaks else 1590.0
-    return {"bound": "tensor", "kernel": "conv_fprop_kernel<256,4> 3x3 256->256 @192x336 x3", "achieved": round(achieved, 1),
+    return {"bound": "tensor", "kernel": "conv_fprop_pair_kernel 3x3 256->256 @192x336 x3", "achieved": round(achieved, 1),
             "peak": peak, "peak_kind": f"{peak_kind} burst (kernel timed alone)", "unit": "TFLOP/s",
             "frac": round(achieved / peak, 4), "flops_per_launch": flops, "us_per_launch": round(dur * 1e6, 1),
             # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/README.md §2)

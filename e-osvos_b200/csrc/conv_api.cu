@@ -8,6 +8,7 @@
 //   their backward (dgrad + wgrad)  : src/meta_optim/meta_optim.py:202-204 (torch.autograd.grad)
 #include <algorithm>
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.h"
 #include "conv_gemm.cuh"
@@ -67,6 +68,7 @@ struct Epilogue {
 
 static int pick_bn(int n_cols, long long m_tiles, int bn_hint) {
   if (bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return bn_hint;
+  if (bn_hint == 512) return 256;   // CTA-pair kernel forced
   if (n_cols <= 64) return 64;
   if (n_cols <= 128) return 128;
   // wide outputs: 256-column tiles halve A re-reads, but only when the grid still fills the chip
@@ -140,9 +142,19 @@ static int run_fprop(const AView& av, const int extent[4], const int conv_stride
   EOSVOS_TRY(make_tensor_map_act(&tmA, av.base, 5, av.dims, av.strides, box, av.estride));
   const uint64_t bdims[2] = {b_k, b_rows};
   const uint64_t bstr[1] = {b_k * 2};
-  const uint32_t bbox[2] = {64, (uint32_t)bn};
+  // tensor-bound shapes (256-wide column tiles, at least one full wave of CTA pairs) run on CTA pairs: each CTA
+  // stages half of B, see conv_fprop_pair_kernel.  bn_hint 512 forces, EOSVOS_FPROP_PAIR=0 disables.
+  static const bool pair_ok = [] {
+    const char* e = getenv("EOSVOS_FPROP_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  const bool pair = bn == 256 && n_valid % 256 == 0 && rows == 128 &&
+                    (bn_hint == 512 || (pair_ok && bn_hint == 0 && p.num_taps * p.kchunks >= 8 &&
+                                        m_tiles * p.n_tiles_n >= 4LL * num_sms()));
+  EOSVOS_REQUIRE(pair || bn_hint != 512, "fprop: CTA-pair kernel needs Cout % 256 == 0 and full 128-pixel tiles");
+  const uint32_t bbox[2] = {64, (uint32_t)(pair ? 128 : bn)};
   EOSVOS_TRY(make_tensor_map_act(&tmB, b_base, 2, bdims, bstr, bbox, nullptr));
-  return launch_fprop(bn, tmA, tmB, p, (int)m_tiles, stream);
+  return launch_fprop(pair ? 512 : bn, tmA, tmB, p, (int)m_tiles, stream);
 }
 
 static inline AView nhwc_view(const void* base, int N, int H, int W, int C, int estride_hw) {

@@ -117,6 +117,31 @@ def test_conv2d_fprop_epilogue_variants():
     assert rel_err(gn[..., 1].cpu(), (ref * ref).sum(-1)) < 1e-3
 
 
+@pytest.mark.parametrize("shape", [(3, 34, 64, 128, 256, 3), (2, 32, 64, 64, 512, 1), (1, 16, 128, 256, 256, 3)])
+def test_conv2d_fprop_cta_pair(shape):
+    """cta_group::2 kernel (bn_hint 512): 256 x 256 tiles on CTA pairs, incl. an odd trailing M tile (51 tiles),
+    two column tiles (Cout 512), and every epilogue (bias/residual/ReLU, GroupNorm statistics)."""
+    N, H, W, Cin, Cout, k = shape
+    x, w = make_conv(N, H, W, Cin, Cout, k, seed=7)
+    g = torch.Generator().manual_seed(6)
+    bias = torch.randn(Cout, generator=g)
+    res = bf(torch.randn(N, Cout, H, W, generator=g)).float()
+    xd, wd = bf(nhwc(x)).to(dev()), bf(w.permute(0, 2, 3, 1).contiguous()).to(dev())
+    base = O.conv2d(x, w, None, 1, k // 2)
+    y = K().conv2d_fprop(xd, wd, stride=1, pad=k // 2, bn_hint=512)
+    y1 = K().conv2d_fprop(xd, wd, stride=1, pad=k // 2, bn_hint=256)
+    assert rel_err(nchw(y.float().cpu()), base) < 4e-3
+    assert torch.equal(y, y1)                      # same products, same fp32 accumulation order per k block
+    y = K().conv2d_fprop(xd, wd, bias.to(dev()), bf(nhwc(res)).to(dev()), stride=1, pad=k // 2, relu=True,
+                         out_fp32=True, bn_hint=512)
+    assert rel_err(nchw(y.cpu()), F.relu(base + bias[None, :, None, None] + res)) < 2e-5
+    gn = torch.zeros(N, 32, 2, device=dev())
+    K().conv2d_fprop(xd, wd, stride=1, pad=k // 2, gn_sum=gn, bn_hint=512)
+    ref = base.reshape(N, 32, -1)
+    assert rel_err(gn[..., 0].cpu(), ref.sum(-1)) < 1e-3
+    assert rel_err(gn[..., 1].cpu(), (ref * ref).sum(-1)) < 1e-3
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv2d_dgrad(case):
     N, H, W, Cin, Cout, k, s, p, bn = case

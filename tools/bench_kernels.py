@@ -42,9 +42,14 @@ def main():
         dy = torch.randn(B, Ho, Wo, Cout, device=dev).to(k.ACT_DTYPE)
         flops = 2.0 * B * Ho * Wo * Cout * Cin * ks * ks
         line = {"name": name, "gflop": flops / 1e9}
-        for bn in (64, 128, 256):
-            if Cout % bn: continue
-            t = timeit(lambda: k.conv2d_fprop(x, w, stride=s, pad=pad, bn_hint=bn))
+        for bn in (64, 128, 256, 512):
+            if Cout % min(bn, 256): continue
+            if bn == 512 and (B * Ho * Wo) % 128: continue
+            try:
+                t = timeit(lambda: k.conv2d_fprop(x, w, stride=s, pad=pad, bn_hint=bn))
+            except Exception as e:
+                line[f"fprop_bn{bn}_tflops"] = str(e)[-60:]
+                continue
             line[f"fprop_bn{bn}_tflops"] = round(flops / t / 1e12, 1)
         for bn in (64, 128, 256):
             if Cin % bn: continue
