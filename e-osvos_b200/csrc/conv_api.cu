@@ -627,9 +627,10 @@ extern "C" int eosvos_deconv2x2_wgrad(const void* x, const void* dy, float* dw, 
 // ---------------------------------------------------------------------------------------------
 extern "C" int eosvos_gemm_wgrad(const void* x, const void* dy, float* dw, long long rows, int n_cols, int m_cols,
                                  long long s_m, int n_inner, long long s_n_inner, long long s_n_outer, float alpha,
-                                 int bn_hint, int split_hint, eosvos_stream_t stream_) {
+                                 int bn_hint, int split_hint, int n_valid, eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EOSVOS_REQUIRE(x && dy && dw, "gemm_wgrad: null pointer");
+  EOSVOS_REQUIRE(n_valid >= 0 && n_valid <= n_cols, "gemm_wgrad: n_valid must be within the x columns");
   EOSVOS_REQUIRE(n_cols % 8 == 0 && m_cols % 8 == 0, "gemm_wgrad: column counts must be multiples of 8");
   EOSVOS_REQUIRE(rows > 0 && rows < (1LL << 31), "gemm_wgrad: bad row count");
   AView a = nhwc_view(dy, 1, 1, (int)rows, m_cols, 1);
@@ -637,6 +638,8 @@ extern "C" int eosvos_gemm_wgrad(const void* x, const void* dy, float* dw, long 
   int tda[1][5] = {{0, 0, 0, 0, 0}}, tdb[1][5] = {{0, 0, 0, 0, 0}};
   const int ext[4] = {(int)rows, 1, 1, 1};
   const int bs[4] = {1, 1, 1, 1};
-  return run_wgrad(a, b, ext, bs, 0, -1, 1, tda, tdb, m_cols, n_cols, dw, s_m, 0, n_inner, s_n_inner, s_n_outer,
-                   alpha, bn_hint, split_hint, stream);
+  // columns >= n_valid (zero padding of x, e.g. the stem's im2col K 147 -> 192) are never written: their destination
+  // offsets would fall outside dw
+  return run_wgrad(a, b, ext, bs, 0, -1, 1, tda, tdb, m_cols, n_valid > 0 ? n_valid : n_cols, dw, s_m, 0, n_inner,
+                   s_n_inner, s_n_outer, alpha, bn_hint, split_hint, stream);
 }

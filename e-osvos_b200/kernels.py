@@ -199,8 +199,9 @@ def conv2d_wgrad(x, dy, ksize, *, stride=1, pad=0, alpha=1.0, bn_hint=0, split_h
     return out
 
 
-def gemm_wgrad(x, dy, out, *, s_m, n_inner=0, s_n_inner=1, s_n_outer=0, alpha=1.0, bn_hint=0, split_hint=0):
-    """out[m*s_m + (n//n_inner)*s_n_outer + (n%n_inner)*s_n_inner] += sum_r dy[r,m] * x[r,n]."""
+def gemm_wgrad(x, dy, out, *, s_m, n_inner=0, s_n_inner=1, s_n_outer=0, alpha=1.0, bn_hint=0, split_hint=0, n_valid=0):
+    """out[m*s_m + (n//n_inner)*s_n_outer + (n%n_inner)*s_n_inner] += sum_r dy[r,m] * x[r,n]  for n < n_valid
+    (0 = every column of x)."""
     _chk(x, ACT_DTYPE, "x")
     _chk(dy, ACT_DTYPE, "dy")
     _chk(out, torch.float32, "out")
@@ -208,7 +209,7 @@ def gemm_wgrad(x, dy, out, *, s_m, n_inner=0, s_n_inner=1, s_n_outer=0, alpha=1.
     rows2, m_cols = dy.shape
     assert rows == rows2
     call("eosvos_gemm_wgrad", _ptr(x), _ptr(dy), _ptr(out), rows, n_cols, m_cols, s_m, n_inner, s_n_inner, s_n_outer,
-         alpha, bn_hint, split_hint, _stream())
+         alpha, bn_hint, split_hint, n_valid, _stream())
     return out
 
 

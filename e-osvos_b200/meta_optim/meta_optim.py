@@ -22,7 +22,7 @@ class _FusedUpdateFn(torch.autograd.Function):
     """outs_i = p_i - lr_i * g_i for every tensor i in one launch."""
 
     @staticmethod
-    def forward(ctx, use_log, n, home, *tensors):
+    def forward(ctx, use_log, n, home, keep_grads, *tensors):
         params, grads, lrs = tensors[:n], tensors[n:2 * n], tensors[2 * n:]
         ps = [p.detach().contiguous() for p in params]
         gs = [g.detach() if (g.is_contiguous() or (g.dim() == 4 and g.is_contiguous(memory_format=torch.channels_last)))
@@ -43,6 +43,10 @@ class _FusedUpdateFn(torch.autograd.Function):
         outs = [arena[o:o + p.numel()].view(p.shape) for o, p in zip(offs, ps)]
         K.meta_update(K.MetaUpdatePlan(ps, gs, ls, outs), use_log)
         ctx.use_log, ctx.n = use_log, n
+        if keep_grads:
+            # meta-training back-propagates through this update later (d/d lr = -rowsum(upstream * g)), after the
+            # next forward/backward has overwritten the static gradient buffers of the CUDA-graphed trunk: keep copies
+            gs = [g.clone() for g in gs]
         ctx.save_for_backward(*gs, *ls)
         return tuple(outs)
 
@@ -60,7 +64,7 @@ class _FusedUpdateFn(torch.autograd.Function):
                 dls.append(None)
                 continue
             dps.append(d)
-            if ctx.needs_input_grad[3 + 2 * n + i]:
+            if ctx.needs_input_grad[4 + 2 * n + i]:
                 prod = -(d * gs[i])
                 red = [k for k in range(prod.dim()) if ls[i].shape[k] == 1 and prod.shape[k] != 1] \
                     if ls[i].dim() == prod.dim() else None
@@ -73,7 +77,7 @@ class _FusedUpdateFn(torch.autograd.Function):
                 dls.append(dl)
             else:
                 dls.append(None)
-        return (None, None, None, *dps, *([None] * n), *dls)
+        return (None, None, None, None, *dps, *([None] * n), *dls)
 
 
 class MetaOptimizer(nn.Module):
@@ -221,6 +225,7 @@ class MetaOptimizer(nn.Module):
             idx = [index.get((id(module), n_p)) for _, module, n_p, _ in groups]
             if arena.device == dev and all(i is not None and shapes[i] == tuple(p.shape) for i, p in zip(idx, params)):
                 home = (arena, [offs[i] for i in idx])
-        new_params = _FusedUpdateFn.apply(bool(self._use_log_init_lr), n, home, *params, *grads, *lrs)
+        new_params = _FusedUpdateFn.apply(bool(self._use_log_init_lr), n, home, bool(self.training), *params, *grads,
+                                          *lrs)
         self.meta_model.set_param_groups(new_params)
         self.state["num_steps"] += 1

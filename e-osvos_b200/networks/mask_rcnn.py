@@ -15,6 +15,7 @@ What runs where:
     that RNG consumption -- device randperm, CPU torch.rand for EXTEND -- is identical).
 There is no CPU path: tensors must be CUDA tensors on an sm_100 device.
 """
+import os
 import types
 from collections import OrderedDict
 
@@ -216,7 +217,7 @@ class MaskRCNN(_MaskRCNN):
         graphed = self.use_cuda_graphs and self.capture is None
         if not graphed:
             req.append((body.conv1.weight, "stem"))
-        trunk = set(id(m) for m in self.backbone.modules()) if graphed else set()
+        trunk = set(id(m) for mod in (self.backbone, self.rpn.head) for m in mod.modules()) if graphed else set()
         for m in self.modules():
             if id(m) in trunk:
                 continue          # the graphed trunk builds its operands inside the graph from its static inputs
@@ -321,7 +322,15 @@ class MaskRCNN(_MaskRCNN):
         for (m, n), t in zip(slots, theta):
             m._parameters[n] = t
         try:
-            return tuple(self._backbone_eager(x8))
+            # the RPN head (shared 3x3 conv + objectness / box 1x1s on every level) has static shapes too: inside
+            # the graph its ~15 forward and ~45 backward launches cost no host time on the critical path
+            feats = self._backbone_eager(x8)
+            lvl = int(os.environ.get("EOSVOS_GRAPH_HEAD", "2"))
+            if lvl == 0:
+                return tuple(feats)
+            if lvl == 1:
+                return tuple(feats) + tuple(self._rpn_head(feats, stage=1))
+            return tuple(feats) + tuple(self._rpn_head(feats))
         finally:
             for (m, n), t in zip(slots, saved):
                 m._parameters[n] = t
@@ -347,7 +356,10 @@ class MaskRCNN(_MaskRCNN):
         if not self.use_cuda_graphs or self.capture is not None:
             return self._backbone_eager(x8)
         if self._trunk_slots is None:
-            self._trunk_slots = [(m, n) for _, m in self.backbone.named_modules()
+            lvl = int(os.environ.get("EOSVOS_GRAPH_HEAD", "2"))
+            mods = (self.backbone,) if lvl == 0 else ((self.backbone, self.rpn.head.conv) if lvl == 1
+                                                      else (self.backbone, self.rpn.head))
+            self._trunk_slots = [(m, n) for mod in mods for _, m in mod.named_modules()
                                  for n, p in m._parameters.items() if p is not None and p.requires_grad]
         theta = [m._parameters[n] for m, n in self._trunk_slots]
         grad_mode = torch.is_grad_enabled() and self.training
@@ -376,6 +388,9 @@ class MaskRCNN(_MaskRCNN):
             with torch.enable_grad() if grad_mode else torch.no_grad():
                 graphed = torch.cuda.make_graphed_callables(self._trunk_functional, tuple(sample))
             per_call = (_lib.launch_count() - c0) // 4      # 3 eager warm-up runs + 1 capture of the same kernels
+            # the warm-up backward ran on uninitialised output gradients (torch's warm-up passes empty_like tensors):
+            # never continue in a zero block it touched
+            K.zero_pool.reset()
             fn = (graphed, per_call)
             if len(self._graphs) >= 6:          # bounded: graphs pin their activation pools
                 self._graphs.pop(next(iter(self._graphs)))
@@ -420,10 +435,25 @@ class MaskRCNN(_MaskRCNN):
             self._anchor_cache = {key: [a.detach() for a in self.rpn.anchor_generator(il, fms)]}
         return self._anchor_cache[key]
 
-    def _rpn(self, feats, image_shape, image_sizes, targets):
+    def _rpn_head(self, feats, stage=0):
+        """tv RPNHead on every level: [pixels, 16] fp32 = (A objectness | 4A box deltas | padding) per level.
+        stage 1: only the shared 3x3 conv; stage 2: only the 1x1 heads on its output (debug split)."""
+        head = self.rpn.head
+        conv = head.conv[0][0] if isinstance(head.conv, nn.Sequential) else head.conv
+        outs = []
+        for f in feats:
+            C = f.shape[-1]
+            t = f if stage == 2 else ops.conv2d(f, conv.weight, conv.bias, pad=1, relu=True)
+            if stage == 1:
+                outs.append(t)
+                continue
+            outs.append(ops.fused_heads(t.reshape(-1, C), [head.cls_logits.weight, head.bbox_pred.weight],
+                                        [head.cls_logits.bias, head.bbox_pred.bias]))
+        return outs
+
+    def _rpn(self, feats, image_shape, image_sizes, targets, head_outs=None):
         rpn = self.rpn
         head = rpn.head
-        conv = head.conv[0][0] if isinstance(head.conv, nn.Sequential) else head.conv
         N = feats[0].shape[0]
         early = None
         if self.training:
@@ -451,11 +481,12 @@ class MaskRCNN(_MaskRCNN):
                 t.record_stream(main)
             early = early + (done,)
         obj, dlt, feat_shapes = [], [], []
-        for f in feats:
+        if head_outs is None:
+            head_outs = self._rpn_head(feats)
+        elif head_outs[0].dtype != torch.float32:          # debug split: only the shared conv ran inside the graph
+            head_outs = self._rpn_head(head_outs, stage=2)
+        for f, o in zip(feats, head_outs):
             _, H, W, C = f.shape
-            t = ops.conv2d(f, conv.weight, conv.bias, pad=1, relu=True)
-            o = ops.fused_heads(t.reshape(-1, C), [head.cls_logits.weight, head.bbox_pred.weight],
-                                [head.cls_logits.bias, head.bbox_pred.bias])
             A = head.cls_logits.weight.shape[0]
             obj.append(o[:, :A].reshape(N, H * W * A, 1))
             dlt.append(o[:, A:A + 4 * A].reshape(N, H * W * A, 4))
@@ -742,7 +773,8 @@ class MaskRCNN(_MaskRCNN):
         grad_ctx = torch.enable_grad() if self.training else torch.no_grad()
         with grad_ctx:
             feats = pre_feats if pre is not None else self._backbone(x8)
-            proposals, rpn_losses = self._rpn(feats, image_shape, image_sizes, targets_t)
+            feats, head_outs = feats[:5], (feats[5:] if len(feats) > 5 else None)
+            proposals, rpn_losses = self._rpn(feats, image_shape, image_sizes, targets_t, head_outs)
             if self.fixed_proposals is not None:
                 proposals = [p.to(device).clone() for p in self.fixed_proposals]
             if self.capture is not None:

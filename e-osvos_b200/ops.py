@@ -200,7 +200,8 @@ def _fused_head_w(ws, pad_to):
     """Stacks several [O_i, K(,1,1)] fp32 weights into one bf16 [pad_to,1,1,K] (zero rows beyond sum O_i)
     and the transposed [K,1,1,64] operand (zero-padded columns) used by the backward GEMMs."""
     kind = ("head", pad_to)
-    hit = _cache_get(ws[0], kind)
+    capturing = torch.cuda.is_current_stream_capturing()     # inside a CUDA graph the operands must be rebuilt from
+    hit = None if capturing else _cache_get(ws[0], kind)     # the graph's static inputs on every replay: no caching
     if hit is not None and all(a is b() and a._version == v for a, (b, v) in zip(ws[1:], hit[2])):
         return hit[0], hit[1]
     flat = torch.cat([w.detach().reshape(w.shape[0], -1) for w in ws], 0)
@@ -209,7 +210,8 @@ def _fused_head_w(ws, pad_to):
     wf.view(pad_to, Kd)[:O] = flat.to(ACT)
     wt = torch.zeros((Kd, 1, 1, 64), device=flat.device, dtype=ACT)
     wt.view(Kd, 64)[:, :O] = flat.t().to(ACT)
-    _cache_put(ws[0], kind, (wf, wt, [(weakref.ref(w), w._version) for w in ws[1:]]))
+    if not capturing:
+        _cache_put(ws[0], kind, (wf, wt, [(weakref.ref(w), w._version) for w in ws[1:]]))
     return wf, wt
 
 
@@ -331,7 +333,9 @@ class StemFn(torch.autograd.Function):
             dw = K.zero_pool.take(tuple(w.shape), w.device)
             T = KH * KW
             # column n = t*I + c  ->  torch offset c*T + t
-            K.gemm_wgrad(col, dz.view(-1, O), dw, s_m=I * T, n_inner=I, s_n_inner=T, s_n_outer=1, alpha=_inv_scale())
+            # col has K = T*I zero-padded to a multiple of 64: only the first T*I columns map into dw
+            K.gemm_wgrad(col, dz.view(-1, O), dw, s_m=I * T, n_inner=I, s_n_inner=T, s_n_outer=1, alpha=_inv_scale(),
+                         n_valid=T * I)
         return None, dw, dgamma, dbeta
 
 

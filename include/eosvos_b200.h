@@ -55,11 +55,12 @@ int eosvos_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, 
 int eosvos_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int KH,
                         int KW, int stride, int pad, float alpha, int bn_hint, int split_hint, int dw_layout,
                         eosvos_stream_t stream);
-/* dw[m * s_m + (n / n_inner) * s_n_outer + (n % n_inner) * s_n_inner] += sum_r dy[r][m] * x[r][n]
- * (Linear / stem-im2col weight gradients with an arbitrary destination layout) */
+/* dw[m * s_m + (n / n_inner) * s_n_outer + (n % n_inner) * s_n_inner] += sum_r dy[r][m] * x[r][n]  for n < n_valid
+ * (Linear / stem-im2col weight gradients with an arbitrary destination layout; n_valid 0 = all n_cols columns,
+ * smaller when trailing x columns are zero padding) */
 int eosvos_gemm_wgrad(const void* x, const void* dy, float* dw, long long rows, int n_cols, int m_cols,
                       long long s_m, int n_inner, long long s_n_inner, long long s_n_outer, float alpha,
-                      int bn_hint, int split_hint, eosvos_stream_t stream);
+                      int bn_hint, int split_hint, int n_valid, eosvos_stream_t stream);
 /* 2x2 / stride-2 transposed convolution of the mask head (tv MaskRCNNPredictor.conv5_mask) */
 int eosvos_deconv2x2_fprop(const void* x, const void* wd, const float* bias4, void* y, int N, int h, int w, int Cin,
                            int Cout, int flags, int bn_hint, eosvos_stream_t stream);

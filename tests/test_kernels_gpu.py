@@ -193,6 +193,24 @@ def test_gemm_wgrad_layouts():
     out = torch.zeros(Nout, Kin, device=dev())
     K().gemm_wgrad(bf(x).to(dev()), bf(dy).to(dev()), out, s_m=Kin)
     assert rel_err(out.cpu(), ref) < 1e-4
+    # stem layout: x = im2col with K = 49 taps x 3 channels zero-padded to 192 columns; the padding columns must not
+    # be written at all (their destination offsets fall outside dw) -- checked with a guard band and non-finite dy,
+    # which is what torch's CUDA-graph warm-up feeds through the backward
+    R, T_, I_, Cout_ = 500, 49, 3, 64
+    xs = torch.zeros(R, 192)
+    xs[:, :T_ * I_] = bf(torch.randn(R, T_ * I_, generator=g)).float()
+    dys = bf(torch.randn(R, Cout_, generator=g)).float()
+    refs = (dys.t() @ xs[:, :T_ * I_]).reshape(Cout_, T_, I_).permute(0, 2, 1).reshape(Cout_, I_ * T_)
+    buf = torch.zeros(Cout_ * I_ * T_ + 256, device=dev())
+    outs = buf[:Cout_ * I_ * T_].view(Cout_, I_ * T_)
+    K().gemm_wgrad(bf(xs).to(dev()), bf(dys).to(dev()), outs, s_m=I_ * T_, n_inner=I_, s_n_inner=T_, s_n_outer=1,
+                   n_valid=T_ * I_)
+    assert rel_err(outs.cpu(), refs) < 1e-4
+    dys[0, :] = float("inf")
+    buf.zero_()
+    K().gemm_wgrad(bf(xs).to(dev()), bf(dys).to(dev()), outs, s_m=I_ * T_, n_inner=I_, s_n_inner=T_, s_n_outer=1,
+                   n_valid=T_ * I_)
+    assert float(buf[Cout_ * I_ * T_:].abs().max()) == 0.0          # nothing (not even NaN = 0 * inf) past the end
 
 
 def test_deconv2x2():

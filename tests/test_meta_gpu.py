@@ -20,7 +20,7 @@ def test_fused_update_autograd_matches_torch():
         gs = [torch.randn(s, generator=g).to(dev) for s in shapes]
         raw = [torch.rand((s[0],) + (1,) * (len(s) - 1), generator=g).mul(1e-2).add(1e-3) for s in shapes]
         ls = [(r.log() if use_log else r).to(dev).requires_grad_(True) for r in raw]
-        outs = _FusedUpdateFn.apply(use_log, len(ps), None, *ps, *gs, *ls)
+        outs = _FusedUpdateFn.apply(use_log, len(ps), None, True, *ps, *gs, *ls)
         ref = [p - gg * (l.exp() if use_log else l) for p, gg, l in zip(ps, gs, ls)]
         ws = [torch.randn(s, generator=g).to(dev) for s in shapes]
         got = torch.autograd.grad(sum((o * w).sum() for o, w in zip(outs, ws)), ps + ls)
