@@ -51,6 +51,8 @@ SIGNATURES = {
     "eosvos_permute_cast": [_P, _P, _P, _P, _P, _I, _I, _P],
     "eosvos_permute_cast_multi_chunk_elems": [],
     "eosvos_permute_cast_multi": [_P, _P, _I, _P],
+    "eosvos_weight_prep_tile_elems": [],
+    "eosvos_weight_prep_multi": [_P, _P, _I, _P],
     "eosvos_affine_warp_cubic": [_P, _P, _P, _P, _I, _I, _I, _P],
     "eosvos_transform": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "eosvos_mask_resize_nearest": [_P, _P, _I, _I, _I, _I, _I, _P],

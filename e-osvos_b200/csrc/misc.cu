@@ -488,6 +488,75 @@ extern "C" int eosvos_permute_cast_multi(const long long* table_dev, const int* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tensor-core operand layouts of MANY parameter tensors in one launch, tiled through shared memory so that both the
+// fp32 reads and the 16-bit writes are coalesced (the element-wise kernels above read with a stride of KH*KW or
+// Cin*KH*KW floats).  Every layout the path needs is a permutation of a contiguous fp32 [X][Y][Z] tensor:
+//     dst[x * dx + y * dy + z * dz] = (act) src[(x * Y + y) * Z + z]          with dx == 1 or dy == 1
+//   conv fprop operand  [O][I][T] -> [O][T][I]   (dy = 1)        conv dgrad operand [O][I][T] -> [I][T][O]   (dx = 1)
+//   fc6 (NHWC pooling)  [O][C][S] -> [O][S][C]   (dy = 1)        its transpose      [O][C][S] -> [S][C][O]   (dx = 1)
+// table: int64 [n][10] = (src, dst, X, Y, Z, dx, dy, dz, TX, TY); tiles: int32 [m][2] = (tensor, tile index).
+// One CTA = one TX x TY x Z tile (<= WP_TILE floats).
+// ---------------------------------------------------------------------------------------------
+namespace eosvos {
+constexpr int WP_TILE = 8192;
+__global__ void __launch_bounds__(256)
+weight_prep_kernel(const long long* __restrict__ table, const int* __restrict__ tiles) {
+  extern __shared__ float wp_smem[];
+  const int t = tiles[blockIdx.x * 2];
+  const int tile = tiles[blockIdx.x * 2 + 1];
+  const long long* e = table + (size_t)t * 10;
+  const float* __restrict__ src = reinterpret_cast<const float*>(e[0]);
+  act_t* __restrict__ dst = reinterpret_cast<act_t*>(e[1]);
+  const int X = (int)e[2], Y = (int)e[3], Z = (int)e[4];
+  const long long dx = e[5], dy = e[6], dz = e[7];
+  const int TX = (int)e[8], TY = (int)e[9];
+  const int tiles_y = (Y + TY - 1) / TY;
+  const int x0 = (tile / tiles_y) * TX, y0 = (tile % tiles_y) * TY;
+  const int nx = min(TX, X - x0), ny = min(TY, Y - y0);
+  const int RL = ny * Z;                 // contiguous floats per x row of this tile
+  const int RLP = (TY * Z) | 1;          // odd row pitch: conflict-free column reads
+  for (int i = threadIdx.x; i < nx * RL; i += 256) {
+    const int x = i / RL, r = i - x * RL;
+    wp_smem[x * RLP + r] = __ldg(src + ((size_t)(x0 + x) * Y + y0) * Z + r);
+  }
+  __syncthreads();
+  if (dy == 1) {
+    for (int i = threadIdx.x; i < nx * RL; i += 256) {
+      const int yi = i % ny;
+      const int rem = i / ny;
+      const int z = rem % Z, x = rem / Z;
+      dst[(long long)(x0 + x) * dx + (y0 + yi) + (long long)z * dz] = float2act(wp_smem[x * RLP + yi * Z + z]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < nx * RL; i += 256) {
+      const int xi = i % nx;
+      const int r = i / nx;
+      const int y = r / Z, z = r - y * Z;
+      dst[(long long)(x0 + xi) + (long long)(y0 + y) * dy + (long long)z * dz] = float2act(wp_smem[xi * RLP + r]);
+    }
+  }
+}
+}  // namespace eosvos
+
+extern "C" int eosvos_weight_prep_tile_elems(void) { return eosvos::WP_TILE; }
+
+extern "C" int eosvos_weight_prep_multi(const long long* table_dev, const int* tiles_dev, int num_tiles,
+                                        eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (num_tiles == 0) return 0;
+  EOSVOS_REQUIRE(table_dev && tiles_dev, "weight_prep_multi: null table");
+  constexpr int SMEM = (eosvos::WP_TILE + 64) * (int)sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e2 = cudaFuncSetAttribute(eosvos::weight_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e2 != cudaSuccess) return eosvos::set_cuda_error(e2, "cudaFuncSetAttribute(weight_prep)");
+    attr_done = true;
+  }
+  eosvos::weight_prep_kernel<<<num_tiles, 256, SMEM, stream>>>(table_dev, tiles_dev);
+  return eosvos::check_launch("weight_prep_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
 // First-frame augmentation on the device: horizontal flip + rotate/scale about the centre with bicubic
 // (a = -0.75, constant-0 border) sampling -- the image half of the reference's RandomHorizontalFlip +
 // RandomScaleNRotate (src/data/custom_transforms.py:40-51,188-211; cv2.warpAffine INTER_CUBIC).  The label half

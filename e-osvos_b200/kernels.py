@@ -496,6 +496,86 @@ def permute_cast_multi(jobs):
     call("eosvos_permute_cast_multi", _ptr(table), _ptr(hit[0]), hit[1], _stream())
 
 
+def _xyz_of_spec(dims, ss, ds):
+    """(dims, src strides, dst strides) of a permuting cast -> (X, Y, Z, dx, dy, dz) with the source contiguous as
+    [X][Y][Z], or None when the source is not a contiguous 3-D walk or neither dx nor dy is 1."""
+    ax = [(int(s), int(n), int(d)) for n, s, d in zip(dims, ss, ds) if int(n) > 1]
+    ax.sort(key=lambda a: -a[0])
+    if ax and ax[-1][0] == 1 and ax[-1][2] == 1:
+        ax.append((0, 1, 0))            # fastest axis unchanged (plain cast): Z = 1, the run is the Y axis
+    while len(ax) < 3:
+        ax.insert(0, (0, 1, 0))
+    if len(ax) != 3:
+        return None
+    (sx, X, dx), (sy, Y, dy), (sz, Z, dz) = ax
+    if sz not in (1, 0) or (Y > 1 and sy != Z) or (X > 1 and sx != Y * Z):
+        return None
+    if Z == 1 and dy != 1 and dx != 1:
+        return None
+    if dy != 1 and dx != 1:
+        return None
+    return X, Y, Z, dx, dy, dz
+
+
+def weight_prep_table(jobs):
+    """jobs: list of (src fp32 tensor, dst ACT tensor, X, Y, Z, dx, dy, dz) -> (int64 table [n,10], int32 tiles [m,2])
+    for eosvos_weight_prep_multi (host numpy arrays)."""
+    import numpy as np
+    cap = _lib.load().eosvos_weight_prep_tile_elems()
+    tab = np.empty((len(jobs), 10), dtype=np.int64)
+    tid, tix = [], []
+    for t, (src, dst, X, Y, Z, dx, dy, dz) in enumerate(jobs):
+        if dy == 1:
+            TY = min(Y, max(1, min(128, cap // Z)))
+            TX = max(1, min(X, 64, cap // (TY * Z)))
+        else:
+            TX = min(X, 32)
+            TY = max(1, min(Y, cap // (TX * Z)))
+        if TX * TY * Z > cap:
+            raise _lib.EosvosError("weight_prep: innermost source dimension too long for one tile")
+        tab[t] = (src.data_ptr(), dst.data_ptr(), X, Y, Z, dx, dy, dz, TX, TY)
+        n = ((X + TX - 1) // TX) * ((Y + TY - 1) // TY)
+        tid.append(np.full(n, t, dtype=np.int32))
+        tix.append(np.arange(n, dtype=np.int32))
+    tiles = np.stack([np.concatenate(tid), np.concatenate(tix)], 1).copy() if jobs else np.zeros((0, 2), np.int32)
+    return tab, tiles
+
+
+class WeightPrepPlan:
+    """A fixed set of (parameter address -> operand buffer) conversions with its tables resident on the device:
+    `launch()` is ONE kernel with static arguments, so it can be captured into a CUDA graph."""
+
+    def __init__(self, jobs, device):
+        tab, tiles = weight_prep_table(jobs)
+        self.table = torch.from_numpy(tab).to(device)
+        self.tiles = torch.from_numpy(tiles).to(device)
+        self.num_tiles = int(tiles.shape[0])
+        self.keep = [(j[0], j[1]) for j in jobs]
+
+    def launch(self):
+        call("eosvos_weight_prep_multi", _ptr(self.table), _ptr(self.tiles), self.num_tiles, _stream())
+
+
+_wp_tile_cache = {}
+
+
+def weight_prep_multi(jobs):
+    """Eager variant: tables staged through pinned memory (tile list cached per shape signature)."""
+    if not jobs:
+        return
+    dev = jobs[0][0].device
+    key = (str(dev), tuple((j[2], j[3], j[4], j[5], j[6], j[7]) for j in jobs))
+    tab, tiles = weight_prep_table(jobs)
+    hit = _wp_tile_cache.get(key)
+    if hit is None:
+        hit = (torch.from_numpy(tiles).to(dev), int(tiles.shape[0]))
+        if len(_wp_tile_cache) > 8:
+            _wp_tile_cache.clear()
+        _wp_tile_cache[key] = hit
+    table = stager.put(tab, dev)
+    call("eosvos_weight_prep_multi", _ptr(table), _ptr(hit[0]), hit[1], _stream())
+
+
 def affine_warp_cubic(src_chw, minv, flip, B):
     """src [3,H,W] fp32, minv [B,6] fp32 (dst->src), flip [B] int32 -> [B,3,H,W] fp32 (bicubic, zero border)."""
     _chk(src_chw, torch.float32, "src")

@@ -115,6 +115,7 @@ class MaskRCNN(_MaskRCNN):
         self._prefetched = {}
         self._pf_slot = 0
         self._theta_home = None
+        self._active_plan = None
 
     # ---- reference API (mask_rcnn.py:523-570) ------------------------------------------------
     def replace_batch_with_group_norms(self):
@@ -321,6 +322,12 @@ class MaskRCNN(_MaskRCNN):
         saved = [m._parameters[n] for m, n in slots]
         for (m, n), t in zip(slots, theta):
             m._parameters[n] = t
+        if self._active_plan is not None:
+            # every 16-bit tensor-core operand of the trunk in ONE launch (static tables -> capturable); the fused
+            # small-head operands are rebuilt by the first pyramid level of each call
+            self._active_plan.launch()
+            for k in [k for k in ops._scope if isinstance(k[1], tuple) and k[1][0] == "head"]:
+                del ops._scope[k]
         try:
             # the RPN head (shared 3x3 conv + objectness / box 1x1s on every level) has static shapes too: inside
             # the graph its ~15 forward and ~45 backward launches cost no host time on the critical path
@@ -384,14 +391,32 @@ class MaskRCNN(_MaskRCNN):
                 torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
             except AttributeError:
                 pass
+            # operand buffers + conversion tables of this graph instance (persistent: the graph bakes their addresses)
+            conv1 = self.backbone.body.conv1
+            reqs = []
+            for (m, n), t in zip(self._trunk_slots, sample[1:]):
+                if n != "weight" or not isinstance(m, nn.Conv2d):
+                    continue
+                if m is conv1:
+                    reqs.append((t, "stem"))
+                elif t.shape[0] >= 64:
+                    reqs.append((t, "f"))
+                    if grad_mode:
+                        reqs.append((t, "t"))
+            plan, vals = ops.build_prep_plan(reqs)
+            self._active_plan = plan
+            ops._scope = {(id(reqs[i][0]), kind): v for (i, kind), v in vals.items()}
             c0 = _lib.launch_count()
-            with torch.enable_grad() if grad_mode else torch.no_grad():
-                graphed = torch.cuda.make_graphed_callables(self._trunk_functional, tuple(sample))
+            try:
+                with torch.enable_grad() if grad_mode else torch.no_grad():
+                    graphed = torch.cuda.make_graphed_callables(self._trunk_functional, tuple(sample))
+            finally:
+                self._active_plan, ops._scope = None, None
             per_call = (_lib.launch_count() - c0) // 4      # 3 eager warm-up runs + 1 capture of the same kernels
             # the warm-up backward ran on uninitialised output gradients (torch's warm-up passes empty_like tensors):
             # never continue in a zero block it touched
             K.zero_pool.reset()
-            fn = (graphed, per_call)
+            fn = (graphed, per_call, plan, vals)
             if len(self._graphs) >= 6:          # bounded: graphs pin their activation pools
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = fn

@@ -136,25 +136,56 @@ def _spec_for(kind):
     raise KeyError(kind)
 
 
+def _prep_jobs(wd, kind):
+    """-> (outputs, tiled jobs, element-wise jobs) for one parameter and operand kind."""
+    outs, tiled, plain = [], [], []
+    for shape, dims, ss, ds in _spec_for(kind)(wd):
+        alloc = torch.zeros if kind == "stem" else torch.empty
+        out = alloc(shape, device=wd.device, dtype=ACT)
+        xyz = K._xyz_of_spec(dims, ss, ds)
+        if xyz is not None:
+            tiled.append((wd, out) + xyz)
+        else:
+            plain.append((wd, out, dims, ss, ds))
+        outs.append(out)
+    return outs, tiled, plain
+
+
 def prep_many(requests):
     """requests: iterable of (parameter, kind).  Builds every missing operand layout with ONE kernel launch."""
-    jobs, pending = [], []
+    tiled, plain, pending = [], [], []
     for w, kind in requests:
         if _cache_get(w, kind) is not None:
             continue
         wd = w.detach()
         if not wd.is_contiguous():
             wd = wd.contiguous()
-        outs = []
-        for shape, dims, ss, ds in _spec_for(kind)(wd):
-            alloc = torch.zeros if kind == "stem" else torch.empty
-            out = alloc(shape, device=wd.device, dtype=ACT)
-            jobs.append((wd, out, dims, ss, ds))
-            outs.append(out)
+        outs, t, p = _prep_jobs(wd, kind)
+        tiled += t
+        plain += p
         pending.append((w, kind, outs[0] if len(outs) == 1 else tuple(outs)))
-    K.permute_cast_multi(jobs)
+    K.weight_prep_multi(tiled)
+    K.permute_cast_multi(plain)
     for w, kind, val in pending:
         _cache_put(w, kind, val)
+
+
+# Operands prepared for the CUDA-graphed trunk: {(id(parameter tensor), kind): operand}.  Set by MaskRCNN while its
+# trunk function runs (warm-up, capture); the operands live in persistent buffers filled by ONE captured launch.
+_scope = None
+
+
+def build_prep_plan(requests):
+    """requests: list of (static parameter tensor, kind) -> (WeightPrepPlan, {(index, kind): operand}).  Every
+    layout must be expressible as a tiled permutation (all conv / stem kinds are)."""
+    jobs, vals = [], {}
+    for i, (w, kind) in enumerate(requests):
+        outs, t, p = _prep_jobs(w.detach(), kind)
+        if p:
+            raise K._lib.EosvosError(f"operand kind {kind} has no tiled layout")
+        jobs += t
+        vals[(i, kind)] = outs[0] if len(outs) == 1 else tuple(outs)
+    return K.WeightPrepPlan(jobs, requests[0][0].device), vals
 
 
 def _prep_direct(w, kind):
@@ -171,6 +202,10 @@ def _prep_direct(w, kind):
 
 
 def _prep_one(w, kind):
+    if _scope is not None:
+        hit = _scope.get((id(w), kind))
+        if hit is not None:
+            return hit
     if torch.cuda.is_current_stream_capturing():
         return _prep_direct(w, kind)
     hit = _cache_get(w, kind)
@@ -200,6 +235,10 @@ def _fused_head_w(ws, pad_to):
     """Stacks several [O_i, K(,1,1)] fp32 weights into one bf16 [pad_to,1,1,K] (zero rows beyond sum O_i)
     and the transposed [K,1,1,64] operand (zero-padded columns) used by the backward GEMMs."""
     kind = ("head", pad_to)
+    if _scope is not None:                                   # graphed trunk: built once per trunk call, reused by the
+        hit = _scope.get((id(ws[0]), kind))                  # other pyramid levels and by the backward
+        if hit is not None:
+            return hit
     capturing = torch.cuda.is_current_stream_capturing()     # inside a CUDA graph the operands must be rebuilt from
     hit = None if capturing else _cache_get(ws[0], kind)     # the graph's static inputs on every replay: no caching
     if hit is not None and all(a is b() and a._version == v for a, (b, v) in zip(ws[1:], hit[2])):
@@ -210,7 +249,9 @@ def _fused_head_w(ws, pad_to):
     wf.view(pad_to, Kd)[:O] = flat.to(ACT)
     wt = torch.zeros((Kd, 1, 1, 64), device=flat.device, dtype=ACT)
     wt.view(Kd, 64)[:, :O] = flat.t().to(ACT)
-    if not capturing:
+    if _scope is not None:
+        _scope[(id(ws[0]), kind)] = (wf, wt)
+    elif not capturing:
         _cache_put(ws[0], kind, (wf, wt, [(weakref.ref(w), w._version) for w in ws[1:]]))
     return wf, wt
 

@@ -122,6 +122,12 @@ int eosvos_permute_cast(const void* src, void* dst, const long long* dims, const
  * (src, dst, dims[4], src strides[4], dst strides[4]), chunks int32 [n][2] = (tensor, chunk index) */
 int eosvos_permute_cast_multi_chunk_elems(void);
 int eosvos_permute_cast_multi(const long long* table_dev, const int* chunks_dev, int num_chunks, eosvos_stream_t stream);
+/* Tensor-core operand layouts of many fp32 parameter tensors in one launch (what cuDNN does internally for the
+ * reference, src/networks/mask_rcnn.py:716): dst[x*dx + y*dy + z*dz] = (16-bit) src[(x*Y + y)*Z + z], dx == 1 or
+ * dy == 1.  table: int64 [n][10] = (src, dst, X, Y, Z, dx, dy, dz, TX, TY) with TX*TY*Z <= tile_elems;
+ * tiles: int32 [m][2] = (tensor, tile index), tile = (x / TX) * ceil(Y / TY) + y / TY. */
+int eosvos_weight_prep_tile_elems(void);
+int eosvos_weight_prep_multi(const long long* table_dev, const int* tiles_dev, int num_tiles, eosvos_stream_t stream);
 /* device half of the first-frame augmentation (reference: src/data/custom_transforms.py:40-51,188-211) */
 int eosvos_affine_warp_cubic(const float* src, const float* minv, const int* flip, float* dst, int B, int H, int W,
                              eosvos_stream_t stream);

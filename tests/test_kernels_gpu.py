@@ -390,6 +390,42 @@ def test_meta_update_bit_exact():
                 assert torch.equal(o.cpu(), r)
 
 
+def test_weight_prep_layouts():
+    """Tiled multi-tensor operand preparation (one launch) == torch permute + cast, for every layout kind."""
+    from eosvos_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    act = K().ACT_DTYPE
+
+    def rnd(*s):
+        return torch.randn(*s, generator=g).to(dev())
+    w3, w1, w7 = rnd(96, 40, 3, 3), rnd(130, 72, 1, 1), rnd(64, 3, 7, 7)
+    fc6, fc7, dc = rnd(72, 49 * 24), rnd(40, 72), rnd(24, 16, 2, 2)
+    reqs = [(w3, "f"), (w3, "t"), (w1, "f"), (w1, "t"), (w7, "stem"), (fc6, ("lf", 24)), (fc6, ("lt", 24)),
+            (fc7, ("lf", 0)), (fc7, ("lt", 0)), (dc, "dc")]
+    ops.clear_prep_cache()
+    ops.prep_many(reqs)
+    got = [ops._cache_get(w, k) for w, k in reqs]
+    ref = [w3.permute(0, 2, 3, 1), w3.permute(1, 2, 3, 0), w1.permute(0, 2, 3, 1), w1.permute(1, 2, 3, 0)]
+    for a, b in zip(got[:4], ref):
+        assert torch.equal(a, b.contiguous().to(act))
+    stem = torch.zeros(64, 192, device=dev())
+    stem[:, :147] = w7.permute(0, 2, 3, 1).reshape(64, 147)
+    assert torch.equal(got[4].view(64, 192), stem.to(act))
+    f6 = fc6.view(72, 24, 49).permute(0, 2, 1).reshape(72, 49 * 24)           # (c, s) -> (s, c)
+    assert torch.equal(got[5].view(72, -1), f6.to(act))
+    assert torch.equal(got[6].view(49 * 24, 72), f6.t().contiguous().to(act))
+    assert torch.equal(got[7].view(40, 72), fc7.to(act))
+    assert torch.equal(got[8].view(72, 40), fc7.t().contiguous().to(act))
+    wf, wt = got[9]
+    assert torch.equal(wf.view(4, 16, 24), dc.permute(2, 3, 1, 0).reshape(4, 16, 24).to(act))
+    assert torch.equal(wt.view(24, 4, 16), dc.permute(0, 2, 3, 1).reshape(24, 4, 16).to(act))
+    # the same layouts through a persistent plan (what the CUDA-graphed trunk captures)
+    plan, vals = ops.build_prep_plan(reqs[:5])
+    plan.launch()
+    for i, (w, k) in enumerate(reqs[:5]):
+        assert torch.equal(vals[(i, k)], got[i])
+
+
 def test_transform_and_stem():
     g = torch.Generator().manual_seed(4)
     img = torch.rand(2, 3, 120, 214, generator=g)
