@@ -210,7 +210,9 @@ def update_roofline(device, meta_optim, model, peaks, peak_kind, reps=20):
     """HBM roofline of the fused MetaOptimizer update on the real 201-tensor parameter set (528.1 MB / step)."""
     from eosvos_b200 import kernels as K
     params = [p.detach() for *_, p in meta_optim.meta_model.param_groups()]
-    grads = [torch.randn_like(p) for p in params]
+    # gradients in the layouts the backward produces: KxK filter gradients arrive channels_last (wgrad epilogue)
+    grads = [torch.randn_like(p).contiguous(memory_format=torch.channels_last) if (p.dim() == 4 and p.shape[-1] > 1)
+             else torch.randn_like(p) for p in params]
     lrs = [l.detach() for l in meta_optim.state["log_lr"]]
     outs = [torch.empty_like(p) for p in params]
     plan = K.MetaUpdatePlan(params, grads, lrs, outs)
@@ -338,12 +340,18 @@ def main():
     def host_batch(i):
         # end to end: frame 0 goes H2D once per step (block); every iteration draws fresh random flips/rotations/
         # scales (host, reference RNG order), warps the label on the host (nearest) and the image on the GPU (bicubic)
+        # (the host half of the NEXT block's first iterations is started while this block finishes, as a per-object
+        # driver would do for the next object)
         if i % ITERS_PER_STEP == 1 or "aug" not in e2e_state:
             if "aug" in e2e_state:
                 e2e_state["aug"].close()
-            e2e_state["aug"] = augment.PrefetchingAugmenter(pin_frame0.to(device, non_blocking=True), gt0_np, BATCH,
-                                                            lambda e: 1 + e)
-        return e2e_state["aug"].get(i)
+            e2e_state["aug"] = e2e_state.pop("next", None) or augment.PrefetchingAugmenter(
+                pin_frame0.to(device, non_blocking=True), gt0_np, BATCH, lambda e: 1 + e, first_epoch=i)
+        out = e2e_state["aug"].get(i)
+        if i % ITERS_PER_STEP == 0:
+            e2e_state["next"] = augment.PrefetchingAugmenter(pin_frame0.to(device, non_blocking=True), gt0_np, BATCH,
+                                                             lambda e: 1 + e, first_epoch=i + 1)
+        return out
 
     def host_frame(i):
         return pin_frames[i].to(device, non_blocking=True)

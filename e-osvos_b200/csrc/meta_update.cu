@@ -38,7 +38,37 @@ meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ 
     const unsigned filt = (unsigned)g_taps * (unsigned)g_cin;
     const unsigned rl = (unsigned)row_len;
     const unsigned end = (unsigned)(start + n);
-    for (unsigned i = (unsigned)start + threadIdx.x; i < end; i += MU_THREADS) {
+    const bool al16 = (((e[0] | e[3]) & 15) == 0);
+    const unsigned nv = al16 ? (unsigned)(n >> 2) : 0u;       // 4 consecutive parameters per thread, 128-bit p / out
+    for (unsigned v = threadIdx.x; v < nv; v += MU_THREADS) {
+      const unsigned i = (unsigned)start + (v << 2);
+      unsigned co = i / filt;
+      const unsigned rem = i - co * filt;
+      unsigned ci = rem / (unsigned)g_taps;
+      unsigned tp = rem - ci * (unsigned)g_taps;
+      const float4 pv = *reinterpret_cast<const float4*>(p + i);
+      float gq[4], lq[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        gq[k] = __ldg(g + (size_t)co * filt + tp * (unsigned)g_cin + ci);
+        const float lv = __ldg(lr + (i + k) / rl);
+        lq[k] = use_log ? expf(lv) : lv;
+        if (++tp == (unsigned)g_taps) {
+          tp = 0;
+          if (++ci == (unsigned)g_cin) {
+            ci = 0;
+            ++co;
+          }
+        }
+      }
+      float4 o;
+      o.x = __fsub_rn(pv.x, __fmul_rn(gq[0], lq[0]));
+      o.y = __fsub_rn(pv.y, __fmul_rn(gq[1], lq[1]));
+      o.z = __fsub_rn(pv.z, __fmul_rn(gq[2], lq[2]));
+      o.w = __fsub_rn(pv.w, __fmul_rn(gq[3], lq[3]));
+      *reinterpret_cast<float4*>(out + i) = o;
+    }
+    for (unsigned i = (unsigned)start + (nv << 2) + threadIdx.x; i < end; i += MU_THREADS) {
       const unsigned co = i / filt;
       const unsigned rem = i - co * filt;
       const unsigned ci = rem / (unsigned)g_taps;

@@ -701,10 +701,48 @@ class MaskRCNN(_MaskRCNN):
         ncls = mp.mask_fcn_logits.weight.shape[0]
         return o[:, :ncls].reshape(n, M, M, ncls).permute(0, 3, 1, 2).contiguous()   # [n, ncls, M, M] fp32
 
+    def _select_training_samples(self, proposals, targets):
+        """tv roi_heads.py:642-678 (select_training_samples) + _utils.py BalancedPositiveNegativeSampler with the same
+        operations in the same order (same torch.randperm calls => same random stream), but ONE host sync (the
+        candidate counts of all images) instead of four `torch.where` syncs per image: every index list is then a
+        `nonzero_static` of known size.  Also returns the positions of the positives inside each image's sample."""
+        rh = self.roi_heads
+        dtype, device = proposals[0].dtype, proposals[0].device
+        gt_boxes = [t["boxes"].to(dtype) for t in targets]
+        gt_labels = [t["labels"] for t in targets]
+        if any(g.numel() == 0 for g in gt_boxes):          # background image: keep torchvision's own special-casing
+            p, m, l, r = rh.select_training_samples(proposals, targets)
+            return p, m, l, r, [torch.nonzero(x > 0).squeeze(1) for x in l]
+        proposals = rh.add_gt_proposals(proposals, gt_boxes)
+        matched_idxs, labels = rh.assign_targets_to_proposals(proposals, gt_boxes, gt_labels)
+        counts = torch.stack([torch.stack(((l >= 1).sum(), (l == 0).sum())) for l in labels]).tolist()
+        sampler = rh.fg_bg_sampler
+        out_p, out_m, out_l, out_g, pos_in = [], [], [], [], []
+        for i, (l, (npos, nneg)) in enumerate(zip(labels, counts)):
+            positive = torch.nonzero_static(l >= 1, size=npos).squeeze(1)
+            negative = torch.nonzero_static(l == 0, size=nneg).squeeze(1)
+            num_pos = min(npos, int(sampler.batch_size_per_image * sampler.positive_fraction))
+            num_neg = min(nneg, sampler.batch_size_per_image - num_pos)
+            perm1 = torch.randperm(npos, device=device)[:num_pos]
+            perm2 = torch.randperm(nneg, device=device)[:num_neg]
+            mask = torch.zeros_like(l, dtype=torch.bool)
+            mask[positive[perm1]] = True
+            mask[negative[perm2]] = True
+            inds = torch.nonzero_static(mask, size=num_pos + num_neg).squeeze(1)
+            p_i, l_i, m_i = proposals[i][inds], l[inds], matched_idxs[i][inds]
+            out_p.append(p_i)
+            out_l.append(l_i)
+            out_m.append(m_i)
+            out_g.append(gt_boxes[i][m_i])
+            pos_in.append(torch.nonzero_static(l_i > 0, size=num_pos).squeeze(1))
+        regression_targets = rh.box_coder.encode(out_g, out_p)
+        return out_p, out_m, out_l, regression_targets, pos_in
+
     def _roi_heads(self, feats, proposals, image_sizes, targets):
         rh = self.roi_heads
         if self.training:
-            proposals, matched_idxs, labels, regression_targets = rh.select_training_samples(proposals, targets)
+            proposals, matched_idxs, labels, regression_targets, pos_in = self._select_training_samples(proposals,
+                                                                                                        targets)
         Pb = self._roi_sizes['box']
         bx = ops.roi_align(feats[:4], self._SCALES, self._rois5(proposals), Pb)
         R, _, _, C = bx.shape
@@ -724,7 +762,7 @@ class MaskRCNN(_MaskRCNN):
             losses = dict(loss_classifier=loss_classifier, loss_box_reg=loss_box_reg)
             mask_proposals, pos_matched_idxs = [], []
             for img_id in range(len(proposals)):
-                pos = torch.nonzero(labels[img_id] > 0).squeeze(1)
+                pos = pos_in[img_id]
                 mask_proposals.append(proposals[img_id][pos])
                 pos_matched_idxs.append(matched_idxs[img_id][pos])
         else:

@@ -117,18 +117,38 @@ class PrefetchingAugmenter:
     its own random.Random(seed_for_epoch(epoch)) -- the same stream the reference gets from
     set_random_seeds(seed + epoch + round) (src/util/evaluate.py:221-222) followed by the dataset's transforms."""
 
-    def __init__(self, frame0_chw_device, gt_hw, batch_size, seed_for_epoch, depth=3):
+    # pinned rings and the worker thread are shared by successive augmenters (one per object / adaptation block):
+    # cudaHostAlloc of ~20 MB costs milliseconds, which would otherwise be paid at the start of every block
+    _rings = {}
+    _pool = None
+
+    def __init__(self, frame0_chw_device, gt_hw, batch_size, seed_for_epoch, depth=3, first_epoch=None):
         import torch
         from concurrent.futures import ThreadPoolExecutor
         self.aug = DeviceAugmenter(frame0_chw_device, gt_hw)
         self.batch_size, self.seed_for_epoch, self.depth = batch_size, seed_for_epoch, depth
         h, w = self.aug.h, self.aug.w
-        self.ring = [(torch.empty((batch_size, 6), dtype=torch.float32).pin_memory(),
-                      torch.empty((batch_size,), dtype=torch.int32).pin_memory(),
-                      torch.empty((batch_size, 1, h, w), dtype=torch.float32).pin_memory()) for _ in range(depth + 1)]
-        self.pool = ThreadPoolExecutor(max_workers=1)
+        key = (batch_size, h, w, depth)
+        rings = PrefetchingAugmenter._rings.setdefault(key, [])
+        # two rings alternate, so an augmenter created while its predecessor still has copies in flight never
+        # writes into that predecessor's buffers
+        if len(rings) < 2:
+            rings.append([(torch.empty((batch_size, 6), dtype=torch.float32).pin_memory(),
+                           torch.empty((batch_size,), dtype=torch.int32).pin_memory(),
+                           torch.empty((batch_size, 1, h, w), dtype=torch.float32).pin_memory())
+                          for _ in range(depth + 1)])
+            self.ring = rings[-1]
+        else:
+            rings.append(rings.pop(0))
+            self.ring = rings[-1]
+        if PrefetchingAugmenter._pool is None:
+            PrefetchingAugmenter._pool = ThreadPoolExecutor(max_workers=1)
+        self.pool = PrefetchingAugmenter._pool
         self.futures = {}
         self.next_slot = 0
+        if first_epoch is not None:          # start the host half now (e.g. while the previous block still runs)
+            for e in range(first_epoch, first_epoch + depth):
+                self._submit(e)
 
     def _submit(self, epoch):
         slot = self.ring[self.next_slot % len(self.ring)]
@@ -149,4 +169,6 @@ class PrefetchingAugmenter:
         return self.aug.device_part(*slot)
 
     def close(self):
-        self.pool.shutdown(wait=False, cancel_futures=True)
+        for f in self.futures.values():
+            f.cancel()
+        self.futures.clear()
