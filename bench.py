@@ -203,7 +203,7 @@ def conv_roofline(device, peaks, peak_kind, reps=20):
             "peak": peak, "peak_kind": f"{peak_kind} burst (kernel timed alone)", "unit": "TFLOP/s",
             "frac": round(achieved / peak, 4), "flops_per_launch": flops, "us_per_launch": round(dur * 1e6, 1),
             # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/README.md §2)
-            "traffic": 151996160}
+            "traffic": 153211648}
 
 
 def update_roofline(device, meta_optim, model, peaks, peak_kind, reps=20):
@@ -231,7 +231,7 @@ def update_roofline(device, meta_optim, model, peaks, peak_kind, reps=20):
     return {"bound": "hbm", "kernel": "meta_update_kernel (201 tensors, 43,975,515 params)",
             "achieved": round(nbytes / dur / 1e9, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
             "frac": round(nbytes / dur / 1e9 / peak, 4), "bytes_per_launch": nbytes, "us_per_launch": round(dur * 1e6, 1),
-            "traffic": 484998656}
+            "traffic": 491065856}
 
 
 def cpu_baseline(sample_iters=1, sample_frames=1):
