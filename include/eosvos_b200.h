@@ -106,6 +106,9 @@ int eosvos_nms_segments(const float* boxes, const int* seg_off, int num_segments
                         void* scratch, unsigned char* keep, eosvos_stream_t stream);
 
 /* ---- K9: MetaOptimizer update (reference: meta_optim.py:177-214, meta_model.py:78-80) */
+/* table_dev: int64 [T][8] = (p, g, lr, out, numel, elements per lr row, g_taps, g_cin); g_taps > 1 means the gradient
+ * of a [Cout][Cin][taps] filter is stored [Cout][taps][Cin] (channels_last, eosvos_conv2d_wgrad dw_layout 1);
+ * chunks_dev: int32 [n][2] = (tensor, chunk index), chunk = eosvos_meta_update_chunk_elems() elements.  out may alias p. */
 int eosvos_meta_update_chunk_elems(void);
 int eosvos_meta_update(const long long* table_dev, const int* chunks_dev, int num_chunks, int use_log,
                        eosvos_stream_t stream);
