@@ -27,7 +27,7 @@ SIGNATURES = {
     "eosvos_launch_count": [],
     "eosvos_act_dtype": [],
     "eosvos_conv2d_fprop": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "eosvos_conv2d_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "eosvos_conv2d_dgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "eosvos_conv2d_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _P],
     "eosvos_gemm_wgrad": [_P, _P, _P, _L, _I, _I, _L, _I, _L, _L, _F, _I, _I, _I, _P],
     "eosvos_deconv2x2_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -278,11 +278,12 @@ extern "C" int eosvos_conv2d_fprop(const void* x, const void* w, const float* bi
 // stride 1: one fprop-style launch with mirrored tap offsets.  stride 2: one launch per input
 // parity class (each class sees only the taps that reach it), no atomics, no zero-insertion.
 // ---------------------------------------------------------------------------------------------
-extern "C" int eosvos_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
-                                   int KH, int KW, int stride, int pad, int flags, int bn_hint,
+extern "C" int eosvos_conv2d_dgrad(const void* dy, const void* wt, void* dx, const void* acc, int N, int H, int W,
+                                   int Cin, int Cout, int KH, int KW, int stride, int pad, int flags, int bn_hint,
                                    eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EOSVOS_REQUIRE(dy && wt && dx, "conv2d_dgrad: null pointer");
+  EOSVOS_REQUIRE(!acc || stride == 1, "conv2d_dgrad: the accumulate operand needs stride 1");
   EOSVOS_REQUIRE(Cout % 64 == 0, "conv2d_dgrad: Cout must be a multiple of 64");
   EOSVOS_REQUIRE(Cin % 8 == 0, "conv2d_dgrad: Cin must be a multiple of 8");
   EOSVOS_REQUIRE(KH * KW <= MAX_TAPS && (stride == 1 || stride == 2), "conv2d_dgrad: unsupported filter");
@@ -311,6 +312,12 @@ extern "C" int eosvos_conv2d_dgrad(const void* dy, const void* wt, void* dx, int
     ep.odim[0] = W;
     ep.odim[1] = H;
     ep.odim[2] = N;
+    if (acc) {   // dx = dgrad + acc (gradient that reached the same tensor through another branch), added in fp32
+      ep.res = acc;
+      ep.rstride[0] = Cin;
+      ep.rstride[1] = (long long)W * Cin;
+      ep.rstride[2] = (long long)H * W * Cin;
+    }
     const int extent[4] = {W, H, N, 1};
     const bool flat = (KH == 1 && KW == 1 && pad == 0);
     if (flat) {
@@ -322,6 +329,10 @@ extern "C" int eosvos_conv2d_dgrad(const void* dy, const void* wt, void* dx, int
       ef.out_fp32 = out_fp32;
       ef.ostride[0] = Cin;
       ef.odim[0] = (int)M;
+      if (acc) {
+        ef.res = acc;
+        ef.rstride[0] = Cin;
+      }
       return run_fprop(avf, ext, cs, 0, -1, 1, taps, bk, Cout, wt, (uint64_t)Cin, (uint64_t)Cout, Cin, ef, bn_hint,
                        stream);
     }

@@ -176,7 +176,7 @@ gn_apply_kernel(const act_t* __restrict__ x, const float* __restrict__ sums, con
 //   MODE 0: dy_eff = dy;  1: dy_eff = dy * (xhat*gamma+beta > 0);  2: dy_eff = dy * (yout > 0)
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(GN_THREADS, MODE == 1 ? 2 : 3)
+__global__ void __launch_bounds__(GN_THREADS, 3)
 gn_bwd_reduce_kernel(const act_t* __restrict__ x, const float* __restrict__ sums,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      const act_t* __restrict__ dy, const act_t* __restrict__ yout,
@@ -189,17 +189,19 @@ gn_bwd_reduce_kernel(const act_t* __restrict__ x, const float* __restrict__ sums
   const int cpg = C / GN_GROUPS;
   const float inv_m = 1.f / ((float)cpg * (float)HW);
   for (int i = threadIdx.x; i < C * 2; i += GN_THREADS) smp[i] = 0.f;
-  // mask test (MODE 1): x*a + b > 0;   S2 accumulates dy_eff * (x - mean), scaled by rstd once at the end
-  float mean[8], a[8], b[8];
+  // mask test (MODE 1): x*a + b > 0.  The loop accumulates S1 = sum dy_eff and R = sum dy_eff * x; the statistics
+  // enter once at the end, S2 = rstd * (R - mean * S1), which keeps the loop at two coefficient and two accumulator
+  // registers per channel (3 CTAs of 256 threads per SM instead of 2)
+  float a[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = my_cv * 8 + k;
     const int g = c / cpg;
-    mean[k] = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
     if (MODE == 1) {
-      const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean[k] * mean[k], 0.f);
+      const float mean = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
+      const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean * mean, 0.f);
       a[k] = rsqrtf(var + eps) * gamma[c];
-      b[k] = beta[c] - mean[k] * a[k];
+      b[k] = beta[c] - mean * a[k];
     }
   }
   __syncthreads();
@@ -225,7 +227,7 @@ gn_bwd_reduce_kernel(const act_t* __restrict__ x, const float* __restrict__ sums
       float de = d[k];
       if (MODE == 1) de = (f[k] * a[k] + b[k] > 0.f) ? de : 0.f;
       s1[k] += de;
-      s2[k] += de * (f[k] - mean[k]);
+      s2[k] += de * f[k];
     }
   };
   int p = p0 + threadIdx.x / cv;
@@ -251,9 +253,10 @@ gn_bwd_reduce_kernel(const act_t* __restrict__ x, const float* __restrict__ sums
   for (int k = 0; k < 8; ++k) {
     const int c = my_cv * 8 + k;
     const int g = c / cpg;
-    const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean[k] * mean[k], 0.f);
+    const float mean = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
+    const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean * mean, 0.f);
     atomicAdd(&smp[c * 2], s1[k]);
-    atomicAdd(&smp[c * 2 + 1], s2[k] * rsqrtf(var + eps));
+    atomicAdd(&smp[c * 2 + 1], (s2[k] - mean * s1[k]) * rsqrtf(var + eps));
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * 2; i += GN_THREADS) {

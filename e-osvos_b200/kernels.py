@@ -156,8 +156,8 @@ def conv2d_fprop(x, w, bias=None, res=None, *, stride=1, pad=0, relu=False, out_
     return out
 
 
-def conv2d_dgrad(dy, wt, in_hw, *, stride=1, pad=0, out_fp32=False, bn_hint=0):
-    """dy [N,Ho,Wo,Cout] bf16, wt [Cin,KH,KW,Cout] bf16 -> dx [N,H,W,Cin]."""
+def conv2d_dgrad(dy, wt, in_hw, *, stride=1, pad=0, out_fp32=False, bn_hint=0, acc=None):
+    """dy [N,Ho,Wo,Cout] 16-bit, wt [Cin,KH,KW,Cout] 16-bit -> dx [N,H,W,Cin] (+ acc [N,H,W,Cin] 16-bit, stride 1)."""
     _chk(dy, ACT_DTYPE, "dy")
     _chk(wt, ACT_DTYPE, "wt")
     N, Ho, Wo, Cout = dy.shape
@@ -166,7 +166,10 @@ def conv2d_dgrad(dy, wt, in_hw, *, stride=1, pad=0, out_fp32=False, bn_hint=0):
     H, W = in_hw
     assert (H + 2 * pad - KH) // stride + 1 == Ho and (W + 2 * pad - KW) // stride + 1 == Wo
     dx = torch.empty((N, H, W, Cin), device=dy.device, dtype=torch.float32 if out_fp32 else ACT_DTYPE)
-    call("eosvos_conv2d_dgrad", _ptr(dy), _ptr(wt), _ptr(dx), N, H, W, Cin, Cout, KH, KW, stride, pad,
+    if acc is not None:
+        _chk(acc, ACT_DTYPE, "acc")
+        assert tuple(acc.shape) == (N, H, W, Cin) and acc.is_contiguous()
+    call("eosvos_conv2d_dgrad", _ptr(dy), _ptr(wt), _ptr(dx), _ptr(acc), N, H, W, Cin, Cout, KH, KW, stride, pad,
          FLAG_OUT_FP32 if out_fp32 else 0, bn_hint, _stream())
     return dx
 

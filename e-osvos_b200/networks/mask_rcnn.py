@@ -285,14 +285,21 @@ class MaskRCNN(_MaskRCNN):
 
     def _bottleneck(self, blk, x):
         s = blk.conv2.stride[0]
-        out = ops.conv_gn(x, blk.conv1.weight, *self._norm_args(blk.bn1), None, 1, 0, True)
+        # conv1 forks its input: the identity branch reads the alias, so its gradient is added inside conv1's dgrad
+        # epilogue instead of by a separate sum kernel over the block input (3 passes over up to 99 MB)
+        fork = torch.is_grad_enabled() and x.requires_grad and blk.conv1.stride[0] == 1
+        if fork:
+            out, xa = ops.conv_gn(x, blk.conv1.weight, *self._norm_args(blk.bn1), None, 1, 0, True, fork=True)
+        else:
+            out = ops.conv_gn(x, blk.conv1.weight, *self._norm_args(blk.bn1), None, blk.conv1.stride[0], 0, True)
+            xa = x
         out = ops.conv_gn(out, blk.conv2.weight, *self._norm_args(blk.bn2), None, s, 1, True)
         if blk.downsample is not None:
             ds = blk.downsample[0].stride[0]
-            identity = ops.conv_gn(x, blk.downsample[0].weight, *self._norm_args(blk.downsample[1]), None, ds, 0,
+            identity = ops.conv_gn(xa, blk.downsample[0].weight, *self._norm_args(blk.downsample[1]), None, ds, 0,
                                    False)
         else:
-            identity = x
+            identity = xa
         return ops.conv_gn(out, blk.conv3.weight, *self._norm_args(blk.bn3), identity, 1, 0, True)
 
     def theta_home(self):
@@ -335,9 +342,12 @@ class MaskRCNN(_MaskRCNN):
             lvl = int(os.environ.get("EOSVOS_GRAPH_HEAD", "2"))
             if lvl == 0:
                 return tuple(feats)
+            alias = list(feats)
             if lvl == 1:
-                return tuple(feats) + tuple(self._rpn_head(feats, stage=1))
-            return tuple(feats) + tuple(self._rpn_head(feats))
+                outs = self._rpn_head(feats, stage=1, alias=alias)
+            else:
+                outs = self._rpn_head(feats, alias=alias)
+            return tuple(alias) + tuple(outs)
         finally:
             for (m, n), t in zip(slots, saved):
                 m._parameters[n] = t
@@ -460,15 +470,23 @@ class MaskRCNN(_MaskRCNN):
             self._anchor_cache = {key: [a.detach() for a in self.rpn.anchor_generator(il, fms)]}
         return self._anchor_cache[key]
 
-    def _rpn_head(self, feats, stage=0):
+    def _rpn_head(self, feats, stage=0, alias=None):
         """tv RPNHead on every level: [pixels, 16] fp32 = (A objectness | 4A box deltas | padding) per level.
         stage 1: only the shared 3x3 conv; stage 2: only the 1x1 heads on its output (debug split)."""
         head = self.rpn.head
         conv = head.conv[0][0] if isinstance(head.conv, nn.Sequential) else head.conv
         outs = []
-        for f in feats:
+        for i, f in enumerate(feats):
             C = f.shape[-1]
-            t = f if stage == 2 else ops.conv2d(f, conv.weight, conv.bias, pad=1, relu=True)
+            if stage == 2:
+                t = f
+            elif alias is not None and torch.is_grad_enabled() and f.requires_grad:
+                # the level is also consumed outside (RoIAlign, coarser levels): hand out the alias so those
+                # gradients are added inside this conv's dgrad epilogue
+                t, fa = ops.conv2d(f, conv.weight, conv.bias, pad=1, relu=True, fork=True)
+                alias[i] = fa
+            else:
+                t = ops.conv2d(f, conv.weight, conv.bias, pad=1, relu=True)
             if stage == 1:
                 outs.append(t)
                 continue

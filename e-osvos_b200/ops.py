@@ -265,36 +265,46 @@ def _gn_cpg_ok(C):
 # --------------------------------------------------------------------------------------------
 class Conv2dFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, res, stride, pad, relu, res_half):
+    def forward(ctx, x, w, bias, res, stride, pad, relu, res_half, fork=False):
+        """fork=True (stride 1): also returns x itself; every OTHER consumer of x reads that alias, so in backward the
+        gradient they produce arrives here and is added inside the dgrad epilogue (no separate sum kernel)."""
         wf = prep_conv_w(w)
         y = K.conv2d_fprop(x, wf, bias.detach() if bias is not None else None, res, stride=stride, pad=pad, relu=relu,
                            res_half=res_half)
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.cfg = (stride, pad, relu, res_half, bias is not None, res is not None)
+        if fork:
+            ctx.set_materialize_grads(False)
+            return y, x
         return y
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dy):
+    def backward(ctx, dy, dxa=None):
         x, w, y = ctx.saved_tensors
         stride, pad, relu, res_half, has_bias, has_res = ctx.cfg
+        if dy is None:                       # only the alias was used
+            return dxa, None, None, None, None, None, None, None, None
         dy = dy.contiguous()
         if relu:
             dy = K.relu_bwd(dy, y)
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
-            dx = K.conv2d_dgrad(dy, prep_conv_wt(w), x.shape[1:3], stride=stride, pad=pad)
+            dx = K.conv2d_dgrad(dy, prep_conv_wt(w), x.shape[1:3], stride=stride, pad=pad,
+                                acc=dxa.contiguous() if dxa is not None else None)
         if ctx.needs_input_grad[1]:
             dw = K.conv2d_wgrad(x, dy, w.shape[2:], stride=stride, pad=pad, alpha=_inv_scale())
         if has_bias and ctx.needs_input_grad[2]:
             db = K.colsum(dy.view(-1, dy.shape[-1]), alpha=_inv_scale())
         if has_res and ctx.needs_input_grad[3]:
             dres = K.sum2x2(dy) if res_half else dy
-        return dx, dw, db, dres, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None
 
 
-def conv2d(x, w, bias=None, res=None, stride=1, pad=0, relu=False, res_half=False):
-    return Conv2dFn.apply(x, w, bias, res, stride, pad, relu, res_half)
+def conv2d(x, w, bias=None, res=None, stride=1, pad=0, relu=False, res_half=False, fork=False):
+    if fork:
+        assert stride == 1
+    return Conv2dFn.apply(x, w, bias, res, stride, pad, relu, res_half, fork)
 
 
 # --------------------------------------------------------------------------------------------
@@ -302,13 +312,14 @@ def conv2d(x, w, bias=None, res=None, stride=1, pad=0, relu=False, res_half=Fals
 # --------------------------------------------------------------------------------------------
 class ConvGnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, gamma, beta, res, stride, pad, relu):
+    def forward(ctx, x, w, gamma, beta, res, stride, pad, relu, fork=False):
         wf = prep_conv_w(w)
         N = x.shape[0]
-        # statistics ride in the conv epilogue when the K loop is long enough to hide them (>= 4 K blocks);
-        # short-K layers (e.g. 1x1 64->256) are epilogue-bound already, there a separate pass over the (mostly
-        # L2-resident) output is cheaper
-        if w.shape[1] * w.shape[2] * w.shape[3] >= 256:
+        # statistics ride in the conv epilogue when the K loop is long enough to hide them: measured on every
+        # ResNet-50 shape (tools/bench_gn_fprop.py), the fused form wins whenever K >= 4 * Cout and loses or ties
+        # for the expanding 1x1 convs (K <= Cout / 2: the epilogue, whose length grows with Cout, is the bound there
+        # and a separate pass over the mostly L2-resident output is cheaper)
+        if w.shape[1] * w.shape[2] * w.shape[3] >= 2 * w.shape[0]:
             sums = K.zero_pool.take((N, 32, 2), x.device)
             z = K.conv2d_fprop(x, wf, stride=stride, pad=pad, gn_sum=sums)
         else:
@@ -319,26 +330,36 @@ class ConvGnFn(torch.autograd.Function):
         mode = 0 if not relu else (2 if res is not None else 1)
         ctx.save_for_backward(x, w, gamma, beta, z, sums, y if mode == 2 else None)
         ctx.cfg = (stride, pad, mode, res is not None)
+        if fork:                             # see Conv2dFn.forward
+            ctx.set_materialize_grads(False)
+            return y, x
         return y
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dy):
+    def backward(ctx, dy, dxa=None):
         x, w, gamma, beta, z, sums, y = ctx.saved_tensors
         stride, pad, mode, has_res = ctx.cfg
+        if dy is None:
+            return dxa, None, None, None, None, None, None, None, None
         dy = dy.contiguous()
         dz, dres, dgamma, dbeta = K.gn_backward(z, sums, gamma.detach(), beta.detach(), dy, yout=y, mask_mode=mode,
                                                 want_dres=has_res and ctx.needs_input_grad[4], alpha=_inv_scale())
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = K.conv2d_dgrad(dz, prep_conv_wt(w), x.shape[1:3], stride=stride, pad=pad)
+            dx = K.conv2d_dgrad(dz, prep_conv_wt(w), x.shape[1:3], stride=stride, pad=pad,
+                                acc=dxa.contiguous() if dxa is not None else None)
+        elif dxa is not None:
+            dx = dxa
         if ctx.needs_input_grad[1]:
             dw = K.conv2d_wgrad(x, dz, w.shape[2:], stride=stride, pad=pad, alpha=_inv_scale())
-        return dx, dw, dgamma, dbeta, dres, None, None, None
+        return dx, dw, dgamma, dbeta, dres, None, None, None, None
 
 
-def conv_gn(x, w, gamma, beta, res=None, stride=1, pad=0, relu=True):
-    return ConvGnFn.apply(x, w, gamma, beta, res, stride, pad, relu)
+def conv_gn(x, w, gamma, beta, res=None, stride=1, pad=0, relu=True, fork=False):
+    if fork:
+        assert stride == 1
+    return ConvGnFn.apply(x, w, gamma, beta, res, stride, pad, relu, fork)
 
 
 # --------------------------------------------------------------------------------------------

@@ -46,9 +46,11 @@ int eosvos_act_dtype(void); /* 0 = bfloat16, 1 = float16 (default build) */
 int eosvos_conv2d_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, float* gn_sum,
                         int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int flags,
                         int bn_hint, eosvos_stream_t stream);
-/* dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], wt[Cin,KH,KW,Cout]) */
-int eosvos_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout, int KH,
-                        int KW, int stride, int pad, int flags, int bn_hint, eosvos_stream_t stream);
+/* dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], wt[Cin,KH,KW,Cout]) (+ acc[N,H,W,Cin], optional, stride 1 only:
+ * the gradient that reached the same activation through another branch -- autograd's separate sum kernel fused
+ * into the epilogue) */
+int eosvos_conv2d_dgrad(const void* dy, const void* wt, void* dx, const void* acc, int N, int H, int W, int Cin,
+                        int Cout, int KH, int KW, int stride, int pad, int flags, int bn_hint, eosvos_stream_t stream);
 /* dw (fp32) += alpha * x (*) dy ; the caller zeroes dw.  dw_layout 0: memory order [Cout][Cin][KH][KW] (torch
  * contiguous); 1: [Cout][KH][KW][Cin] (torch channels_last strides of the same logical [Cout,Cin,KH,KW] tensor:
  * the input channel is innermost, so the epilogue issues 16-byte vector reductions) */

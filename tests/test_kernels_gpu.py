@@ -157,6 +157,10 @@ def test_conv2d_dgrad(case):
     dx = K().conv2d_dgrad(bf(nhwc(dy)).to(dev()), wt, (H, W), stride=s, pad=p, bn_hint=bn if Cin % max(bn, 1) == 0 else 0)
     got = nchw(dx.float().cpu())
     assert rel_err(got, ref) < 4e-3, (case, rel_err(got, ref))
+    if s == 1:      # gradient of another branch accumulated in the epilogue (fp32 add, one rounding)
+        acc = bf(torch.randn(ref.shape, generator=g)).float()
+        dx2 = K().conv2d_dgrad(bf(nhwc(dy)).to(dev()), wt, (H, W), stride=s, pad=p, acc=bf(nhwc(acc)).to(dev()))
+        assert rel_err(nchw(dx2.float().cpu()), ref + acc) < 4e-3
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
