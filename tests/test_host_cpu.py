@@ -30,6 +30,47 @@ def test_library_exports_every_declared_symbol():
     assert lib.eosvos_device_check(0) != 0 and len(_lib.last_error()) > 0
 
 
+def test_weight_prep_tables_cover_every_layout():
+    """Host half of the tiled operand preparation: every layout spec maps to a contiguous [X][Y][Z] walk, and the
+    table / tile list reproduce torch's permute when the kernel's index arithmetic is replayed in numpy."""
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200 import kernels as K
+    from eosvos_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    cases = [(torch.randn(96, 40, 3, 3, generator=g), "f"), (torch.randn(96, 40, 3, 3, generator=g), "t"),
+             (torch.randn(130, 72, 1, 1, generator=g), "f"), (torch.randn(130, 72, 1, 1, generator=g), "t"),
+             (torch.randn(64, 3, 7, 7, generator=g), "stem"), (torch.randn(72, 49 * 24, generator=g), ("lf", 24)),
+             (torch.randn(72, 49 * 24, generator=g), ("lt", 24)), (torch.randn(40, 72, generator=g), ("lf", 0)),
+             (torch.randn(40, 72, generator=g), ("lt", 0)), (torch.randn(24, 16, 2, 2, generator=g), "dc")]
+    cap = K._lib.load().eosvos_weight_prep_tile_elems()
+    for w, kind in cases:
+        for shape, dims, ss, ds in ops._spec_for(kind)(w):
+            xyz = K._xyz_of_spec(dims, ss, ds)
+            assert xyz is not None, kind
+            X, Y, Z, dx, dy, dz = xyz
+            assert X * Y * Z == w.numel() and (dx == 1 or dy == 1)
+            # reference: the element-wise definition of the spec
+            n = int(np.prod(shape))
+            ref = np.zeros(n, np.float32)
+            src = w.reshape(-1).numpy()
+            idx = np.indices(dims).reshape(4, -1)
+            ref[(idx * np.array(ds)[:, None]).sum(0)] = src[(idx * np.array(ss)[:, None]).sum(0)]
+            # replay of weight_prep_kernel from the host tables
+            dst = torch.zeros(n)
+            tab, tiles = K.weight_prep_table([(w, dst, X, Y, Z, dx, dy, dz)])
+            TX, TY = int(tab[0, 8]), int(tab[0, 9])
+            assert TX * TY * Z <= cap and TX <= 64
+            out = np.zeros(n, np.float32)
+            tiles_y = (Y + TY - 1) // TY
+            assert tiles.shape[0] == ((X + TX - 1) // TX) * tiles_y
+            for _, tile in tiles:
+                x0, y0 = (tile // tiles_y) * TX, (tile % tiles_y) * TY
+                xs, ys = np.arange(x0, min(x0 + TX, X)), np.arange(y0, min(y0 + TY, Y))
+                xx, yy, zz = np.meshgrid(xs, ys, np.arange(Z), indexing="ij")
+                out[xx * dx + yy * dy + zz * dz] = src[(xx * Y + yy) * Z + zz]
+            assert np.array_equal(out, ref), kind
+
+
 def test_no_cpu_fallback():
     import eosvos_b200  # noqa: F401
     from eosvos_b200 import _lib, kernels
