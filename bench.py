@@ -59,6 +59,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.first = 0
+
+    def mark(self):
+        """Samples taken from here on belong to the timed region (the process itself is started before the warm-up:
+        nvidia-smi's start-up stalls the driver for a few hundred ms, which must not land inside the timing)."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -82,7 +88,7 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -361,14 +367,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for s in range(args.warmup):
         run_block(model, meta_optim, dev_batch, dev_frame, dev_target, s)
     # ---- timed region 1: device-resident inputs
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     l0 = _lib.launch_count()
     t0 = time.perf_counter()
     for s in range(args.steps):

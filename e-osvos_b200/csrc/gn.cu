@@ -363,9 +363,11 @@ __global__ void gn_bwd_param_kernel(const float* __restrict__ part, float* __res
 }
 
 static int gn_chunk(int HW, int N, int C, int* chunks) {
-  // ~3 resident CTAs per SM overall, two waves; each CTA covers whole unrolled passes of pixels
+  // exactly one wave of 3 resident CTAs per SM with equal work: the per-CTA prologue (32 dependent coefficient loads
+  // per thread) and the atomic epilogue are paid once per SM slot; each CTA covers whole unrolled passes of pixels
   const int pix_per_pass = GN_THREADS / (C >> 3) * GN_UNROLL;
-  int want = (6 * num_sms() + N - 1) / N;
+  int want = (3 * num_sms()) / N;
+  if (want < 1) want = 1;
   int chunk = (HW + want - 1) / want;
   chunk = ((chunk + pix_per_pass - 1) / pix_per_pass) * pix_per_pass;
   if (chunk < pix_per_pass) chunk = pix_per_pass;
