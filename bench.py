@@ -50,58 +50,92 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md recipe), read through NVML inside this
+    process every 100 ms (a light query; an `nvidia-smi -lms` child was measured to perturb the timed region by up to
+    12 %).  Falls back to one nvidia-smi query per second when NVML is unavailable."""
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []          # (sm_mhz, reason bitmask or list)
         self.first = 0
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.t = None
+        self.nvml = None
 
-    def mark(self):
-        """Samples taken from here on belong to the timed region (the process itself is started before the warm-up:
-        nvidia-smi's start-up stalls the driver for a few hundred ms, which must not land inside the timing)."""
-        self.first = len(self.lines)
+    def _gpu_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.gpu
+        if vis:
+            ent = vis.split(",")[self.gpu].strip()
+            if ent.isdigit():
+                idx = int(ent)
+            else:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(ent)
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.nvml, h = self._gpu_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(h, self.nvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll_nvml, args=(h,), daemon=True)
         except Exception:
-            self.proc = None
+            self.nvml = None
+            self.t = threading.Thread(target=self._poll_smi, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll_nvml(self, h):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)),
+                                     int(n.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                pass
+            self.stop_flag.wait(float(os.environ.get("EOSVOS_CLOCK_POLL_S", "0.1")))
+
+    def _poll_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.max_mhz = float(f[1])
+                self.samples.append((float(f[0]), [nm for (nm, _), v in zip(self.REASONS, f[2:6])
+                                                   if v.lower().startswith("active")]))
+            except Exception:
+                pass
+            self.stop_flag.wait(1.0)
+
+    def mark(self):
+        """Samples taken from here on belong to the timed region (the sampler itself starts before the warm-up)."""
+        self.first = len(self.samples)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines[self.first:]:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.t is not None:
+            self.t.join(timeout=3)
+        sel = self.samples[self.first:] or self.samples[-1:]
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
+        reasons = set()
+        for _, r in sel:
+            if isinstance(r, int):
+                for nm, attr in self.REASONS:
+                    if r & int(getattr(self.nvml, attr)):
+                        reasons.add(nm)
+            else:
+                reasons.update(r)
+        return {"sm_mhz": float(np.median([c for c, _ in sel])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(sel)}
 
 
 # ------------------------------------------------------------------------------------------------

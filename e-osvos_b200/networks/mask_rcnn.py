@@ -401,6 +401,8 @@ class MaskRCNN(_MaskRCNN):
         theta = [m._parameters[n] for m, n in slots]
         ent = self._graphs.get(key)
         if ent is None:
+            if os.environ.get("EOSVOS_DEBUG_GRAPHS"):
+                print("[eosvos] capturing graph", key[:2], "have", len(self._graphs), flush=True)
             arena, offs, shapes, index = self.theta_home()
             sample = [t.detach().clone().requires_grad_(t.requires_grad and grad_mode) for t in inputs]
             nin = len(sample)
@@ -806,8 +808,11 @@ class MaskRCNN(_MaskRCNN):
         if self.training:
             proposals, matched_idxs, labels, regression_targets, pos_in = self._select_training_samples(proposals,
                                                                                                         targets)
+        # (only the regular case -- every image filled its 512-RoI sample -- is worth a graph: odd sizes, e.g. when
+        # the RPN produced no proposal, would each cost a capture)
         graphed_box = (self.training and self.use_cuda_graphs and self.capture is None and torch.is_grad_enabled()
-                       and os.environ.get("EOSVOS_GRAPH_BOX", "1") != "0")
+                       and os.environ.get("EOSVOS_GRAPH_BOX", "1") != "0"
+                       and all(p.shape[0] == rh.fg_bg_sampler.batch_size_per_image for p in proposals))
         if graphed_box:
             # static shapes (512 sampled RoIs per image): the whole box branch, its loss and their backward replay as
             # a second pair of CUDA graphs; only the mask branch (n_pos RoIs) stays eager
