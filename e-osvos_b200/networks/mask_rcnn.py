@@ -393,7 +393,7 @@ class MaskRCNN(_MaskRCNN):
             return ()
         return list(self._graphed_call(key, self._trunk_functional, [x8], self._trunk_slots, kinds, grad_mode))
 
-    def _graphed_call(self, key, fn, inputs, slots, kinds, grad_mode):
+    def _graphed_call(self, key, fn, inputs, slots, kinds, grad_mode, alias_inputs=0):
         """Runs fn(*inputs, *theta) -- theta = the tensors currently installed in `slots` -- as a CUDA graph (forward
         and, in grad mode, backward), capturing it on first use.  The graph's static parameter inputs are the
         parameters' home addresses (theta_home), its tensor-core operands live in persistent buffers filled by one
@@ -404,7 +404,10 @@ class MaskRCNN(_MaskRCNN):
             if os.environ.get("EOSVOS_DEBUG_GRAPHS"):
                 print("[eosvos] capturing graph", key[:2], "have", len(self._graphs), flush=True)
             arena, offs, shapes, index = self.theta_home()
-            sample = [t.detach().clone().requires_grad_(t.requires_grad and grad_mode) for t in inputs]
+            # the first `alias_inputs` inputs already live at fixed addresses (static outputs of another graph): the
+            # new graph reads them in place instead of receiving a copy on every call
+            sample = [(t.detach() if i < alias_inputs else t.detach().clone()).requires_grad_(t.requires_grad and grad_mode)
+                      for i, t in enumerate(inputs)]
             nin = len(sample)
             with torch.no_grad():
                 for (m, n), t in zip(slots, theta):
@@ -832,7 +835,8 @@ class MaskRCNN(_MaskRCNN):
                 return (("lf", inner), ("lt", inner))
             key = ("box", tuple(rois5.shape), tuple(tuple(f.shape) for f in feats[:4]), feats[0].device.index)
             loss_classifier, loss_box_reg = self._graphed_call(
-                key, self._box_train_functional, list(feats[:4]) + [rois5, lab_c, reg_c], self._box_slots, kinds, True)
+                key, self._box_train_functional, list(feats[:4]) + [rois5, lab_c, reg_c], self._box_slots, kinds, True,
+                alias_inputs=4)
             class_logits = box_regression = None
         else:
             o = self._box_branch(feats[:4], self._rois5(proposals))
