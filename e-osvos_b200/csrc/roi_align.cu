@@ -90,6 +90,10 @@ roi_align_kernel(const RoiLevels lv, const float* __restrict__ rois, act_t* __re
   const int r = (int)(t / P);
   const float* roi = rois + (size_t)r * 5;
   const int b = (int)roi[0];
+  if (b < 0) {   // padding row of a fixed-size RoI list (CUDA-graphed mask branch): zeros forward, nothing backward
+    if (!BWD) *reinterpret_cast<uint4*>(out + (size_t)idx * 8) = make_uint4(0, 0, 0, 0);
+    return;
+  }
   const float bx1 = roi[1], by1 = roi[2], bx2 = roi[3], by2 = roi[4];
   const int l = roi_level(bx1, by1, bx2, by2);
   const int H = lv.H[l], W = lv.W[l];
@@ -161,6 +165,10 @@ mask_target_kernel(const uint8_t* __restrict__ masks, const float* __restrict__ 
   const int ph = (int)((idx / M) % M);
   const int r = (int)(idx / ((long long)M * M));
   const float* roi = rois + (size_t)r * 5;
+  if (roi[0] < 0.f) {   // padding row
+    out[idx] = 0.f;
+    return;
+  }
   const uint8_t* m = masks + (size_t)((int)roi[0]) * H * W;
   const float x1 = roi[1], y1 = roi[2], x2 = roi[3], y2 = roi[4];
   const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);

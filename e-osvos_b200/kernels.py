@@ -340,6 +340,21 @@ def mask_targets(masks_u8, rois, M):
 
 
 # ------------------------------------------------------------------------------------------- K7
+def mask_loss_per_roi(logits, labels, targets):
+    """Lovasz hinge per RoI: -> (loss_per_roi [R], dlogits [R,Cc,M,M] = d loss_r / d logits, unscaled)."""
+    _chk(logits, torch.float32, "logits")
+    _chk(labels, torch.int64, "labels")
+    _chk(targets, torch.float32, "targets")
+    R, Cc = logits.shape[0], logits.shape[1]
+    P = logits.shape[2] * logits.shape[3]
+    loss = torch.zeros((), device=logits.device, dtype=torch.float32)
+    per = torch.empty((R,), device=logits.device, dtype=torch.float32)
+    dlogits = torch.empty_like(logits)
+    call("eosvos_mask_loss_lovasz", _ptr(logits), _ptr(labels), _ptr(targets), _ptr(loss), _ptr(per), _ptr(dlogits), R,
+         Cc, P, _stream())
+    return per, dlogits.mul_(float(R))       # the kernel folds the 1/R of the mean into the gradient
+
+
 def mask_loss(logits, labels, targets, kind="LOVASZ"):
     """logits [R,Cc,M,M] fp32, labels [R] int64, targets [R,M,M] fp32 -> (loss scalar, dlogits)."""
     _chk(logits, torch.float32, "logits")

@@ -117,6 +117,7 @@ class MaskRCNN(_MaskRCNN):
         self._theta_home = None
         self._active_plan = None
         self._box_slots = None
+        self._mask_slots = None
 
     # ---- reference API (mask_rcnn.py:523-570) ------------------------------------------------
     def replace_batch_with_group_norms(self):
@@ -440,7 +441,7 @@ class MaskRCNN(_MaskRCNN):
             # never continue in a zero block it touched
             K.zero_pool.reset()
             ent = (graphed, per_call, plan, vals)
-            if len(self._graphs) >= 8:          # bounded: graphs pin their activation pools
+            if len(self._graphs) >= 12:         # bounded: graphs pin their activation pools
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = ent
         from .. import _lib
@@ -720,8 +721,12 @@ class MaskRCNN(_MaskRCNN):
 
     def _mask_branch(self, feats, mask_proposals):
         rh = self.roi_heads
+        return self._mask_branch_rois(feats, self._rois5(mask_proposals))
+
+    def _mask_branch_rois(self, feats, rois5):
+        rh = self.roi_heads
         P = self._roi_sizes['mask']
-        x = ops.roi_align(feats[:4], self._SCALES, self._rois5(mask_proposals), P)
+        x = ops.roi_align(feats[:4], self._SCALES, rois5, P)
         for blk in rh.mask_head:
             conv = blk[0] if isinstance(blk, nn.Sequential) else blk
             x = ops.conv2d(x, conv.weight, conv.bias, pad=1, relu=True)
@@ -806,6 +811,74 @@ class MaskRCNN(_MaskRCNN):
             for (m, n), t in zip(slots, saved):
                 m._parameters[n] = t
 
+    _MASK_BUCKETS = (8, 32, 128)
+
+    def _mask_train_functional(self, f0, f1, f2, f3, rois5, labels, gt_masks, tgt_rois, weights, *theta):
+        """Mask branch + Lovasz loss on a padded, fixed-size list of positive RoIs (rows with weight 0 are padding)
+        as a pure function with static shapes -- the third CUDA graph pair of a training iteration."""
+        slots = self._mask_slots
+        saved = [m._parameters[n] for m, n in slots]
+        for (m, n), t in zip(slots, theta):
+            m._parameters[n] = t
+        if self._active_plan is not None:
+            self._active_plan.launch()
+            for k in [k for k in ops._scope if isinstance(k[1], tuple) and k[1][0] == "head"]:
+                del ops._scope[k]
+        try:
+            logits = self._mask_branch_rois([f0, f1, f2, f3], rois5)
+            tg = K.mask_targets(gt_masks, tgt_rois, logits.shape[-1])
+            return ops.mask_loss_weighted(logits, labels, tg, weights)
+        finally:
+            for (m, n), t in zip(slots, saved):
+                m._parameters[n] = t
+
+    def _mask_loss_graphed(self, feats, mask_proposals, pos_matched_idxs, targets):
+        """Pads the positive RoIs of the batch to the next bucket size and replays the mask graph; None when the
+        case is not covered (no positives, BCE, ragged ground truth)."""
+        rh = self.roi_heads
+        n = sum(p.shape[0] for p in mask_proposals)
+        cap = len(mask_proposals) * int(rh.fg_bg_sampler.batch_size_per_image * rh.fg_bg_sampler.positive_fraction)
+        sizes = [b for b in self._MASK_BUCKETS if b < cap] + [cap]
+        if n == 0 or n > cap or rh.maskrcnn_loss != 'LOVASZ':
+            return None
+        R = next(b for b in sizes if b >= n)
+        device = feats[0].device
+        gt_masks = torch.cat([t["masks"] for t in targets], 0).contiguous()
+        gt_labels = [t["labels"] for t in targets]
+        lab = torch.cat([l[i] for l, i in zip(gt_labels, pos_matched_idxs)], dim=0)
+        rois5 = self._rois5(mask_proposals)
+        offs, tro = 0, []
+        for t, p, i in zip(targets, mask_proposals, pos_matched_idxs):
+            tro.append(torch.cat([(i + offs).to(p)[:, None], p], dim=1))
+            offs += t["masks"].shape[0]
+        tro = torch.cat(tro, 0).to(torch.float32)
+        pad = R - n
+        w = torch.full((R,), 1.0 / n, device=device, dtype=torch.float32)
+        if pad:
+            w[n:] = 0.0
+            fill = rois5.new_zeros((pad, 5))
+            fill[:, 0] = -1.0                       # negative image index = padding row (skipped by the kernels)
+            rois5 = torch.cat([rois5, fill], 0)
+            tro = torch.cat([tro, fill], 0)
+            lab = torch.cat([lab, lab.new_ones(pad)], 0)
+        if self._mask_slots is None:
+            mods = (rh.mask_head, rh.mask_predictor)
+            self._mask_slots = [(m, n_) for mod in mods for _, m in mod.named_modules()
+                                for n_, p in m._parameters.items() if p is not None and p.requires_grad]
+
+        def kinds(m, n_, t):
+            if n_ != "weight":
+                return ()
+            if isinstance(m, nn.ConvTranspose2d):
+                return ("dc",)
+            if isinstance(m, nn.Conv2d) and t.shape[0] >= 64:
+                return ("f", "t")
+            return ()
+        key = ("mask", R, tuple(gt_masks.shape), tuple(tuple(f.shape) for f in feats[:4]), device.index)
+        return self._graphed_call(key, self._mask_train_functional,
+                                  list(feats[:4]) + [rois5.contiguous(), lab.contiguous(), gt_masks, tro.contiguous(), w],
+                                  self._mask_slots, kinds, True, alias_inputs=4)
+
     def _roi_heads(self, feats, proposals, image_sizes, targets):
         rh = self.roi_heads
         if self.training:
@@ -867,7 +940,16 @@ class MaskRCNN(_MaskRCNN):
             mask_proposals = [p["boxes"] for p in result]
 
         n_mask = sum(p.shape[0] for p in mask_proposals)
-        if n_mask > 0:
+        loss_mask_graphed = None
+        if (graphed_box and os.environ.get("EOSVOS_GRAPH_MASK", "0") == "1"
+                and all(t["masks"].shape[0] == targets[0]["masks"].shape[0] for t in targets)):
+            # opt-in: the mask branch, its targets and the Lovasz loss on the positives padded to a bucket size as a
+            # third graph pair.  Measured neutral on B200 (47 vs 47-49 iter/s): with the trunk and the box branch
+            # graphed the iteration is GPU-bound, and the padded rows cost what the saved launches gain.
+            loss_mask_graphed = self._mask_loss_graphed(feats, mask_proposals, pos_matched_idxs, targets)
+        if loss_mask_graphed is not None:
+            mask_logits = None
+        elif n_mask > 0:
             mask_logits = self._mask_branch(feats, mask_proposals)
             if self.capture is not None:
                 self.capture.update(mask_logits=mask_logits.detach())
@@ -881,7 +963,9 @@ class MaskRCNN(_MaskRCNN):
             kind = rh.maskrcnn_loss
             if kind not in ('BCE', 'LOVASZ'):
                 raise NotImplementedError
-            if n_mask == 0:
+            if loss_mask_graphed is not None:
+                loss_mask = loss_mask_graphed
+            elif n_mask == 0:
                 loss_mask = torch.zeros((), device=feats[0].device)
             else:
                 gt_masks = [t["masks"] for t in targets]

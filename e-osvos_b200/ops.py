@@ -622,3 +622,25 @@ class MaskLossFn(torch.autograd.Function):
 
 def mask_loss(logits, labels, targets, kind):
     return MaskLossFn.apply(logits, labels, targets, kind)
+
+
+class MaskLossWeightedFn(torch.autograd.Function):
+    """sum_r weights[r] * lovasz_hinge(logits[r], targets[r]): the reference's mean over the positive RoIs
+    (loss_lovasz.py:232-250 via mask_rcnn.py:56-92) when weights = valid / n_valid over a PADDED, fixed-size RoI list
+    (what lets the mask branch run as a CUDA graph)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, targets, weights):
+        per, dlogits = K.mask_loss_per_roi(logits.contiguous(), labels, targets)
+        ctx.save_for_backward(dlogits.mul_(weights.view(-1, 1, 1, 1)))
+        return (per * weights).sum()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None, None, None
+
+
+def mask_loss_weighted(logits, labels, targets, weights):
+    return MaskLossWeightedFn.apply(logits, labels, targets, weights)

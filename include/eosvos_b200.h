@@ -79,7 +79,9 @@ int eosvos_gn_backward(const void* x, const float* sums, const float* gamma, con
                        const void* yout, float* part, void* dx, void* dres, float* dgamma, float* dbeta, int N, int HW,
                        int C, float eps, int mask_mode, float alpha, eosvos_stream_t stream);
 
-/* ---- K4: multi-scale RoIAlign (reference: mask_rcnn.py:113,147 -> torchvision::roi_align) */
+/* ---- K4: multi-scale RoIAlign (reference: mask_rcnn.py:113,147 -> torchvision::roi_align).  rois [R][5] =
+ *      (image index, x1, y1, x2, y2); a NEGATIVE image index marks a padding row of a fixed-size list: zeros forward,
+ *      no contribution backward (same convention in eosvos_mask_targets) */
 int eosvos_roi_align_fwd(const void* const* feats, const int* Hs, const int* Ws, const float* scales, const float* rois,
                          void* out, int R, int P, int C, int sampling, eosvos_stream_t stream);
 int eosvos_roi_align_bwd(float* const* dfeats, const int* Hs, const int* Ws, const float* scales, const float* rois,
