@@ -249,14 +249,25 @@ gn_bwd_reduce_kernel(const act_t* __restrict__ x, const float* __restrict__ sums
     if (MODE == 2) yv = ldg16(yout + o);
     one(xv, dv, yv);
   }
+  // narrow layers (C/8 < 32): several lanes of a warp own the same channels -- combine them with shuffles first, so
+  // the shared-memory atomics below see 8-way instead of 32-way same-address conflicts (C = 64: 30 -> 15 us)
+  for (int off = cv; off < 32; off <<= 1) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = my_cv * 8 + k;
-    const int g = c / cpg;
-    const float mean = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
-    const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean * mean, 0.f);
-    atomicAdd(&smp[c * 2], s1[k]);
-    atomicAdd(&smp[c * 2 + 1], (s2[k] - mean * s1[k]) * rsqrtf(var + eps));
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
+    }
+  }
+  if (cv >= 32 || (threadIdx.x & 31) < cv) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = my_cv * 8 + k;
+      const int g = c / cpg;
+      const float mean = sums[((size_t)n * GN_GROUPS + g) * 2] * inv_m;
+      const float var = fmaxf(sums[((size_t)n * GN_GROUPS + g) * 2 + 1] * inv_m - mean * mean, 0.f);
+      atomicAdd(&smp[c * 2], s1[k]);
+      atomicAdd(&smp[c * 2 + 1], (s2[k] - mean * s1[k]) * rsqrtf(var + eps));
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * 2; i += GN_THREADS) {
