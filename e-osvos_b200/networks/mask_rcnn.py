@@ -785,6 +785,16 @@ class MaskRCNN(_MaskRCNN):
         bp = rh.box_predictor
         return ops.fused_heads(h, [bp.cls_score.weight, bp.bbox_pred.weight], [bp.cls_score.bias, bp.bbox_pred.bias])
 
+    @staticmethod
+    def _fastrcnn_loss_static(class_logits, box_regression, labels, reg_targets):
+        """tv roi_heads.py:12-53 (fastrcnn_loss) on concatenated labels / targets, with the positive rows selected by
+        a mask instead of `torch.where` (static shapes, no host sync): same terms, same 1/N normalisation."""
+        loss_cls = F.cross_entropy(class_logits, labels)
+        N, nc = class_logits.shape
+        sel = box_regression.reshape(N, nc, 4).gather(1, labels.clamp(min=0)[:, None, None].expand(N, 1, 4))
+        per = F.smooth_l1_loss(sel.squeeze(1), reg_targets, beta=1 / 9, reduction="none").sum(dim=1)
+        return loss_cls, (per * (labels > 0).to(per.dtype)).sum() / N
+
     def _box_train_functional(self, f0, f1, f2, f3, rois5, labels, reg_targets, *theta):
         """Box branch + tv fastrcnn_loss (roi_heads.py:12-53) as a pure function with static shapes (R = 512 per
         image), what the second CUDA graph of a training iteration captures.  The loss is the reference's, with the
@@ -801,12 +811,7 @@ class MaskRCNN(_MaskRCNN):
             o = self._box_branch([f0, f1, f2, f3], rois5)
             nc = self.roi_heads.box_predictor.cls_score.weight.shape[0]
             class_logits, box_regression = o[:, :nc], o[:, nc:nc + 4 * nc]
-            loss_cls = F.cross_entropy(class_logits, labels)
-            N = labels.numel()
-            sel = box_regression.reshape(N, nc, 4).gather(1, labels.clamp(min=0)[:, None, None].expand(N, 1, 4))
-            per = F.smooth_l1_loss(sel.squeeze(1), reg_targets, beta=1 / 9, reduction="none").sum(dim=1)
-            loss_box = (per * (labels > 0).to(per.dtype)).sum() / N
-            return loss_cls, loss_box
+            return self._fastrcnn_loss_static(class_logits, box_regression, labels, reg_targets)
         finally:
             for (m, n), t in zip(slots, saved):
                 m._parameters[n] = t

@@ -86,6 +86,49 @@ def test_no_cpu_fallback():
         opt.step(loss)                      # the fused update is a CUDA kernel; on CPU it must raise, not fall back
 
 
+def test_single_sync_roi_sampling_equals_torchvision():
+    """MaskRCNN._select_training_samples (one host sync, nonzero_static) must return exactly what torchvision's
+    select_training_samples (the reference's call, mask_rcnn.py:113) returns from the same RNG state -- it is pure
+    torch, so the equality is checked on the CPU."""
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200.networks.mask_rcnn import MaskRCNN
+    torch.manual_seed(0)
+    model = MaskRCNN('resnet50', num_classes=2,
+                     batch_norm={'accum_stats': False, 'learn_weight': False, 'learn_bias': False}, train_encoder=True,
+                     roi_pool_output_sizes={'box': 7, 'mask': 28}, eval_augment_rpn_proposals_mode='EXTEND',
+                     replace_batch_with_group_norms=True, box_nms_thresh=0.5, maskrcnn_loss='LOVASZ')
+    g = torch.Generator().manual_seed(5)
+    gts = [torch.tensor([[100.0, 80.0, 300.0, 260.0]]), torch.tensor([[400.0, 120.0, 640.0, 300.0]])]
+    proposals, targets = [], []
+    for gt in gts:
+        ctr = torch.rand(900, 2, generator=g) * torch.tensor([1300.0, 740.0])
+        wh = torch.rand(900, 2, generator=g) * 300 + 8
+        far = torch.cat([ctr - wh / 2, ctr + wh / 2], 1).clamp(min=0)
+        near = gt + (torch.rand(40, 4, generator=g) - 0.5) * 60          # enough IoU >= 0.5 candidates: 25 % cap applies
+        proposals.append(torch.cat([far, near.clamp(min=0)], 0))
+        targets.append({"boxes": gt, "labels": torch.ones(1, dtype=torch.int64),
+                        "masks": torch.zeros(1, 8, 8, dtype=torch.uint8)})
+    torch.manual_seed(11)
+    ref_p, ref_m, ref_l, ref_r = model.roi_heads.select_training_samples([p.clone() for p in proposals], targets)
+    torch.manual_seed(11)
+    got_p, got_m, got_l, got_r, pos_in = model._select_training_samples([p.clone() for p in proposals], targets)
+    for a, b in zip(ref_p + ref_m + ref_l + list(ref_r), got_p + got_m + got_l + list(got_r)):
+        assert torch.equal(a, b)
+    for l, p in zip(got_l, pos_in):
+        assert torch.equal(p, torch.nonzero(l > 0).squeeze(1)) and 0 < p.numel() <= 128
+        assert l.numel() == 512
+    # the static-shape restatement of fastrcnn_loss used inside the box-branch graph == torchvision's
+    from torchvision.models.detection.roi_heads import fastrcnn_loss
+    logits = torch.randn(1024, 2, generator=g, requires_grad=True)
+    boxreg = torch.randn(1024, 8, generator=g, requires_grad=True)
+    lc, lb = fastrcnn_loss(logits, boxreg, got_l, list(got_r))
+    sc, sb = MaskRCNN._fastrcnn_loss_static(logits, boxreg, torch.cat(got_l), torch.cat(list(got_r)))
+    assert torch.allclose(lc, sc, rtol=1e-6, atol=0) and torch.allclose(lb, sb, rtol=1e-5, atol=1e-8)
+    g1 = torch.autograd.grad(lc + lb, (logits, boxreg))
+    g2 = torch.autograd.grad(sc + sb, (logits, boxreg))
+    assert all(torch.allclose(a, b, rtol=1e-5, atol=1e-9) for a, b in zip(g1, g2))
+
+
 def test_meta_optimizer_mirrors_reference_api():
     import eosvos_b200  # noqa: F401
     from eosvos_b200.meta_optim.meta_optim import MetaOptimizer
