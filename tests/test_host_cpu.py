@@ -1,6 +1,7 @@
 """CPU-only tests: the C-ABI library loads and exports every symbol include/eosvos_b200.h declares, the host
 side mirrors the reference API, the product fails loudly without a GPU, sharding / schedule logic, and a
 world_size-2 gloo run of the multi-GPU plumbing (no compute calls: there is no GPU here)."""
+import math
 import os
 import re
 import subprocess
@@ -127,6 +128,48 @@ def test_single_sync_roi_sampling_equals_torchvision():
     g1 = torch.autograd.grad(lc + lb, (logits, boxreg))
     g2 = torch.autograd.grad(sc + sb, (logits, boxreg))
     assert all(torch.allclose(a, b, rtol=1e-5, atol=1e-9) for a, b in zip(g1, g2))
+
+
+def test_davis_metrics_and_png_writer(tmp_path):
+    """J / F restated from the published DAVIS-2017 definitions (the reference's `davis` package is not vendored):
+    analytic cases, per-sequence statistics, and the object-id PNG round trip."""
+    import cv2
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200.util import metrics as MT
+    H, W = 120, 160
+    a = np.zeros((H, W), bool)
+    a[30:90, 40:120] = True
+    assert MT.jaccard(a, a) == 1.0 and MT.f_measure(a, a) == 1.0
+    assert MT.jaccard(np.zeros_like(a), np.zeros_like(a)) == 1.0 and MT.f_measure(np.zeros_like(a), np.zeros_like(a)) == 1.0
+    b = np.zeros_like(a)
+    b[30:90, 80:160] = True                                  # shifted by half its width: IoU = 1/3
+    assert abs(MT.jaccard(a, b) - (60 * 40) / (60 * 120)) < 1e-12
+    assert MT.f_measure(a, np.zeros_like(a)) == 0.0          # precision 0 (n_gt == 0) -> F = 0
+    far = np.zeros_like(a)
+    far[100:110, 5:15] = True
+    assert MT.f_measure(a, far) == 0.0                       # no boundary pixel within the tolerance
+    one = np.roll(a, 1, axis=1)                              # one-pixel shift: inside the 2-pixel tolerance band
+    assert math.ceil(0.008 * np.linalg.norm((H, W))) == 2 and MT.f_measure(a, one) == 1.0
+    three = np.roll(a, 6, axis=1)                            # 6-pixel shift: only the horizontal edges still match
+    f3 = MT.f_measure(a, three)
+    assert 0.3 < f3 < 0.8
+    bm = MT.seg2bmap(a)
+    assert bm.sum() == 2 * (60 + 80) and bm[29, 39] and not bm[60, 80]      # one-pixel-wide closed contour
+    # statistics: mean / recall(>0.5) / decay(first quarter - last quarter)
+    m, r, d = MT.sequence_statistics([1.0, 0.9, 0.8, 0.7, 0.4, 0.3, 0.2, 0.1])
+    assert abs(m - 0.55) < 1e-12 and abs(r - 0.5) < 1e-12 and d > 0.5
+    # sequence driver drops the first and the last frame
+    lab = np.zeros((5, H, W), np.uint8)
+    lab[:, 30:90, 40:120] = 1
+    pred = lab.copy()
+    pred[0] = 0
+    pred[4] = 0
+    res = MT.evaluate_sequence_jf(pred, lab, 1)
+    assert res["J"][0][0] == 1.0 and res["F"][0][0] == 1.0
+    paths = MT.save_predictions(pred, str(tmp_path), "seq")
+    assert len(paths) == 5 and os.path.basename(paths[3]) == "00003.png"
+    back = cv2.imread(paths[2], cv2.IMREAD_UNCHANGED)
+    assert back.dtype == np.uint8 and back.shape == (H, W) and np.array_equal(back, pred[2])
 
 
 def test_meta_optimizer_mirrors_reference_api():
