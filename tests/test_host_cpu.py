@@ -172,6 +172,28 @@ def test_davis_metrics_and_png_writer(tmp_path):
     assert back.dtype == np.uint8 and back.shape == (H, W) and np.array_equal(back, pred[2])
 
 
+def test_helper_func_mirrors_reference(tmp_path):
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200.util import helper_func as HF
+    from eosvos_b200.networks.mask_rcnn import MaskRCNN
+    split = tmp_path / "val.txt"
+    split.write_text("bear\ncamel\n")
+    ckpt = tmp_path / "parent.pth"
+    torch.save({"w": torch.ones(2)}, str(ckpt))
+    model, states = HF.init_parent_model(
+        'MaskRCNN', 'resnet50', True, None, True, {'accum_stats': False, 'learn_weight': False, 'learn_bias': False},
+        {'box': 7, 'mask': 28}, 'EXTEND', 0.5, 'LOVASZ', train={'paths': [str(ckpt)], 'val_split_files': [str(split)]})
+    assert isinstance(model, MaskRCNN) and states['train']['splits'] == [['bear', 'camel']]
+    assert torch.equal(states['train']['states'][0]['w'], torch.ones(2))
+    with pytest.raises(NotImplementedError):
+        HF.init_parent_model('DeepLabV3', 'resnet50', True, None, True, {}, {}, None, 0.5, 'LOVASZ')
+    # early_stopping (helper_func.py:388-398)
+    assert HF.early_stopping([1.0, 0.9], None, 0.0) is False
+    assert HF.early_stopping([1.0, 0.9, 0.8], 3, 0.0) is False                 # not more than `patience` entries yet
+    assert HF.early_stopping([1.0, 0.5, 0.5, 0.5, 0.5], 3, 0.01) is True       # no improvement over the last 3
+    assert HF.early_stopping([1.0, 0.9, 0.8, 0.7, 0.2], 3, 0.01) is False
+
+
 def test_meta_optimizer_mirrors_reference_api():
     import eosvos_b200  # noqa: F401
     from eosvos_b200.meta_optim.meta_optim import MetaOptimizer
