@@ -159,17 +159,24 @@ __device__ __forceinline__ void fprop_epilogue_tile(const FpropParams& p, const 
     if (valid) {
       if (p.res) {
         const act_t* rp = p.res + roff + col0;
+        uint4 rv[4];
+        if ((reinterpret_cast<uintptr_t>(rp) & 31) == 0 && col0 + 32 <= p.n_valid) {
+          ld_global_nc_256(rp, rv[0], rv[1]);
+          ld_global_nc_256(rp + 16, rv[2], rv[3]);
+        } else {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8)
+            rv[j8] = (col0 + j8 * 8 < p.n_valid) ? __ldg(reinterpret_cast<const uint4*>(rp + j8 * 8))
+                                                 : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
-          if (col0 + j8 * 8 < p.n_valid) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j8 * 8));
-            const act2_t* rh = reinterpret_cast<const act2_t*>(&rv);
+          const act2_t* rh = reinterpret_cast<const act2_t*>(&rv[j8]);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 rf = act22float2(rh[k]);
-              f[j8 * 8 + 2 * k] += rf.x;
-              f[j8 * 8 + 2 * k + 1] += rf.y;
-            }
+          for (int k = 0; k < 4; ++k) {
+            const float2 rf = act22float2(rh[k]);
+            f[j8 * 8 + 2 * k] += rf.x;
+            f[j8 * 8 + 2 * k + 1] += rf.y;
           }
         }
       }
@@ -187,16 +194,23 @@ __device__ __forceinline__ void fprop_epilogue_tile(const FpropParams& p, const 
         }
       } else {
         act_t* op = reinterpret_cast<act_t*>(p.out) + o;
+        uint4 w[4];
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
-          if (col0 + j8 * 8 < p.n_valid) {
-            uint4 w;
-            w.x = pack_act2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-            w.y = pack_act2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-            w.z = pack_act2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-            w.w = pack_act2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-            *reinterpret_cast<uint4*>(op + j8 * 8) = w;
-          }
+          w[j8].x = pack_act2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+          w[j8].y = pack_act2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+          w[j8].z = pack_act2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+          w[j8].w = pack_act2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+        }
+        // each lane owns 64 contiguous bytes of its output row: two 256-bit stores (whole 32-byte sectors) when the
+        // row is 32-byte aligned, else four 128-bit ones
+        if ((reinterpret_cast<uintptr_t>(op) & 31) == 0 && col0 + 32 <= p.n_valid) {
+          st_global_256(op, w[0], w[1]);
+          st_global_256(op + 16, w[2], w[3]);
+        } else {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8)
+            if (col0 + j8 * 8 < p.n_valid) *reinterpret_cast<uint4*>(op + j8 * 8) = w[j8];
         }
       }
     }
