@@ -51,7 +51,7 @@ def load_peaks():
 
 class ClockSampler:
     """SM clock + throttle reasons during the timed region (B200_PROFILING.md recipe), read through NVML inside this
-    process every 100 ms (a light query; an `nvidia-smi -lms` child was measured to perturb the timed region by up to
+    process every 250 ms (a light query; an `nvidia-smi -lms` child was measured to perturb the timed region by up to
     12 %).  Falls back to one nvidia-smi query per second when NVML is unavailable."""
     REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
                ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
@@ -98,7 +98,7 @@ class ClockSampler:
                                      int(n.nvmlDeviceGetCurrentClocksEventReasons(h))))
             except Exception:
                 pass
-            self.stop_flag.wait(float(os.environ.get("EOSVOS_CLOCK_POLL_S", "0.1")))
+            self.stop_flag.wait(float(os.environ.get("EOSVOS_CLOCK_POLL_S", "0.25")))
 
     def _poll_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
