@@ -362,7 +362,6 @@ class MaskRCNN(_MaskRCNN):
         through the host-side section.  Two alternating graph instances keep frame f's features intact."""
         if self.training or not self.use_cuda_graphs or self.capture is not None:
             return
-        B, _, h, w = inputs.shape
         x8, _, sizes, padded = self._transform(inputs, None)
         slot = self._pf_slot
         self._pf_slot ^= 1
@@ -750,7 +749,6 @@ class MaskRCNN(_MaskRCNN):
         return all_boxes, all_scores, all_labels
 
     def _mask_branch(self, feats, mask_proposals):
-        rh = self.roi_heads
         return self._mask_branch_rois(feats, self._rois5(mask_proposals))
 
     def _mask_branch_rois(self, feats, rois5):
