@@ -1,0 +1,119 @@
+"""DAVIS-layout sequence I/O and a per-dataset evaluation driver around `evaluate_sequence` -- the data format on
+the input side of the hot path and the host loop of reference src/util/evaluate.py:20-439.
+
+Layout (reference src/data/davis.py:50-58, src/util/helper_func.py:265-273):
+    {root}/JPEGImages/480p/<seq>/<frame>.jpg     RGB frames
+    {root}/Annotations/480p/<seq>/<frame>.png    object-id label maps (palette PNG; ids 0..K)
+    {root}/<split>_seqs.txt                      one sequence name per line
+Pixels reach the model exactly as in src/data/vos_dataset.py:233,276-279 with `normalize: False`
+(cfgs/meta.yaml:114): cv2 BGR -> RGB, float32 / 255; labels as float ids via PIL (`np.atleast_3d(label)[..., 0]`).
+"""
+import os
+
+import numpy as np
+import torch
+
+
+def list_sequences(root, split):
+    with open(os.path.join(root, f"{split}_seqs.txt")) as f:
+        return [ln.strip() for ln in f if ln.strip()]
+
+
+def load_sequence(root, seq, resolution="480p", pin=False):
+    """-> (frames float32 [T,3,H,W] RGB in [0,1], labels uint8 [T,H,W] (zeros where a frame has no annotation),
+    frame names, has_label [T] bool)."""
+    import cv2
+    from PIL import Image
+    img_dir = os.path.join(root, "JPEGImages", resolution, seq)
+    lab_dir = os.path.join(root, "Annotations", resolution, seq)
+    names = sorted(os.path.splitext(f)[0] for f in os.listdir(img_dir) if f.lower().endswith((".jpg", ".jpeg", ".png")))
+    if not names:
+        raise FileNotFoundError(f"no frames under {img_dir}")
+    frames, labels, has = [], [], []
+    for n in names:
+        path = next(os.path.join(img_dir, n + e) for e in (".jpg", ".jpeg", ".png") if os.path.exists(os.path.join(img_dir, n + e)))
+        bgr = cv2.imread(path, cv2.IMREAD_COLOR)
+        if bgr is None:
+            raise IOError(f"could not read {path}")
+        frames.append(np.ascontiguousarray(bgr[..., ::-1]))
+        lp = os.path.join(lab_dir, n + ".png")
+        if os.path.exists(lp):
+            labels.append(np.atleast_3d(np.array(Image.open(lp)))[..., 0].astype(np.uint8))
+            has.append(True)
+        else:
+            labels.append(None)
+            has.append(False)
+    H, W = frames[0].shape[:2]
+    lab = np.zeros((len(names), H, W), np.uint8)
+    for i, l in enumerate(labels):
+        if l is not None:
+            lab[i] = l
+    fr = torch.from_numpy(np.stack(frames)).permute(0, 3, 1, 2).float().div_(255.0).contiguous()
+    if pin and torch.cuda.is_available():
+        fr = fr.pin_memory()
+    return fr, torch.from_numpy(lab), names, np.array(has, dtype=bool)
+
+
+def write_sequence(root, seq, frames_u8, labels_u8, resolution="480p", names=None, jpeg_quality=95):
+    """frames_u8 [T,H,W,3] RGB uint8, labels_u8 [T,H,W] ids -> DAVIS layout on disk (labels as palette PNGs)."""
+    import cv2
+    from PIL import Image
+    img_dir = os.path.join(root, "JPEGImages", resolution, seq)
+    lab_dir = os.path.join(root, "Annotations", resolution, seq)
+    os.makedirs(img_dir, exist_ok=True)
+    os.makedirs(lab_dir, exist_ok=True)
+    palette = [0, 0, 0, 128, 0, 0, 0, 128, 0, 128, 128, 0, 0, 0, 128, 128, 0, 128, 0, 128, 128, 128, 128, 128]
+    palette += [0] * (768 - len(palette))
+    for i in range(frames_u8.shape[0]):
+        n = names[i] if names is not None else f"{i:05d}"
+        cv2.imwrite(os.path.join(img_dir, n + ".jpg"), np.ascontiguousarray(frames_u8[i][..., ::-1]),
+                    [cv2.IMWRITE_JPEG_QUALITY, jpeg_quality])
+        im = Image.fromarray(np.asarray(labels_u8[i], dtype=np.uint8), mode="P")
+        im.putpalette(palette)
+        im.save(os.path.join(lab_dir, n + ".png"))
+
+
+def write_split(root, split, seqs):
+    os.makedirs(root, exist_ok=True)
+    with open(os.path.join(root, f"{split}_seqs.txt"), "w") as f:
+        f.write("\n".join(seqs) + "\n")
+
+
+def evaluate_dataset(model, meta_optim, meta_optim_state_dict, root, split, save_dir=None, rank=0, world_size=1,
+                     evaluate_fn=None, **cfg):
+    """Per-dataset loop of reference evaluate.py:95-439 on this rank's share of the sequences (whole videos are
+    sharded longest-first over ranks, no exchange): load -> evaluate_sequence (fine-tune + propagate, every object)
+    -> PNGs -> J / F.  Returns {seq: {"J": [...], "F": [...], "time_per_frame": s, "num_objects": K}}.
+    `cfg` is passed to evaluate_sequence (num_epochs_eval, online_adapt_step, ...)."""
+    from . import metrics
+    from .shard import unit_cost
+    if evaluate_fn is None:
+        from .evaluate import evaluate_sequence as evaluate_fn
+    seqs = list_sequences(root, split)
+    sched_cfg = {k: cfg[k] for k in ("num_epochs_eval", "online_adapt_step", "online_adapt_epochs") if k in cfg}
+    loaded = {}
+    costs = []
+    for s in seqs:
+        fr, lab, names, has = load_sequence(root, s)
+        K = int(lab[0].max())
+        loaded[s] = (fr, lab, names, has)
+        costs.append((K * unit_cost(fr.shape[0], batch=cfg.get("batch_size", 3), **sched_cfg) if sched_cfg else K * fr.shape[0], s))
+    loads = [0.0] * world_size
+    mine = []
+    for c, s in sorted(costs, reverse=True):
+        r = min(range(world_size), key=lambda j: (loads[j], j))
+        loads[r] += c
+        if r == rank:
+            mine.append(s)
+    results = {}
+    for s in mine:
+        fr, lab, names, has = loaded[s]
+        pred, stats = evaluate_fn(model, meta_optim, meta_optim_state_dict, fr, lab[0], **cfg)
+        pred_np = pred.cpu().numpy() if isinstance(pred, torch.Tensor) else np.asarray(pred)
+        if save_dir is not None:
+            metrics.save_predictions(pred_np, save_dir, s, names)
+        K = int(lab[0].max())
+        ann = np.where(has)[0]
+        jf = metrics.evaluate_sequence_jf(pred_np[ann], lab.numpy()[ann], K) if ann.size >= 3 else {"J": [], "F": []}
+        results[s] = {"J": jf["J"], "F": jf["F"], "time_per_frame": stats.get("time_per_frame"), "num_objects": K}
+    return results

@@ -194,6 +194,48 @@ def test_helper_func_mirrors_reference(tmp_path):
     assert HF.early_stopping([1.0, 0.9, 0.8, 0.7, 0.2], 3, 0.01) is False
 
 
+def test_davis_io_and_dataset_driver(tmp_path):
+    """DAVIS-layout round trip (JPEG frames, palette-PNG labels, split file) and the per-dataset driver: sharding by
+    whole sequences over ranks, PNG output, J/F -- with the CUDA fine-tune/propagate step replaced by a stub that
+    returns the ground truth (the real one needs the GPU; it is covered by tests/test_model_gpu.py)."""
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200.util import davis_io as IO
+    from eosvos_b200.util import synthetic
+    root = str(tmp_path / "DAVIS-2017")
+    seqs = {"alpha": (5, 1), "beta": (8, 2), "gamma": (4, 1)}
+    truth = {}
+    for i, (name, (T, K)) in enumerate(seqs.items()):
+        fr, lab = synthetic.make_video(3 + i, T, 96, 128, K)
+        IO.write_sequence(root, name, fr, lab)
+        truth[name] = (fr, lab)
+    IO.write_split(root, "val", list(seqs))
+    assert IO.list_sequences(root, "val") == list(seqs)
+    fr, lab, names, has = IO.load_sequence(root, "beta")
+    assert fr.shape == (8, 3, 96, 128) and fr.dtype == torch.float32 and 0.0 <= float(fr.min()) and float(fr.max()) <= 1.0
+    assert names[0] == "00000" and has.all() and torch.equal(lab, torch.from_numpy(truth["beta"][1]))     # labels lossless
+    ref = torch.from_numpy(truth["beta"][0]).permute(0, 3, 1, 2).float() / 255.0
+    assert float((fr - ref).abs().mean()) < 0.02                                                        # JPEG is lossy
+
+    calls = []
+
+    def stub(model, meta_optim, state, frames, first_label, **cfg):
+        name = next(n for n, (f, l) in truth.items() if f.shape[0] == frames.shape[0])
+        calls.append((name, cfg))
+        return torch.from_numpy(truth[name][1]), {"time_per_frame": 0.01}
+    out_dir = str(tmp_path / "preds")
+    res0 = IO.evaluate_dataset(None, None, None, root, "val", save_dir=out_dir, rank=0, world_size=2, evaluate_fn=stub,
+                               num_epochs_eval=10, online_adapt_step=5, online_adapt_epochs=4)
+    res1 = IO.evaluate_dataset(None, None, None, root, "val", save_dir=out_dir, rank=1, world_size=2, evaluate_fn=stub,
+                               num_epochs_eval=10, online_adapt_step=5, online_adapt_epochs=4)
+    assert set(res0) | set(res1) == set(seqs) and not (set(res0) & set(res1))
+    assert "beta" in res0                       # the costliest sequence (2 objects, 8 frames) goes to rank 0 first
+    for name, r in {**res0, **res1}.items():
+        assert r["num_objects"] == seqs[name][1] and len(r["J"]) == seqs[name][1]
+        assert all(j[0] == 1.0 for j in r["J"]) and all(f[0] == 1.0 for f in r["F"])
+        assert len(os.listdir(os.path.join(out_dir, name))) == seqs[name][0]
+    assert calls[0][1]["online_adapt_step"] == 5
+
+
 def test_meta_optimizer_mirrors_reference_api():
     import eosvos_b200  # noqa: F401
     from eosvos_b200.meta_optim.meta_optim import MetaOptimizer
