@@ -80,6 +80,26 @@ class _FusedUpdateFn(torch.autograd.Function):
         return (None, None, None, None, *dps, *([None] * n), *dls)
 
 
+def remap_reference_checkpoint(state_dict):
+    """Renames the keys of a checkpoint written by the reference under torchvision 0.4 (README.md:23) to the module
+    names of the installed torchvision: `mask_head.mask_fcn{i}` -> `mask_head.{i-1}.0`,
+    `rpn.head.conv` -> `rpn.head.conv.0.0`, `fpn.inner_blocks.{i}` / `fpn.layer_blocks.{i}` -> `....{i}.0`.  Works on
+    model state dicts ('.'-separated) and on MetaOptimizer state dicts, whose keys embed the parameter name with
+    '-' separators (`model_init_<name>`, `log_init_lr_<name>`, meta_optim.py:65,78).  Keys already in the new naming
+    are left alone."""
+    import re
+    out = type(state_dict)()
+    for k, v in state_dict.items():
+        for sep in (".", "-"):
+            q = re.escape(sep)
+            k = re.sub(rf"mask_head{q}mask_fcn(\d+){q}", lambda m: f"mask_head{sep}{int(m.group(1)) - 1}{sep}0{sep}", k)
+            k = re.sub(rf"rpn{q}head{q}conv{q}(weight|bias)$", rf"rpn{sep}head{sep}conv{sep}0{sep}0{sep}\1", k)
+            k = re.sub(rf"fpn{q}(inner_blocks|layer_blocks){q}(\d+){q}(weight|bias)$",
+                       rf"fpn{sep}\1{sep}\2{sep}0{sep}\3", k)
+        out[k] = v
+    return out
+
+
 class MetaOptimizer(nn.Module):
 
     def __init__(self, model, init_lr, learn_model_init, second_order_gradients, lr_hierarchy_level,
@@ -133,6 +153,16 @@ class MetaOptimizer(nn.Module):
 
         self.state = {}
         self._init_state()
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """As nn.Module.load_state_dict; checkpoints written by the reference under torchvision 0.4 module names are
+        accepted (remap_reference_checkpoint)."""
+        own = set(super(MetaOptimizer, self).state_dict().keys())
+        if any(k not in own for k in state_dict):
+            remapped = remap_reference_checkpoint(state_dict)
+            if sum(k in own for k in remapped) > sum(k in own for k in state_dict):
+                state_dict = remapped
+        return super(MetaOptimizer, self).load_state_dict(state_dict, strict=strict, **kw)
 
     # ---- meta_optim.py:83-107
     def _lr_values(self, lrs):

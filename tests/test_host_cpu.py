@@ -236,6 +236,38 @@ def test_davis_io_and_dataset_driver(tmp_path):
     assert calls[0][1]["online_adapt_step"] == 5
 
 
+def test_reference_checkpoint_key_remap():
+    """A MetaOptimizer checkpoint written under torchvision 0.4 module names loads into the optimizer built on the
+    installed torchvision (and a model state dict maps onto the installed model's keys)."""
+    import re
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200.meta_optim.meta_optim import MetaOptimizer, remap_reference_checkpoint
+    from eosvos_b200.networks.mask_rcnn import MaskRCNN
+    torch.manual_seed(0)
+    model = MaskRCNN('resnet50', num_classes=2,
+                     batch_norm={'accum_stats': False, 'learn_weight': False, 'learn_bias': False}, train_encoder=True,
+                     roi_pool_output_sizes={'box': 7, 'mask': 28}, eval_augment_rpn_proposals_mode='EXTEND',
+                     replace_batch_with_group_norms=True, box_nms_thresh=0.5, maskrcnn_loss='LOVASZ')
+    opt = MetaOptimizer(model, 1e-3, True, False, 'NEURON', False, None)
+
+    def to_tv04(k, sep):
+        q = re.escape(sep)
+        k = re.sub(rf"mask_head{q}(\d+){q}0{q}", lambda m: f"mask_head{sep}mask_fcn{int(m.group(1)) + 1}{sep}", k)
+        k = re.sub(rf"rpn{q}head{q}conv{q}0{q}0{q}", f"rpn{sep}head{sep}conv{sep}", k)
+        return re.sub(rf"fpn{q}(inner_blocks|layer_blocks){q}(\d+){q}0{q}", rf"fpn{sep}\1{sep}\2{sep}", k)
+    new = opt.state_dict()
+    old = {to_tv04(k, "-"): v.clone() + 1.0 for k, v in new.items()}
+    assert set(old) != set(new) and "model_init_roi_heads-mask_head-mask_fcn1-weight" in old
+    assert "log_init_lr_rpn-head-conv-weight" in old and "model_init_backbone-fpn-inner_blocks-2-bias" in old
+    assert set(remap_reference_checkpoint(old)) == set(new)
+    assert set(remap_reference_checkpoint(dict(new))) == set(new)            # idempotent on current names
+    opt.load_state_dict(old)                                                 # strict: every key must land
+    for k, v in opt.state_dict().items():
+        assert torch.equal(v, old[to_tv04(k, "-")])
+    msd = model.state_dict()
+    assert set(remap_reference_checkpoint({to_tv04(k, "."): v for k, v in msd.items()})) == set(msd)
+
+
 def test_meta_optimizer_mirrors_reference_api():
     import eosvos_b200  # noqa: F401
     from eosvos_b200.meta_optim.meta_optim import MetaOptimizer
