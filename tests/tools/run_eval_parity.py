@@ -1,7 +1,7 @@
 """GPU diagnostic: fine-tune on the GPU for a few iterations, copy the weights into the CPU oracle, then compare
 the inference path (boxes, probability maps, thresholded masks) frame by frame from IDENTICAL state."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import bench
 from eosvos_b200.util import evaluate as E, synthetic

@@ -1,6 +1,6 @@
 """GPU diagnostic: product model (CUDA kernels) vs oracle model (CPU fp32) stage by stage."""
 import os, sys, time, contextlib
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from unittest import mock
 import eosvos_b200
