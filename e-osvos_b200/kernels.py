@@ -82,6 +82,41 @@ class PinnedStager:
 stager = PinnedStager()
 
 
+class TargetStatsCache:
+    """Host-side (xmin, ymin, xmax, ymax, count) per object id of a label tensor, remembered for the EXACT tensor
+    contents they were computed from: an entry is valid only while the same tensor object still has the same storage
+    address and autograd version counter (any in-place edit bumps `_version`).  Producers that already know the
+    boxes on the host (the augmentation thread, the fused inference tail) `put` them so MaskRCNN.forward skips its
+    mask->box kernel and the D2H read-back."""
+
+    def __init__(self, capacity=16):
+        self.capacity = capacity
+        self.entries = {}
+
+    def put(self, t, stats, ign):
+        import weakref
+        key = id(t)
+        if len(self.entries) >= self.capacity:
+            for k in [k for k, v in self.entries.items() if v[0]() is None]:
+                del self.entries[k]
+            while len(self.entries) >= self.capacity:
+                self.entries.pop(next(iter(self.entries)))
+        self.entries[key] = (weakref.ref(t), t.data_ptr(), t._version, tuple(t.shape), stats, ign)
+
+    def get(self, t):
+        hit = self.entries.get(id(t))
+        if hit is None:
+            return None
+        ref, ptr, version, shape, stats, ign = hit
+        if ref() is t and ptr == t.data_ptr() and version == t._version and shape == tuple(t.shape):
+            return stats, ign
+        del self.entries[id(t)]
+        return None
+
+
+target_stats = TargetStatsCache()
+
+
 class ZeroPool:
     """Hands out zero-initialised fp32 views carved from ONE zeroed block per iteration (instead of ~200
     torch.zeros calls): accumulate-into outputs (split-K weight gradients, GroupNorm statistics, RoIAlign-bwd

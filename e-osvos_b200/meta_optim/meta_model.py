@@ -81,14 +81,24 @@ class MetaModel:
             else:
                 module._parameters[n_p].data.copy_(flat.data)
             offset += n
+        self._invalidate_operand_cache()
+
+    @staticmethod
+    def _invalidate_operand_cache():
+        """`.data` writes do not bump autograd's version counter, which (with identity and address) validates the
+        cached 16-bit tensor-core operand layouts of a parameter (ops._prep_cache): drop them."""
+        from .. import ops
+        ops.clear_prep_cache()
 
     def copy_params_from(self, model: nn.Module):
         for dst, src in zip(self.model.parameters(), model.parameters()):
             dst.data.copy_(src.data)
+        self._invalidate_operand_cache()
 
     def copy_params_to(self, model: nn.Module):
         for src, dst in zip(self.model.parameters(), model.parameters()):
             dst.data.copy_(src.data)
+        self._invalidate_operand_cache()
 
     def copy_grads_from(self, model: nn.Module):
         for dst, src in zip(self.model.parameters(), model.parameters()):

@@ -250,7 +250,10 @@ class MetaOptimizer(nn.Module):
         n = len(params)
         home = None
         theta_home = getattr(self.meta_model.model, "theta_home", None)
-        if callable(theta_home):
+        # The stable arena is written IN PLACE (theta_{t+1} over theta_t).  That is only sound when no autograd graph
+        # still refers to theta_t: true at evaluation time (every step is followed by detach_param_groups), not in
+        # meta-training, where forward graphs may be kept across steps (multi_step_bptt_loss, meta_run.py:158-178).
+        if callable(theta_home) and not self.training:
             arena, offs, shapes, index = theta_home()
             idx = [index.get((id(module), n_p)) for _, module, n_p, _ in groups]
             if arena.device == dev and all(i is not None and shapes[i] == tuple(p.shape) for i, p in zip(idx, params)):

@@ -166,8 +166,8 @@ class MaskRCNN(_MaskRCNN):
         B = targets.shape[0]
         Kc = max(self.num_classes - 1, 1)
         t32 = targets.to(torch.float32).contiguous()
-        pre = getattr(targets, "_eosvos_target_stats", None)
-        if pre is not None and not flip_label and tuple(pre[0].shape) == (B, Kc, 5):
+        pre = K.target_stats.get(targets) if not flip_label else None
+        if pre is not None and tuple(pre[0].shape) == (B, Kc, 5):
             # fast path: the producer of `targets` already knows the per-id boxes / counts on the HOST (the
             # augmentation thread, or the previous frame's fused tail kernel via run_frames) -> no kernel, no sync
             stats, ign = pre
@@ -177,10 +177,8 @@ class MaskRCNN(_MaskRCNN):
             packed = torch.cat([stats_d.flatten(), ign_d]).cpu()   # ONE small D2H (the reference does several)
             stats = packed[:B * Kc * 5].view(B, Kc, 5)
             ign = packed[B * Kc * 5:]
-            try:        # static batches (OnA rounds re-use the same tensors every iteration) pay the sync once
-                targets._eosvos_target_stats = (stats, ign)
-            except Exception:
-                pass
+            if not flip_label:      # static batches (OnA rounds re-use the same tensors every iteration) pay the sync
+                K.target_stats.put(targets, stats, ign)     # once; keyed on (tensor, data_ptr, _version)
         out = []
         for b in range(B):
             mask = t32[b]                            # [1,H,W]
@@ -368,7 +366,7 @@ class MaskRCNN(_MaskRCNN):
         feats = self._backbone(x8, slot=slot)
         if len(self._prefetched) >= 2:
             self._prefetched.clear()
-        self._prefetched[id(inputs)] = (inputs, x8, sizes, padded, feats)
+        self._prefetched[id(inputs)] = (inputs, x8, sizes, padded, feats, inputs._version, inputs.data_ptr())
 
     def _backbone(self, x8, slot=0):
         if not self.use_cuda_graphs or self.capture is not None:
@@ -506,12 +504,20 @@ class MaskRCNN(_MaskRCNN):
 
     # ---- RPN (reference mask_rcnn.py:217-344) ---------------------------------------------------
     def _anchors(self, image_shape, image_sizes, feat_shapes, device):
+        """Anchors of one (batch, padded size, pyramid) signature, generated once and kept per signature (fine-tuning
+        at batch 3 and inference at batch 1 alternate).  Generation is synchronised before the entry is published, so
+        every stream (the RPN side stream in particular) may read them without further ordering."""
         key = (tuple(image_shape), tuple(image_sizes), tuple(feat_shapes), str(device))
-        if key not in self._anchor_cache:
+        hit = self._anchor_cache.get(key)
+        if hit is None:
             il = _ImageListLike(image_shape, list(image_sizes), device)
             fms = [torch.empty((image_shape[0], 1, h, w), device=device, dtype=torch.float32) for h, w in feat_shapes]
-            self._anchor_cache = {key: [a.detach() for a in self.rpn.anchor_generator(il, fms)]}
-        return self._anchor_cache[key]
+            hit = [a.detach() for a in self.rpn.anchor_generator(il, fms)]
+            torch.cuda.current_stream(device).synchronize()     # once per signature
+            if len(self._anchor_cache) >= 8:
+                self._anchor_cache.pop(next(iter(self._anchor_cache)))
+            self._anchor_cache[key] = hit
+        return hit
 
     def _rpn_head(self, feats, stage=0, alias=None):
         """tv RPNHead on every level: [pixels, 16] fp32 = (A objectness | 4A box deltas | padding) per level.
@@ -1033,7 +1039,8 @@ class MaskRCNN(_MaskRCNN):
         pre = None
         if self._prefetched:
             pf = self._prefetched.pop(id(inputs), None)
-            if pf is not None and pf[0] is inputs and not self.training:
+            if (pf is not None and pf[0] is inputs and pf[5] == inputs._version and pf[6] == inputs.data_ptr()
+                    and not self.training):
                 pre = (pf[1], pf[2], pf[3])
                 pre_feats = pf[4]
         x8, targets_t, (oh, ow), (Hp, Wp) = self._transform(inputs, targets, pre)

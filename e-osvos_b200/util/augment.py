@@ -103,7 +103,7 @@ class DeviceAugmenter:
         flip_d = as_t(flips).to(dev, non_blocking=True)
         gts_d = as_t(gts).to(dev, non_blocking=True)
         if stats is not None:
-            gts_d._eosvos_target_stats = stats       # host-side boxes/counts: lets forward() skip a stream sync
+            K.target_stats.put(gts_d, *stats)        # host-side boxes/counts: lets forward() skip a stream sync
         return K.affine_warp_cubic(self.src, minv_d, flip_d, minv_d.shape[0]), gts_d
 
     def batch(self, batch_size, rots=(-30, 30), scales=(.75, 1.25)):

@@ -54,6 +54,17 @@ def load_sequence(root, seq, resolution="480p", pin=False):
     return fr, torch.from_numpy(lab), names, np.array(has, dtype=bool)
 
 
+def sequence_meta(root, seq, resolution="480p"):
+    """(number of frames, number of objects in the first annotation) without decoding any frame."""
+    from PIL import Image
+    img_dir = os.path.join(root, "JPEGImages", resolution, seq)
+    lab_dir = os.path.join(root, "Annotations", resolution, seq)
+    T = sum(1 for f in os.listdir(img_dir) if f.lower().endswith((".jpg", ".jpeg", ".png")))
+    labs = sorted(f for f in os.listdir(lab_dir) if f.lower().endswith(".png"))
+    K = int(np.atleast_3d(np.array(Image.open(os.path.join(lab_dir, labs[0]))))[..., 0].max()) if labs else 0
+    return T, K
+
+
 def write_sequence(root, seq, frames_u8, labels_u8, resolution="480p", names=None, jpeg_quality=95):
     """frames_u8 [T,H,W,3] RGB uint8, labels_u8 [T,H,W] ids -> DAVIS layout on disk (labels as palette PNGs)."""
     import cv2
@@ -91,13 +102,12 @@ def evaluate_dataset(model, meta_optim, meta_optim_state_dict, root, split, save
         from .evaluate import evaluate_sequence as evaluate_fn
     seqs = list_sequences(root, split)
     sched_cfg = {k: cfg[k] for k in ("num_epochs_eval", "online_adapt_step", "online_adapt_epochs") if k in cfg}
-    loaded = {}
+    # the cost model needs only (frame count, object count): read them from the directory listing and the first
+    # annotation instead of decoding every sequence on every rank
     costs = []
     for s in seqs:
-        fr, lab, names, has = load_sequence(root, s)
-        K = int(lab[0].max())
-        loaded[s] = (fr, lab, names, has)
-        costs.append((K * unit_cost(fr.shape[0], batch=cfg.get("batch_size", 3), **sched_cfg) if sched_cfg else K * fr.shape[0], s))
+        T, K = sequence_meta(root, s)
+        costs.append((K * unit_cost(T, batch=cfg.get("batch_size", 3), **sched_cfg) if sched_cfg else K * T, s))
     loads = [0.0] * world_size
     mine = []
     for c, s in sorted(costs, reverse=True):
@@ -107,7 +117,7 @@ def evaluate_dataset(model, meta_optim, meta_optim_state_dict, root, split, save
             mine.append(s)
     results = {}
     for s in mine:
-        fr, lab, names, has = loaded[s]
+        fr, lab, names, has = load_sequence(root, s, pin=True)     # only this rank's share, one sequence at a time
         pred, stats = evaluate_fn(model, meta_optim, meta_optim_state_dict, fr, lab[0], **cfg)
         pred_np = pred.cpu().numpy() if isinstance(pred, torch.Tensor) else np.asarray(pred)
         if save_dir is not None:

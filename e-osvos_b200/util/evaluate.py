@@ -10,6 +10,7 @@ import time
 import numpy as np
 import torch
 
+from .. import kernels as K
 from . import augment
 from .shard import ona_schedule
 
@@ -63,7 +64,7 @@ def run_frames(model, frames_dev, start_target):
                     targets = nxt
                     # boxes / counts of the propagated target are already on the host: the next forward skips its
                     # own mask->box kernel and read-back
-                    targets._eosvos_target_stats = (stats_cpu, torch.zeros(stats_cpu.shape[0], dtype=torch.int32))
+                    K.target_stats.put(targets, stats_cpu, torch.zeros(stats_cpu.shape[0], dtype=torch.int32))
             probs_all.append(probs)
             boxes_all.append(boxes)
     return torch.cat(probs_all), torch.cat(boxes_all)

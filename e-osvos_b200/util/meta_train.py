@@ -61,6 +61,10 @@ class FusedRAdam:
             K.radam_step(p, flat_grad[off:off + n], g["m"], g["v"], gscale=gscale, clip=grad_clip,
                          beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, lr=g["lr"], wd=g["wd"],
                          step_size=step_size * g["lr"], rectified=rect, clamp=clamp)
+        # the kernel wrote through raw pointers: autograd's version counters did not move, so the 16-bit operand
+        # layouts cached per (tensor, version) for theta_0 are stale now
+        from .. import ops
+        ops.clear_prep_cache()
 
 
 def task_meta_gradients(model, meta_optim, train_batch, meta_batch, num_epochs=5, bptt_epochs=5, seed=1, rank=0,

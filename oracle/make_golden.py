@@ -23,8 +23,56 @@ def synthetic_frame(seed, h=96, w=170):
     return img, tgt
 
 
+EVAL_OVERRIDES = {"parent_model.train.val_split_files": [], "parent_model.val.val_split_files": [],
+                  "parent_model.test.val_split_files": []}
+# tiny end-to-end cases for the reference's evaluate() worker (CPU): (fixture, dataset, named configs, overrides, videos)
+EVAL_CASES = [
+    ("evaluate_davis_ona", "DAVIS-2017", ["DAVIS-2017", "e-OSVOS-OnA"],
+     {"num_epochs.eval": 4, "eval_online_adapt.step": 2, "eval_online_adapt.num_epochs": 2,
+      "parent_model.box_nms_thresh": 0.05},
+     dict(videos=[("synth_a", 3, 5, 2)], height=96, width=170)),
+    ("evaluate_youtube_late", "YouTube-VOS", ["YouTube-VOS", "e-OSVOS-OnA"],
+     {"num_epochs.eval": 3, "eval_online_adapt.step": 2, "eval_online_adapt.num_epochs": 2,
+      "parent_model.box_nms_thresh": 0.05, "datasets.val.split": "valid_seqs", "datasets.val.eval": True},
+     dict(videos=[("synth_y", 5, 5, 2, [0, 2])], height=90, width=160)),
+]
+
+
+def small_transform_spy(name, obj):
+    if name == "model":
+        obj.transform.min_size, obj.transform.max_size = (MIN_SIZE,), MAX_SIZE
+
+
+def evaluate_goldens(only=None):
+    """Runs the UNMODIFIED reference worker util.evaluate.evaluate (evaluate.py:20-439) on tiny synthetic trees and
+    stores what it returns through shared_dict plus the PNG predictions it wrote."""
+    import tempfile
+    from oracle import ref_harness as RH
+    for name, dataset, named, over, tree in EVAL_CASES:
+        if only and name not in only:
+            continue
+        over = dict(EVAL_OVERRIDES, **over)
+        cfg = RH.compose_config(named, over)
+        with tempfile.TemporaryDirectory() as wd:
+            if dataset == "DAVIS-2017":
+                RH.make_davis_tree(wd, tree["videos"], split=cfg["datasets"]["val"]["split"], height=tree["height"],
+                                   width=tree["width"])
+            else:
+                RH.make_youtube_tree(wd, tree["videos"], split=cfg["datasets"]["val"]["split"], height=tree["height"],
+                                     width=tree["width"])
+            shared, preds, log, _ = RH.run_reference_evaluate(cfg, "val", wd, "cpu", spy=small_transform_spy)
+        keep = {k: shared[k] for k in ("J_seq", "F_seq", "J_recall_seq", "J_decay_seq", "train_loss_seq",
+                                       "train_losses_seq", "init_J_seq")}
+        torch.save({"named": named, "overrides": over, "config": cfg, "tree": tree, "dataset": dataset, "shared": keep,
+                    "preds": {k: torch.from_numpy(v) for k, v in preds.items()}, "min_size": MIN_SIZE,
+                    "max_size": MAX_SIZE}, os.path.join(OUT, f"{name}.pt"))
+        print(name, "J", keep["J_seq"], "train_loss_seq", keep["train_loss_seq"])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "evaluate":
+        return evaluate_goldens(sys.argv[2:])
     mr, ll, mo, mm = ref_shims.reference_modules()
 
     # --- Lovasz hinge (loss_lovasz.py:78-126) ------------------------------------------------
@@ -91,6 +139,7 @@ def main():
                     "eval_probs": probs.half(), "eval_boxes": boxes, "min_size": MIN_SIZE, "max_size": MAX_SIZE},
                    os.path.join(OUT, f"model_small_{kind.lower()}.pt"))
         opt.reset()
+    evaluate_goldens()
     print("golden fixtures written to", OUT)
 
 

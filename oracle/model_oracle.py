@@ -38,7 +38,9 @@ class OracleMaskRCNN(TvMaskRCNN):
         super().__init__(bb, num_classes, box_roi_pool=box_pool, mask_roi_pool=mask_pool, mask_head=None,
                          box_score_thresh=box_nms_thresh)
         self.num_classes = num_classes
-        self.aug_mode = eval_augment_rpn_proposals_mode
+        # same attributes the reference's callers poke from outside (helper_func.py:72,92,123-125)
+        self.rpn._eval_augment_proposals_mode = eval_augment_rpn_proposals_mode
+        self.roi_heads._eval_augment_proposals_mode = eval_augment_rpn_proposals_mode
         self.loss_kind = maskrcnn_loss
         if replace_batch_with_group_norms:            # mask_rcnn.py:523-534
             for module in self.modules():
@@ -50,6 +52,15 @@ class OracleMaskRCNN(TvMaskRCNN):
                         module._modules[k] = gn
         self.backbone.requires_grad_(True)            # mask_rcnn.py:493-494
         self.fixed_proposals = None                   # test hook: bypass RPN proposals with given boxes
+        self.fixed_detection_rows = None              # test hook: take THESE proposal rows as the detections
+
+    @property
+    def aug_mode(self):
+        return self.rpn._eval_augment_proposals_mode
+
+    @aug_mode.setter
+    def aug_mode(self, v):
+        self.rpn._eval_augment_proposals_mode = v
 
     # ---- mask_rcnn.py:582-714
     @staticmethod
@@ -130,12 +141,21 @@ class OracleMaskRCNN(TvMaskRCNN):
             boxes = box_ops.clip_boxes_to_image(boxes, shape)
             labels = torch.arange(ncls).view(1, -1).expand_as(scores)
             boxes, scores, labels = boxes[:, 1:].reshape(-1, 4), scores[:, 1:].flatten(), labels[:, 1:].flatten()
+            all_boxes, all_scores = boxes, scores           # one candidate per (proposal row, foreground class)
             inds = torch.nonzero(scores > rh.score_thresh).squeeze(1)
             boxes, scores, labels = boxes[inds], scores[inds], labels[inds]
             keep = box_ops.remove_small_boxes(boxes, min_size=1e-2)
-            boxes, scores, labels = boxes[keep], scores[keep], labels[keep]
+            boxes, scores, labels, inds = boxes[keep], scores[keep], labels[keep], inds[keep]
             keep = box_ops.batched_nms(boxes, scores, labels, rh.nms_thresh)[:rh.detections_per_img]
-            res.append(dict(boxes=boxes[keep], scores=scores[keep], labels=labels[keep]))
+            rows = inds[keep]
+            if self.fixed_detection_rows is not None:      # test hook: the caller's choice among the candidates
+                rows = self.fixed_detection_rows[len(res)].to(torch.int64)
+                lab_all = torch.arange(ncls).view(1, -1).expand(len(all_scores) // (ncls - 1), ncls)[:, 1:].flatten()
+                res.append(dict(boxes=all_boxes[rows], scores=all_scores[rows], labels=lab_all[rows]))
+            else:
+                res.append(dict(boxes=boxes[keep], scores=scores[keep], labels=labels[keep]))
+            self.last_candidates = getattr(self, "last_candidates", [])
+            self.last_candidates.append(dict(boxes=all_boxes, scores=all_scores, rows=rows))
         return res
 
     # ---- mask_rcnn.py:95-214
@@ -157,6 +177,7 @@ class OracleMaskRCNN(TvMaskRCNN):
                 mask_props.append(proposals[i][pos])
                 pos_idx.append(matched_idxs[i][pos])
         else:
+            self.last_candidates = []
             result = self.detections_stage(class_logits, box_regression, proposals, image_shapes)
             self.last_detections = [{k: v.detach().clone() for k, v in r.items()} for r in result]
             mask_props = [r["boxes"] for r in result]
@@ -234,9 +255,12 @@ class OracleMetaOptimizer:
     """NEURON-level learned-LR SGD: meta_optim.py:46-67 (LR init), :144-155 (reset), :177-214 (step);
     meta_model.py:49-80 (param groups live in module._parameters)."""
 
-    def __init__(self, model, init_lr=1e-3, use_log_init_lr=False):
+    def __init__(self, model, init_lr=1e-3, use_log_init_lr=False, **_unused):
         self.model = model
+        self.meta_model = self                      # meta_optim.meta_model.detach_param_groups() (evaluate.py:274)
         self.use_log = use_log_init_lr
+        self.only_box_head = False
+        self.training = False
         self.lrs = []
         for _, p in model.named_parameters():
             if p.requires_grad:
@@ -251,9 +275,41 @@ class OracleMetaOptimizer:
                 if p is not None and p.requires_grad:
                     yield n_m, module, n_p, p
 
-    def reset(self):
+    def reset(self, keep_state=False):
+        if keep_state:
+            self.detach_param_groups()
+            return
         for n_m, module, n_p, _ in self.groups():
             module._parameters[n_p] = self.init[f"{n_m}.{n_p}"]
+
+    # ---- the reference's optimizer surface used by evaluate.py:119-121,196-205,267-274
+    def state_dict(self):
+        names = list(self.init.keys())
+        sd = OrderedDict((f"log_init_lr_{n.replace('.', '-')}", l) for n, l in zip(names, self.lrs))
+        sd.update((f"model_init_{n.replace('.', '-')}", p) for n, p in self.init.items())
+        return sd
+
+    def load_state_dict(self, sd):
+        with torch.no_grad():
+            for n, l in zip(list(self.init.keys()), self.lrs):
+                l.copy_(sd[f"log_init_lr_{n.replace('.', '-')}"])
+            for n, p in self.init.items():
+                p.copy_(sd[f"model_init_{n.replace('.', '-')}"])
+
+    def eval(self):
+        self.training = False
+
+    def train(self):
+        self.training = True
+
+    def set_train_loss(self, loss):
+        pass
+
+    def detach_param_groups(self):
+        for _, module, n_p, p in self.groups():
+            d = p.detach()
+            d.requires_grad = True
+            module._parameters[n_p] = d
 
     def step(self, loss):
         groups = list(self.groups())

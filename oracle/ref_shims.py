@@ -3,7 +3,7 @@
 Imports the UNMODIFIED reference (dvl-tum/e-osvos, read-only at /root/reference) under the installed
 torch 2.11 / torchvision 0.26 by monkey-patching only the API drift listed in SURVEY.md §8c.  Used in
 the build container to pin oracle/ against the real reference and to generate tests/golden/*; the GPU
-box has no /root/reference, so nothing that runs there may import this module.
+box has no /root/reference: there the unmodified copy under oracle/_ref/ (oracle/install_ref.py) is imported.
 """
 import os
 import sys
@@ -12,7 +12,20 @@ import types
 import torch
 import torchvision
 
-REFERENCE_ROOT = os.environ.get("EOSVOS_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference():
+    """$EOSVOS_REFERENCE, else the read-only checkout of the build container, else the unmodified copy that
+    oracle/install_ref.py placed under oracle/_ref/ (what the GPU box has)."""
+    cands = [os.environ.get("EOSVOS_REFERENCE"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "src", "networks")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 class _CallableInt(int):

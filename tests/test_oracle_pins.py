@@ -62,3 +62,57 @@ def test_model_matches_reference(kind):
         probs, boxes = model(g["img"], g["tgt"])
     assert torch.allclose(boxes, g["eval_boxes"], rtol=1e-4, atol=1e-3)
     assert (probs - g["eval_probs"].float()).abs().max().item() < 2e-3   # fixture stored as fp16
+
+
+def _oracle_evaluate_case(g):
+    """Rebuilds the synthetic sequence of a tests/golden/evaluate_*.pt fixture and runs the oracle's
+    evaluate_sequence with the configuration the reference worker was given."""
+    from oracle import evaluate_oracle as EO
+    from oracle import ref_harness as RH
+    cfg = g["config"]            # the composed Sacred configuration the reference worker ran with
+    tree = g["tree"]
+    out = {}
+    for video in tree["videos"]:
+        name, seed, T, K = video[:4]
+        appear = video[4] if len(video) > 4 else None
+        frames, labels = RH.synthetic_video(seed, T, tree["height"], tree["width"], K, appear=appear)
+        if appear is None:
+            seq = EO.OracleSequence(frames, labels)
+        else:
+            seq = EO.OracleSequence(frames, labels, annotated=[i in set(appear) for i in range(T)],
+                                    objects=[(k + 1, appear[k]) for k in range(K)], test_mode=True)
+        EO.set_random_seeds(cfg["seed"])
+        pm = cfg["parent_model"]
+        model = MO.OracleMaskRCNN(pm["encoder"], 2, pm["roi_pool_output_sizes"], pm["eval_augment_rpn_proposals_mode"],
+                                  pm["replace_batch_with_group_norms"], pm["box_nms_thresh"], pm["maskrcnn_loss"])
+        model.transform.min_size, model.transform.max_size = (g["min_size"],), g["max_size"]
+        opt = MO.OracleMetaOptimizer(model, cfg["meta_optim_cfg"]["init_lr"], cfg["meta_optim_cfg"]["use_log_init_lr"])
+        import copy
+        sd = copy.deepcopy(opt.state_dict())
+        ona = cfg["eval_online_adapt"]
+        pred, rec = EO.evaluate_sequence(
+            model, opt, sd, seq, seed=cfg["seed"], num_epochs_eval=cfg["num_epochs"]["eval"], step=ona["step"],
+            ona_epochs=ona["num_epochs"], min_prop=ona["min_prop"], batch_size=cfg["data_cfg"]["batch_sizes"]["train"],
+            random_train_transform=cfg["data_cfg"]["random_train_transform"], reset_model_mode=ona["reset_model_mode"])
+        out[name] = (pred, rec)
+    return out
+
+
+@pytest.mark.parametrize("case", ["evaluate_davis_ona", "evaluate_youtube_late"])
+def test_evaluate_sequence_matches_reference(case):
+    """oracle/evaluate_oracle.py (data path + fine-tune rounds + online adaptation + run_loader + merge) against the
+    UNMODIFIED reference worker `util.evaluate.evaluate` (evaluate.py:20-439) run on the same synthetic tree: the
+    final loss of every fine-tuning round and every predicted object-id mask.  Same CPU arithmetic and the same
+    random streams on both sides => equal up to float summation order."""
+    g = load(f"{case}.pt")
+    res = _oracle_evaluate_case(g)
+    losses = []
+    for name, (pred, rec) in res.items():
+        losses += rec["train_loss_seq"]
+        ref = g["preds"][name]
+        diff = (pred != ref).float().mean().item()
+        assert pred.shape == ref.shape and diff < 1e-4, (name, diff)
+    ref_losses = g["shared"]["train_loss_seq"]
+    assert len(losses) == len(ref_losses)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 1e-4 * abs(b), (losses, ref_losses)
