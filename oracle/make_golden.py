@@ -69,10 +69,103 @@ def evaluate_goldens(only=None):
         print(name, "J", keep["J_seq"], "train_loss_seq", keep["train_loss_seq"])
 
 
+def radam_golden():
+    """The reference's own optimizer (src/util/radam.py:28-94) with the per-group lr / weight decay of
+    train_meta.py:110-127 over 8 steps (crosses the N_sma >= 5 switch at step 6)."""
+    from oracle import ref_harness as RH
+    _, _, _, radam = RH.reference_workers()
+    g = torch.Generator().manual_seed(17)
+    shapes = [(7, 5), (11,), (3, 4, 2, 2)]
+    groups_cfg = [(1e-5, 1e-3), (1e-5, 0.0), (1e-3, 0.0)]         # model_init / log_init_lr / default
+    params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    p0 = [p.detach().clone() for p in params]
+    opt = radam.RAdam([{"params": [p], "lr": lr, "weight_decay": wd} for p, (lr, wd) in zip(params, groups_cfg)], lr=1e-3)
+    grads, traj = [], []
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(8):
+            gs = [torch.randn(s, generator=g) for s in shapes]
+            for p, gg in zip(params, gs):
+                p.grad = gg.clone()
+            opt.step()
+            grads.append(gs)
+            traj.append([p.detach().clone() for p in params])
+    torch.save({"p0": p0, "groups": groups_cfg, "grads": grads, "traj": traj}, os.path.join(OUT, "radam.pt"))
+    print("radam golden: final norms", [t.norm().item() for t in traj[-1]])
+
+
+def meta_run_golden():
+    """ONE meta-iteration of the UNMODIFIED reference worker util.meta_run.meta_run (meta_run.py:14-243) on a tiny
+    synthetic DAVIS-2017 train tree, CPU: meta_batch_size 1, num_epochs.train 2, bptt_epochs 2.  Stored: the batches
+    the worker fed to the model (so the oracle can be driven with the very same tensors), its losses, and the
+    meta-gradients it accumulated into `shared_meta_optim_grads` (norm + first 32 values per parameter)."""
+    import tempfile
+    from oracle import ref_harness as RH
+    ev, hf, mrun, _ = RH.reference_workers()
+    import meta_optim.meta_optim as ref_mo
+    over = dict(EVAL_OVERRIDES, **{"meta_batch_size": 1, "num_epochs.train": 2, "bptt_epochs": 2,
+                                   "datasets.train.split": "train_seqs", "eval_datasets": False,
+                                   "num_meta_processes_per_gpu": 1,
+                                   # per-task colour jitter calls a torchvision-0.4-only API (ColorJitter.get_params
+                                   # returning a transform); it precedes the model and is not on the path
+                                   "random_frame_transform_per_task": False})
+    cfg = RH.compose_config(["DAVIS-2017"], over)
+    seen = []
+
+    def spy_init(**kw):
+        model, states = hf.init_parent_model(**kw)
+        model.transform.min_size, model.transform.max_size = (MIN_SIZE,), MAX_SIZE
+        model.register_forward_pre_hook(
+            lambda m, args: seen.append((args[0].clone(), args[1].clone(), torch.get_rng_state().clone())))
+        return model, states
+
+    class OneShot(dict):
+        def __getitem__(self, k):
+            if k == "sub_iter_done" and dict.get(self, k):
+                raise RH._StopEvaluation()
+            return dict.__getitem__(self, k)
+
+    saved = (mrun.init_parent_model, mrun.device_for_process)
+    try:
+        mrun.init_parent_model = spy_init
+        mrun.device_for_process = lambda *a, **k: (torch.device("cpu"), torch.device("cpu"))
+        with tempfile.TemporaryDirectory() as wd, RH._cwd(wd):
+            RH.make_davis_tree(wd, [("synth_t", 9, 4, 1)], split="train_seqs", height=96, width=170)
+            hf.set_random_seeds(cfg["seed"])
+            model, _ = hf.init_parent_model(**cfg["parent_model"])
+            meta_optim = ref_mo.MetaOptimizer(model, **cfg["meta_optim_cfg"])
+            sd = {k: v.detach().clone() for k, v in meta_optim.state_dict().items()}
+            grads = {n: torch.zeros_like(p) for n, p in meta_optim.named_parameters()}
+            shared = OneShot(sub_iter_done=False, meta_epoch_done=False)
+            try:
+                mrun.meta_run(0, model.state_dict(), sd, torch.get_rng_state(), cfg, cfg["datasets"]["train"], shared,
+                              {"meta_iter": 0, "meta_epoch": 0}, grads, None, 1)
+            except RH._StopEvaluation:
+                pass
+    finally:
+        mrun.init_parent_model, mrun.device_for_process = saved
+    metrics = dict.__getitem__(shared, "seqs_metrics")
+    packed = []
+    for a, b, r in seen:
+        u8 = (a * 255.0).round().to(torch.uint8)
+        assert torch.equal(u8.float() / 255.0, a), "frames are k/255 exactly (no colour jitter / warp in this case)"
+        packed.append((u8, b.to(torch.uint8), r))
+    torch.save({"config": cfg, "batches": packed,
+                "train_loss": metrics["train_loss"], "meta_loss": metrics["meta_loss"],
+                "grad_norms": {n: g_.norm().item() for n, g_ in grads.items()},
+                "grad_samples": {n: g_.flatten()[:32].clone() for n, g_ in grads.items()},
+                "min_size": MIN_SIZE, "max_size": MAX_SIZE}, os.path.join(OUT, "meta_run.pt"))
+    print("meta_run golden:", len(seen), "forwards; train", metrics["train_loss"], "meta", metrics["meta_loss"])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "evaluate":
         return evaluate_goldens(sys.argv[2:])
+    if len(sys.argv) > 1 and sys.argv[1] == "meta":
+        radam_golden()
+        return meta_run_golden()
     mr, ll, mo, mm = ref_shims.reference_modules()
 
     # --- Lovasz hinge (loss_lovasz.py:78-126) ------------------------------------------------
@@ -140,6 +233,8 @@ def main():
                    os.path.join(OUT, f"model_small_{kind.lower()}.pt"))
         opt.reset()
     evaluate_goldens()
+    radam_golden()
+    meta_run_golden()
     print("golden fixtures written to", OUT)
 
 

@@ -345,22 +345,29 @@ def jaccard(pred, gt):
     return 1.0 if union == 0 else (pred & gt).sum().item() / union
 
 
-def oracle_meta_gradients(model, lrs, train_batch, meta_batch, num_epochs=5):
+def oracle_meta_gradients(model, lrs, train_batch, meta_batch, num_epochs=5, rng_states=None):
     """First-order BPTT of reference src/util/meta_run.py:124-214 in plain torch: theta_{k+1} = theta_k - lr * g_k with
     g_k detached (meta_optim.py:202-207, second_order False), meta loss after the last step, gradients w.r.t. theta_0
-    and the learning rates.  `model` must hold leaf parameters theta_0; `lrs` leaf tensors (requires_grad)."""
+    and the learning rates.  `model` must hold leaf parameters theta_0; `lrs` leaf tensors (requires_grad).
+    train_batch: one (inputs, gts) pair or a list with one pair per epoch; rng_states: optional torch RNG state to
+    install before every forward (num_epochs train forwards + the meta forward).
+    Pinned to the unmodified reference worker by tests/test_oracle_pins.py::test_meta_gradients_match_reference."""
     slots = [(n_m, module, n_p) for n_m, module in model.named_modules()
              for n_p, p in module._parameters.items() if p is not None and p.requires_grad]
     theta0 = [module._parameters[n_p] for _, module, n_p in slots]
     cur = theta0
     try:
-        for _ in range(num_epochs):
+        for e in range(num_epochs):
             model.train()
-            loss, _ = model(*train_batch)
+            if rng_states is not None:
+                torch.set_rng_state(rng_states[e])
+            loss, _ = model(*(train_batch[e] if isinstance(train_batch, list) else train_batch))
             grads = torch.autograd.grad(loss, cur)
             cur = [p - g.detach() * lr for p, g, lr in zip(cur, grads, lrs)]
             for (_, module, n_p), t in zip(slots, cur):
                 module._parameters[n_p] = t
+        if rng_states is not None:
+            torch.set_rng_state(rng_states[num_epochs])
         meta_loss, _ = model(*meta_batch)
         out = torch.autograd.grad(meta_loss, list(theta0) + list(lrs), allow_unused=True)
     finally:

@@ -116,3 +116,48 @@ def test_evaluate_sequence_matches_reference(case):
     assert len(losses) == len(ref_losses)
     for a, b in zip(losses, ref_losses):
         assert abs(a - b) <= 1e-4 * abs(b), (losses, ref_losses)
+
+
+def test_radam_matches_reference():
+    """oracle radam_reference against the reference's own optimizer (src/util/radam.py:28-94) over 8 steps with the
+    per-group lr / weight decay of train_meta.py:110-127."""
+    g = load("radam.pt")
+    ps = [p.clone() for p in g["p0"]]
+    ms = [torch.zeros_like(p) for p in ps]
+    vs = [torch.zeros_like(p) for p in ps]
+    for step, (grads, want) in enumerate(zip(g["grads"], g["traj"]), start=1):
+        for i, (lr, wd) in enumerate(g["groups"]):
+            ps[i], ms[i], vs[i] = MO.radam_reference(ps[i], grads[i], ms[i], vs[i], step, lr=lr, wd=wd)
+            assert torch.allclose(ps[i], want[i], rtol=1e-6, atol=1e-8), (step, i)
+
+
+def test_meta_gradients_match_reference():
+    """oracle_meta_gradients (first-order BPTT) against ONE meta-iteration of the unmodified reference worker
+    util.meta_run.meta_run (meta_run.py:96-238): same theta_0 / lambda (same seeds), the very batches the worker fed
+    to the model and the RNG state it had at every forward."""
+    from oracle import evaluate_oracle as EO
+    g = load("meta_run.pt")
+    cfg = g["config"]
+    EO.set_random_seeds(cfg["seed"])
+    pm = cfg["parent_model"]
+    model = MO.OracleMaskRCNN(pm["encoder"], 2, pm["roi_pool_output_sizes"], pm["eval_augment_rpn_proposals_mode"],
+                              pm["replace_batch_with_group_norms"], pm["box_nms_thresh"], pm["maskrcnn_loss"])
+    model.transform.min_size, model.transform.max_size = (g["min_size"],), g["max_size"]
+    opt = MO.OracleMetaOptimizer(model, cfg["meta_optim_cfg"]["init_lr"], cfg["meta_optim_cfg"]["use_log_init_lr"])
+    lrs = [l.clone().requires_grad_(True) for l in opt.lrs]
+    batches = [(a.float() / 255.0, b.float()) for a, b, _ in g["batches"]]
+    rng = [r for _, _, r in g["batches"]]
+    n = cfg["num_epochs"]["train"]
+    assert len(batches) == n + 1
+    meta_loss, dtheta, dlr = MO.oracle_meta_gradients(model, lrs, batches[:n], batches[n], num_epochs=n, rng_states=rng)
+    assert abs(meta_loss.item() - g["meta_loss"]["synth_t"][0]) <= 1e-4 * abs(meta_loss.item())
+    names = [k for k, p in model.named_parameters() if p.requires_grad]
+    assert len(names) == len(dtheta) == len(dlr)
+    for nme, gt, gl in zip(names, dtheta, dlr):
+        for prefix, got in (("model_init_", gt), ("log_init_lr_", gl)):
+            key = prefix + nme.replace(".", "-")
+            ref_n = g["grad_norms"][key]
+            got = torch.zeros(1) if got is None else got
+            assert abs(got.norm().item() - ref_n) <= 2e-3 * max(ref_n, 1e-6) + 1e-9, (key, got.norm().item(), ref_n)
+            if ref_n > 0:
+                assert torch.allclose(got.flatten()[:32], g["grad_samples"][key], rtol=5e-3, atol=1e-6 * max(ref_n, 1e-12) + 1e-10), key
