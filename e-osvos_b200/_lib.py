@@ -45,6 +45,14 @@ SIGNATURES = {
     "eosvos_mask_to_bbox": [_P, _P, _I, _I, _I, _I, _P],
     "eosvos_nms_scratch_bytes": [_I, _I],
     "eosvos_nms_segments": [_P, _P, _I, _I, _F, _P, _P, _P],
+    "eosvos_rpn_scratch_bytes": [_I, _P, _I, _I],
+    "eosvos_rpn_scratch_zero_bytes": [_I, _I],
+    "eosvos_rpn_select": [_P, _P, _I, _I, _I, _P, _P, _I, _F, _F, _F, _P, _P, _P, _P, _P],
+    "eosvos_rpn_postnms": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "eosvos_extend_boxes": [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _F, _I, _I, _P, _P],
+    "eosvos_det_top1": [_P, _P, _I, _I, _I, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P],
+    "eosvos_roi_match": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P],
+    "eosvos_roi_encode": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "eosvos_meta_update_chunk_elems": [],
     "eosvos_meta_update": [_P, _P, _I, _I, _P],
     "eosvos_radam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
@@ -64,7 +72,8 @@ SIGNATURES = {
     "eosvos_relu_bwd": [_P, _P, _P, _L, _P],
     "eosvos_colsum": [_P, _P, _L, _I, _F, _P],
 }
-_RESTYPES = {"eosvos_nms_scratch_bytes": c_longlong, "eosvos_last_error": c_char_p, "eosvos_launch_count": ctypes.c_ulonglong}
+_RESTYPES = {"eosvos_nms_scratch_bytes": c_longlong, "eosvos_rpn_scratch_bytes": c_longlong,
+             "eosvos_rpn_scratch_zero_bytes": c_longlong, "eosvos_last_error": c_char_p, "eosvos_launch_count": ctypes.c_ulonglong}
 
 
 class EosvosError(RuntimeError):

@@ -1,0 +1,730 @@
+// Region-proposal and detection post-processing as fixed-shape device kernels.
+//
+// Reference call sites: src/networks/mask_rcnn.py:237-249 (BoxCoder.decode of ALL 257,796 x N anchors, then tv rpn.py
+// filter_proposals: per-level top-k, clip, small-box / score filter, per-level NMS, post-NMS top-n), :251-332 (EXTEND /
+// REPLACE proposal augmentation from the previous frame's box), :347-420 (postprocess_detections) and tv
+// roi_heads.py:642-678 (assign_targets_to_proposals).  The reference reaches ~150 small ATen launches and several host
+// synchronisations per image through these; here every stage is one launch over padded, statically shaped buffers:
+//
+//   rpn_keys_kernel / rpn_hist2_kernel / rpn_compact_kernel   two-level (11 + 11 bit) radix select of the top-k
+//                                                              objectness logits of every (image, level) segment
+//   rpn_sort_decode_kernel   bitonic sort of the <= 4096 survivors, box decoding of ONLY the selected anchors,
+//                            clip, validity (min size, score threshold), sigmoid
+//   (nms.cu)                 per-segment NMS on the decoded boxes
+//   rpn_postnms_kernel       rank of every kept box among all levels of its image by merge-counting the sorted
+//                            segments (binary searches over prefix sums of the keep flags) -> first post_nms_top_n
+//   extend_boxes_kernel      jittered copies of the target box (CPU random numbers uploaded by the caller, same
+//                            arithmetic order as the reference so the boxes are bit-equal)
+//   det_top1_kernel          detections_per_img == 1 (multi_object 'single_id', evaluate.py:106-107): softmax, box
+//                            decode, clip, score / size filter and arg-max in one launch (the best-scoring valid
+//                            candidate always survives NMS)
+//   roi_match_kernel         IoU matching of proposals (+ appended ground-truth boxes) with class labels and the
+//                            foreground / background counts the sampler needs
+//   roi_encode_kernel        regression targets + (image, box) rows of the sampled RoIs
+// Arithmetic that feeds discrete decisions uses explicit round-to-nearest multiplies / adds (no FMA contraction), i.e.
+// the operation sequence of the ATen elementwise kernels the reference runs.
+#include "common.h"
+#include "../../include/eosvos_b200.h"
+
+namespace eosvos {
+
+constexpr int RPN_MAX_LEVELS = 8;
+constexpr int RPN_BINS = 2048;       // 11-bit digits
+constexpr int RPN_CAP = 4096;        // survivors per segment handed to the sorter
+constexpr int RPN_CHUNK = 4096;      // anchors per CTA in the streaming passes
+
+struct RpnLevels {
+  const float* head[RPN_MAX_LEVELS];   // fp32 [N * hw][16]: A objectness logits, then A x 4 box deltas
+  int hw[RPN_MAX_LEVELS];              // pixels per image
+  int anchor_off[RPN_MAX_LEVELS];      // first anchor of the level in the per-image anchor list
+  int out_off[RPN_MAX_LEVELS];         // first slot of the level in the per-image candidate list
+  int k[RPN_MAX_LEVELS];               // min(pre_nms_top_n, hw * A)
+  int num_levels, A, anchors_per_image, cand_per_image;
+};
+
+__device__ __forceinline__ unsigned ord_key(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);     // ascending unsigned order == ascending float order
+}
+
+// Largest digit d with  #(keys whose digit > d) < need <= #(keys whose digit >= d); also returns that first count.
+// hist: RPN_BINS counters (global or shared).  Called by all threads of a 256-thread CTA; result broadcast.
+__device__ void find_digit(const unsigned* __restrict__ hist, int need, int* s_tmp /* >= 12 ints of smem */, int& digit,
+                           int& above) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int PER = RPN_BINS / 256;
+  unsigned local[PER];
+  unsigned sum = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {            // thread t owns bins (2047 - 8t) ... (2047 - 8t - 7), descending
+    local[j] = hist[RPN_BINS - 1 - (tid * PER + j)];
+    sum += local[j];
+  }
+  unsigned inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) s_tmp[warp] = (int)inc;
+  if (tid == 0) s_tmp[10] = -1;
+  __syncthreads();
+  unsigned warp_base = 0;
+  for (int w = 0; w < warp; ++w) warp_base += (unsigned)s_tmp[w];
+  const unsigned before = warp_base + inc - sum;       // keys in bins above this thread's bins
+  if ((int)before < need && need <= (int)(before + sum)) {
+    unsigned acc = before;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if ((int)acc < need && need <= (int)(acc + local[j])) {
+        s_tmp[10] = RPN_BINS - 1 - (tid * PER + j);
+        s_tmp[11] = (int)acc;
+      }
+      acc += local[j];
+    }
+  }
+  __syncthreads();
+  digit = s_tmp[10];
+  above = s_tmp[11];
+  __syncthreads();
+}
+
+// grid (chunks, levels, images) x 256
+__global__ void __launch_bounds__(256)
+rpn_keys_kernel(const RpnLevels lv, unsigned* __restrict__ keys, unsigned* __restrict__ hist1) {
+  const int l = blockIdx.y, n = blockIdx.z;
+  const int count = lv.hw[l] * lv.A;
+  const int base = blockIdx.x * RPN_CHUNK;
+  if (base >= count) return;
+  __shared__ unsigned h[RPN_BINS];
+  for (int b = threadIdx.x; b < RPN_BINS; b += 256) h[b] = 0;
+  __syncthreads();
+  const float* src = lv.head[l] + (size_t)n * lv.hw[l] * 16;
+  unsigned* dst = keys + (size_t)n * lv.anchors_per_image + lv.anchor_off[l];
+  const int end = min(base + RPN_CHUNK, count);
+  for (int i = base + threadIdx.x; i < end; i += 256) {
+    const int row = i / lv.A, a = i - row * lv.A;
+    const unsigned key = ord_key(src[(size_t)row * 16 + a]);
+    dst[i] = key;
+    atomicAdd(&h[key >> 21], 1u);
+  }
+  __syncthreads();
+  unsigned* g = hist1 + (size_t)(n * lv.num_levels + l) * RPN_BINS;
+  for (int b = threadIdx.x; b < RPN_BINS; b += 256)
+    if (h[b]) atomicAdd(&g[b], h[b]);
+}
+
+__global__ void __launch_bounds__(256)
+rpn_hist2_kernel(const RpnLevels lv, const unsigned* __restrict__ keys, const unsigned* __restrict__ hist1,
+                 unsigned* __restrict__ hist2) {
+  const int l = blockIdx.y, n = blockIdx.z;
+  const int count = lv.hw[l] * lv.A;
+  const int base = blockIdx.x * RPN_CHUNK;
+  if (base >= count) return;
+  __shared__ unsigned h[RPN_BINS];
+  __shared__ int s_tmp[12];
+  const int seg = n * lv.num_levels + l;
+  int d1, above1;
+  find_digit(hist1 + (size_t)seg * RPN_BINS, lv.k[l], s_tmp, d1, above1);
+  for (int b = threadIdx.x; b < RPN_BINS; b += 256) h[b] = 0;
+  __syncthreads();
+  const unsigned* src = keys + (size_t)n * lv.anchors_per_image + lv.anchor_off[l];
+  const int end = min(base + RPN_CHUNK, count);
+  for (int i = base + threadIdx.x; i < end; i += 256) {
+    const unsigned key = src[i];
+    if ((int)(key >> 21) == d1) atomicAdd(&h[(key >> 10) & (RPN_BINS - 1)], 1u);
+  }
+  __syncthreads();
+  unsigned* g = hist2 + (size_t)seg * RPN_BINS;
+  for (int b = threadIdx.x; b < RPN_BINS; b += 256)
+    if (h[b]) atomicAdd(&g[b], h[b]);
+}
+
+__global__ void __launch_bounds__(256)
+rpn_compact_kernel(const RpnLevels lv, const unsigned* __restrict__ keys, const unsigned* __restrict__ hist1,
+                   const unsigned* __restrict__ hist2, unsigned* __restrict__ counters,
+                   unsigned long long* __restrict__ list) {
+  const int l = blockIdx.y, n = blockIdx.z;
+  const int count = lv.hw[l] * lv.A;
+  const int base = blockIdx.x * RPN_CHUNK;
+  if (base >= count) return;
+  __shared__ int s_tmp[12];
+  const int seg = n * lv.num_levels + l;
+  int d1, above1, d2, above2;
+  find_digit(hist1 + (size_t)seg * RPN_BINS, lv.k[l], s_tmp, d1, above1);
+  find_digit(hist2 + (size_t)seg * RPN_BINS, lv.k[l] - above1, s_tmp, d2, above2);
+  const unsigned prefix22 = ((unsigned)d1 << 11) | (unsigned)d2;
+  const unsigned* src = keys + (size_t)n * lv.anchors_per_image + lv.anchor_off[l];
+  const int end = min(base + RPN_CHUNK, count);
+  for (int i = base + threadIdx.x; i < end; i += 256) {
+    const unsigned key = src[i];
+    if ((key >> 10) >= prefix22) {
+      const unsigned slot = atomicAdd(&counters[seg], 1u);
+      if (slot < RPN_CAP) list[(size_t)seg * RPN_CAP + slot] = ((unsigned long long)key << 32) | (unsigned)(~(unsigned)i);
+    }
+  }
+}
+
+__device__ __forceinline__ void bitonic_desc(unsigned long long* s, int n /* power of two */) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const bool desc = (i & k) == 0;
+        const unsigned long long a = s[i], b = s[p];
+        if ((a < b) == desc) {
+          s[i] = b;
+          s[p] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct RpnDecodeArgs {
+  float img_h[16], img_w[16];          // per image (resized, un-padded) size; N <= 16
+  float clip, min_size, score_thresh;  // bbox_xform_clip, rpn.min_size, rpn.score_thresh
+};
+
+// grid (levels, images) x 1024
+__global__ void __launch_bounds__(1024)
+rpn_sort_decode_kernel(const RpnLevels lv, const RpnDecodeArgs args, const unsigned* __restrict__ counters,
+                       const unsigned long long* __restrict__ list, const float4* __restrict__ anchors,
+                       float4* __restrict__ boxes, float* __restrict__ scores, unsigned char* __restrict__ valid) {
+  __shared__ unsigned long long s[RPN_CAP];
+  const int l = blockIdx.x, n = blockIdx.y;
+  const int seg = n * lv.num_levels + l;
+  const int n_sel = min((int)counters[seg], RPN_CAP);
+  int n_sort = 1;
+  while (n_sort < n_sel) n_sort <<= 1;
+  n_sort = max(n_sort, 2);
+  for (int i = threadIdx.x; i < n_sort; i += blockDim.x) s[i] = i < n_sel ? list[(size_t)seg * RPN_CAP + i] : 0ULL;
+  __syncthreads();
+  bitonic_desc(s, n_sort);
+  const int k = lv.k[l];
+  const float* src = lv.head[l] + (size_t)n * lv.hw[l] * 16;
+  const float4* anc = anchors + lv.anchor_off[l];
+  const size_t out = (size_t)n * lv.cand_per_image + lv.out_off[l];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    float prob = 0.f;
+    bool ok = false;
+    if (j < n_sel) {
+      const int idx = (int)(~(unsigned)(s[j] & 0xffffffffULL));
+      const int row = idx / lv.A, a = idx - row * lv.A;
+      const float* r = src + (size_t)row * 16;
+      const float logit = r[a];
+      const float dx = r[lv.A + a * 4 + 0], dy = r[lv.A + a * 4 + 1];
+      const float dw = fminf(r[lv.A + a * 4 + 2], args.clip), dh = fminf(r[lv.A + a * 4 + 3], args.clip);
+      const float4 an = anc[idx];
+      // tv _utils.py BoxCoder.decode_single (weights 1, 1, 1, 1), one rounding per ATen elementwise op
+      const float w = __fsub_rn(an.z, an.x), h = __fsub_rn(an.w, an.y);
+      const float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
+      const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+      const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+      const float hw_ = __fmul_rn(0.5f, pw), hh_ = __fmul_rn(0.5f, ph);
+      float x1 = __fsub_rn(pcx, hw_), y1 = __fsub_rn(pcy, hh_), x2 = __fadd_rn(pcx, hw_), y2 = __fadd_rn(pcy, hh_);
+      const float W = args.img_w[n], H = args.img_h[n];
+      x1 = fminf(fmaxf(x1, 0.f), W);
+      x2 = fminf(fmaxf(x2, 0.f), W);
+      y1 = fminf(fmaxf(y1, 0.f), H);
+      y2 = fminf(fmaxf(y2, 0.f), H);
+      prob = 1.f / (1.f + expf(-logit));
+      ok = (x2 - x1) >= args.min_size && (y2 - y1) >= args.min_size && prob >= args.score_thresh;
+      if (ok) box = make_float4(x1, y1, x2, y2);
+    }
+    boxes[out + j] = box;             // invalid boxes are zero: zero area, IoU 0 with everything, suppress nothing
+    scores[out + j] = prob;
+    valid[out + j] = ok ? 1 : 0;
+  }
+}
+
+// One CTA per image.  Candidates are sorted by descending score inside every level segment; `keep` are the NMS flags.
+// Final order = descending score over all kept boxes, ties by candidate index (== torch's stable argsort of the
+// concatenated list): rank(i) = #kept before i in its own segment + sum over other segments of #kept with a larger
+// score (or an equal score when the segment comes first).
+__global__ void __launch_bounds__(1024)
+rpn_postnms_kernel(const RpnLevels lv, const float4* __restrict__ boxes, const float* __restrict__ scores,
+                   const unsigned char* __restrict__ valid, const unsigned char* __restrict__ keep, int post_n,
+                   int out_stride, int out_offset, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
+                   int* __restrict__ out_count) {
+  extern __shared__ unsigned char smem_raw[];
+  const int n = blockIdx.x;
+  const int C = lv.cand_per_image, L = lv.num_levels;
+  float* s_score = reinterpret_cast<float*>(smem_raw);                 // [C]
+  int* s_pre = reinterpret_cast<int*>(s_score + C);                    // [C + L]: exclusive prefix per segment (+ total)
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const size_t base = (size_t)n * C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < C; i += blockDim.x) s_score[i] = scores[base + i];
+  // exclusive scan of the flags, segment by segment (block-wide, 1024 per round)
+  for (int l = 0; l < L; ++l) {
+    const int off = lv.out_off[l], k = lv.k[l];
+    int* pre = s_pre + off + l;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int b = 0; b < k; b += blockDim.x) {
+      const int i = b + tid;
+      const int f = (i < k && keep[base + off + i] && valid[base + off + i]) ? 1 : 0;
+      int inc = f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (lane == 31) s_warp[warp] = inc;
+      __syncthreads();
+      int wb = 0;
+      for (int w = 0; w < warp; ++w) wb += s_warp[w];
+      const int carry = s_carry;
+      if (i < k) pre[i] = carry + wb + inc - f;
+      __syncthreads();
+      if (tid == blockDim.x - 1) s_carry = carry + wb + inc;
+      __syncthreads();
+    }
+    if (tid == 0) pre[k] = s_carry;
+    __syncthreads();
+  }
+  int total = 0;
+  for (int l = 0; l < L; ++l) total += s_pre[lv.out_off[l] + l + lv.k[l]];
+  const int n_out = min(total, post_n);
+  if (tid == 0) out_count[n] = n_out;
+  float4* ob = out_boxes + (size_t)n * out_stride + out_offset;
+  float* os = out_scores ? out_scores + (size_t)n * out_stride + out_offset : nullptr;
+  for (int i = tid; i < post_n; i += blockDim.x) {       // padding rows: zero boxes
+    if (i >= n_out) {
+      ob[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (os) os[i] = 0.f;
+    }
+  }
+  for (int la = 0; la < L; ++la) {
+    const int offa = lv.out_off[la], ka = lv.k[la];
+    const int* prea = s_pre + offa + la;
+    for (int q = tid; q < ka; q += blockDim.x) {
+      if (prea[q + 1] == prea[q]) continue;              // not kept
+      const float sc = s_score[offa + q];
+      int rank = prea[q];
+      for (int lb = 0; lb < L; ++lb) {
+        if (lb == la) continue;
+        const int offb = lv.out_off[lb], kb = lv.k[lb];
+        const float* sb = s_score + offb;
+        int lo = 0, hi = kb;                              // first position whose score is NOT "ahead of" sc
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const bool ahead = lb < la ? (sb[mid] >= sc) : (sb[mid] > sc);
+          if (ahead) lo = mid + 1; else hi = mid;
+        }
+        rank += s_pre[offb + lb + lo];
+      }
+      if (rank < post_n) {
+        ob[rank] = boxes[base + offa + q];
+        if (os) os[rank] = sc;
+      }
+    }
+  }
+}
+
+// jittered copies of the (resized) target boxes: reference mask_rcnn.py:262-285.  rand: [B][G][4][n_aug] uniform
+// numbers drawn on the host in the reference's order (x_min, y_min, x_max, y_max draws per box).  stats: int32
+// [B][G][5] = (xmin, ymin, xmax, ymax, count) in input-frame pixels (mask_to_bbox / paste tail); a target without
+// pixels falls back to `fallback` (the start target, helper_func.py:124-126).
+__global__ void extend_boxes_kernel(const int* __restrict__ stats, const int* __restrict__ fallback,
+                                    const float* __restrict__ rnd, float rw, float rh, float img_w, float img_h,
+                                    float share, int G, int n_aug, int out_stride, int out_offset,
+                                    float4* __restrict__ out) {
+  const int b = blockIdx.y, g = blockIdx.z;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_aug) return;
+  const int* st = stats + ((size_t)b * G + g) * 5;
+  if (st[4] <= 0 && fallback) st = fallback + ((size_t)b * G + g) * 5;
+  // resize_boxes (tv transform.py): integer pixel box (+1 on the max side, mask_rcnn.py:626-632) times the fp32 ratios
+  const float x0 = __fmul_rn((float)st[0], rw), y0 = __fmul_rn((float)st[1], rh);
+  const float x1 = __fmul_rn((float)(st[2] + 1), rw), y1 = __fmul_rn((float)(st[3] + 1), rh);
+  const float bw = __fsub_rn(x1, x0), bh = __fsub_rn(y1, y0);
+  const float* r = rnd + ((size_t)b * G + g) * 4 * n_aug;
+  float4 o;
+  o.x = __fsub_rn(x0, __fmul_rn(__fmul_rn(r[j], bw), share));
+  o.y = __fsub_rn(y0, __fmul_rn(__fmul_rn(r[n_aug + j], bh), share));
+  o.z = __fadd_rn(x1, __fmul_rn(__fmul_rn(r[2 * n_aug + j], bw), share));
+  o.w = __fadd_rn(y1, __fmul_rn(__fmul_rn(r[3 * n_aug + j], bh), share));
+  o.x = fminf(fmaxf(o.x, 0.f), img_w);
+  o.y = fminf(fmaxf(o.y, 0.f), img_h);
+  o.z = fminf(fmaxf(o.z, 0.f), img_w);
+  o.w = fminf(fmaxf(o.w, 0.f), img_h);
+  out[(size_t)b * out_stride + out_offset + g * n_aug + j] = o;
+}
+
+struct DetArgs {
+  float wx, wy, ww, wh, clip;          // box coder weights (10, 10, 5, 5), bbox_xform_clip
+  float score_thresh, min_size;        // roi_heads.score_thresh, 1e-2
+  float img_w, img_h;                  // resized image size (clip)
+  float back_w, back_h;                // ratios back to the input frame (tv transform.py postprocess)
+};
+
+// One CTA per image: best-scoring valid (row, class) candidate.  head: fp32 [B * R][16] = class logits [ncls], then
+// box deltas [ncls][4].  Outputs per image: det_box [4] (input-frame coordinates), det_score, det_label (int64),
+// det_row (int32: row * (ncls - 1) + class - 1, -1 when nothing passed), det_roi [5] = (image, box in resized
+// coordinates) or (-1, 0, 0, 0, 0) -- the RoI of the mask branch --, chan [ncls - 1] (int32: index of the detection
+// that fills class channel c, -1 = none).
+__global__ void __launch_bounds__(1024)
+det_top1_kernel(const float* __restrict__ head, const float4* __restrict__ props, const DetArgs a, int R, int ncls,
+                float* __restrict__ det_box, float* __restrict__ det_score, long long* __restrict__ det_label,
+                int* __restrict__ det_row, float* __restrict__ det_roi, int* __restrict__ chan) {
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float best = -1.f;
+  int best_c = 0x7fffffff;
+  float4 best_box = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = tid; r < R; r += blockDim.x) {
+    const float* h = head + ((size_t)b * R + r) * 16;
+    float m = h[0];
+    for (int c = 1; c < ncls; ++c) m = fmaxf(m, h[c]);
+    float den = 0.f;
+    for (int c = 0; c < ncls; ++c) den += expf(h[c] - m);
+    const float4 p = props[(size_t)b * R + r];
+    const float w = __fsub_rn(p.z, p.x), hh = __fsub_rn(p.w, p.y);
+    const float cx = __fadd_rn(p.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(p.y, __fmul_rn(0.5f, hh));
+    for (int c = 1; c < ncls; ++c) {
+      const float score = expf(h[c] - m) / den;
+      if (!(score > a.score_thresh)) continue;
+      const float* d = h + ncls + c * 4;
+      const float dx = d[0] / a.wx, dy = d[1] / a.wy;
+      const float dw = fminf(d[2] / a.ww, a.clip), dh = fminf(d[3] / a.wh, a.clip);
+      const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, hh), cy);
+      const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), hh);
+      const float hw_ = __fmul_rn(0.5f, pw), hh_ = __fmul_rn(0.5f, ph);
+      float x1 = __fsub_rn(pcx, hw_), y1 = __fsub_rn(pcy, hh_), x2 = __fadd_rn(pcx, hw_), y2 = __fadd_rn(pcy, hh_);
+      x1 = fminf(fmaxf(x1, 0.f), a.img_w);
+      x2 = fminf(fmaxf(x2, 0.f), a.img_w);
+      y1 = fminf(fmaxf(y1, 0.f), a.img_h);
+      y2 = fminf(fmaxf(y2, 0.f), a.img_h);
+      if (!((x2 - x1) >= a.min_size && (y2 - y1) >= a.min_size)) continue;
+      const int cand = r * (ncls - 1) + (c - 1);
+      if (score > best || (score == best && cand < best_c)) {
+        best = score;
+        best_c = cand;
+        best_box = make_float4(x1, y1, x2, y2);
+      }
+    }
+  }
+  // block arg-max: larger score wins, ties by the smaller candidate index (stable descending sort order)
+  __shared__ float s_sc[32];
+  __shared__ int s_c[32];
+  __shared__ float4 s_b[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    float4 ob;
+    ob.x = __shfl_xor_sync(0xffffffffu, best_box.x, o);
+    ob.y = __shfl_xor_sync(0xffffffffu, best_box.y, o);
+    ob.z = __shfl_xor_sync(0xffffffffu, best_box.z, o);
+    ob.w = __shfl_xor_sync(0xffffffffu, best_box.w, o);
+    if (os > best || (os == best && oc < best_c)) {
+      best = os;
+      best_c = oc;
+      best_box = ob;
+    }
+  }
+  if (lane == 0) {
+    s_sc[warp] = best;
+    s_c[warp] = best_c;
+    s_b[warp] = best_box;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int w = 1; w < nw; ++w)
+      if (s_sc[w] > best || (s_sc[w] == best && s_c[w] < best_c)) {
+        best = s_sc[w];
+        best_c = s_c[w];
+        best_box = s_b[w];
+      }
+    const bool found = best >= 0.f;
+    const int cls = found ? best_c % (ncls - 1) + 1 : 0;
+    det_box[b * 4 + 0] = found ? __fmul_rn(best_box.x, a.back_w) : 0.f;
+    det_box[b * 4 + 1] = found ? __fmul_rn(best_box.y, a.back_h) : 0.f;
+    det_box[b * 4 + 2] = found ? __fmul_rn(best_box.z, a.back_w) : 0.f;
+    det_box[b * 4 + 3] = found ? __fmul_rn(best_box.w, a.back_h) : 0.f;
+    det_score[b] = found ? best : 0.f;
+    det_label[b] = cls;
+    det_row[b] = found ? best_c : -1;
+    det_roi[b * 5 + 0] = found ? (float)b : -1.f;
+    det_roi[b * 5 + 1] = found ? best_box.x : 0.f;
+    det_roi[b * 5 + 2] = found ? best_box.y : 0.f;
+    det_roi[b * 5 + 3] = found ? best_box.z : 0.f;
+    det_roi[b * 5 + 4] = found ? best_box.w : 0.f;
+    for (int c = 1; c < ncls; ++c) chan[b * (ncls - 1) + c - 1] = (found && c == cls) ? b : -1;
+  }
+}
+
+// tv roi_heads.py assign_targets_to_proposals for a padded proposal list.  Rows of image b: P proposal slots (the
+// first count[b] are real) followed by the image's ground-truth boxes (add_gt_proposals); gt_off [B + 1].
+// labels int64: class of the matched ground truth (IoU >= thr), 0 background, -1 padding;  matched int64: arg-max
+// ground truth (first maximum), clamped at 0;  counts int32 [B][2] = (#foreground, #background), caller-zeroed.
+__global__ void __launch_bounds__(256)
+roi_match_kernel(const float4* __restrict__ props, const int* __restrict__ count, const float4* __restrict__ gt_boxes,
+                 const long long* __restrict__ gt_labels, const int* __restrict__ gt_off, int P, int rows_per_image,
+                 float thr, float4* __restrict__ all_boxes, long long* __restrict__ labels,
+                 long long* __restrict__ matched, int* __restrict__ counts) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g0 = gt_off[b], G = gt_off[b + 1] - g0;
+  int fg = 0, bg = 0;
+  if (i < rows_per_image) {
+    const bool is_gt = i >= P;
+    const bool real = is_gt ? (i - P) < G : i < count[b];
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long lab = -1, mi = 0;
+    if (real) {
+      box = is_gt ? gt_boxes[g0 + i - P] : props[(size_t)b * P + i];
+      const float area = __fmul_rn(__fsub_rn(box.z, box.x), __fsub_rn(box.w, box.y));
+      float best = -1.f;
+      for (int g = 0; g < G; ++g) {
+        const float4 t = gt_boxes[g0 + g];
+        const float ta = __fmul_rn(__fsub_rn(t.z, t.x), __fsub_rn(t.w, t.y));
+        const float w = fmaxf(__fsub_rn(fminf(box.z, t.z), fmaxf(box.x, t.x)), 0.f);
+        const float h = fmaxf(__fsub_rn(fminf(box.w, t.w), fmaxf(box.y, t.y)), 0.f);
+        const float inter = __fmul_rn(w, h);
+        const float iou = inter / __fsub_rn(__fadd_rn(ta, area), inter);
+        if (iou > best) {
+          best = iou;
+          mi = g;
+        }
+      }
+      if (G == 0) {
+        lab = 0;
+      } else if (best >= thr) {
+        lab = gt_labels[g0 + mi];
+      } else {
+        lab = 0;
+      }
+      fg = lab >= 1;
+      bg = lab == 0;
+    }
+    const size_t o = (size_t)b * rows_per_image + i;
+    all_boxes[o] = box;
+    labels[o] = lab;
+    matched[o] = mi;
+  }
+  fg = __reduce_add_sync(0xffffffffu, fg);
+  bg = __reduce_add_sync(0xffffffffu, bg);
+  if ((threadIdx.x & 31) == 0) {
+    if (fg) atomicAdd(&counts[b * 2 + 0], fg);
+    if (bg) atomicAdd(&counts[b * 2 + 1], bg);
+  }
+}
+
+// Sampled RoIs -> (image, box) rows, labels, regression targets (tv _utils.py encode_boxes, weights wx..wh).
+// inds int64 [B][S]: row inside the image's candidate list (roi_match_kernel layout).
+__global__ void roi_encode_kernel(const float4* __restrict__ all_boxes, const long long* __restrict__ labels,
+                                  const long long* __restrict__ matched, const float4* __restrict__ gt_boxes,
+                                  const int* __restrict__ gt_off, const long long* __restrict__ inds, int S,
+                                  int rows_per_image, float wx, float wy, float ww, float wh, float* __restrict__ rois5,
+                                  long long* __restrict__ out_labels, long long* __restrict__ out_matched,
+                                  float4* __restrict__ reg) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= S) return;
+  const long long r = inds[(size_t)b * S + j];
+  const size_t src = (size_t)b * rows_per_image + r;
+  const float4 p = all_boxes[src];
+  const long long mi = matched[src];
+  const int G = gt_off[b + 1] - gt_off[b];
+  const float4 t = G > 0 ? gt_boxes[gt_off[b] + mi] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t o = (size_t)b * S + j;
+  rois5[o * 5 + 0] = (float)b;
+  rois5[o * 5 + 1] = p.x;
+  rois5[o * 5 + 2] = p.y;
+  rois5[o * 5 + 3] = p.z;
+  rois5[o * 5 + 4] = p.w;
+  out_labels[o] = labels[src];
+  out_matched[o] = mi;
+  const float ex_w = __fsub_rn(p.z, p.x), ex_h = __fsub_rn(p.w, p.y);
+  const float ex_cx = __fadd_rn(p.x, __fmul_rn(0.5f, ex_w)), ex_cy = __fadd_rn(p.y, __fmul_rn(0.5f, ex_h));
+  const float gt_w = __fsub_rn(t.z, t.x), gt_h = __fsub_rn(t.w, t.y);
+  const float gt_cx = __fadd_rn(t.x, __fmul_rn(0.5f, gt_w)), gt_cy = __fadd_rn(t.y, __fmul_rn(0.5f, gt_h));
+  float4 e;
+  e.x = __fmul_rn(wx, __fsub_rn(gt_cx, ex_cx)) / ex_w;
+  e.y = __fmul_rn(wy, __fsub_rn(gt_cy, ex_cy)) / ex_h;
+  e.z = __fmul_rn(ww, logf(gt_w / ex_w));
+  e.w = __fmul_rn(wh, logf(gt_h / ex_h));
+  reg[o] = e;
+}
+
+}  // namespace eosvos
+
+using namespace eosvos;
+
+static int fill_levels(RpnLevels& lv, const void* const* heads, const int* hw, int num_levels, int A, int pre_nms_top_n) {
+  if (num_levels < 1 || num_levels > RPN_MAX_LEVELS) return -1;
+  lv.num_levels = num_levels;
+  lv.A = A;
+  int aoff = 0, ooff = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    lv.head[l] = reinterpret_cast<const float*>(heads[l]);
+    lv.hw[l] = hw[l];
+    lv.anchor_off[l] = aoff;
+    lv.out_off[l] = ooff;
+    lv.k[l] = hw[l] * A < pre_nms_top_n ? hw[l] * A : pre_nms_top_n;
+    aoff += hw[l] * A;
+    ooff += lv.k[l];
+  }
+  lv.anchors_per_image = aoff;
+  lv.cand_per_image = ooff;
+  return 0;
+}
+
+extern "C" long long eosvos_rpn_scratch_bytes(int N, const int* hw, int num_levels, int A) {
+  long long anchors = 0;
+  for (int l = 0; l < num_levels; ++l) anchors += (long long)hw[l] * A;
+  const long long segs = (long long)N * num_levels;
+  // [zeroed by the caller: hist1, hist2, counters] [keys] [survivor lists]
+  return segs * (2 * RPN_BINS + 1) * 4 + N * anchors * 4 + segs * RPN_CAP * 8 + 64;
+}
+
+extern "C" long long eosvos_rpn_scratch_zero_bytes(int N, int num_levels) {
+  return (long long)N * num_levels * (2 * RPN_BINS + 1) * 4;
+}
+
+// Per-level top-k + decode + clip + validity of the RPN head outputs.  heads[l]: fp32 [N * hw[l]][16]; anchors: fp32
+// [sum hw*A][4] (one image's anchors, identical for every image of the batch); image_hw: host [N][2] (h, w) of the
+// resized images.  Candidate list per image: level after level, min(pre_nms_top_n, hw*A) slots each, sorted by
+// descending objectness.  scratch: eosvos_rpn_scratch_bytes(...) bytes whose first eosvos_rpn_scratch_zero_bytes(...)
+// bytes are zero.
+extern "C" int eosvos_rpn_select(const void* const* heads, const int* hw, int num_levels, int A, int N,
+                                 const float* anchors, const float* image_hw, int pre_nms_top_n, float bbox_clip,
+                                 float min_size, float score_thresh, void* scratch, float* boxes, float* scores,
+                                 unsigned char* valid, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RpnLevels lv;
+  EOSVOS_REQUIRE(fill_levels(lv, heads, hw, num_levels, A, pre_nms_top_n) == 0, "rpn_select: 1..8 pyramid levels");
+  EOSVOS_REQUIRE(N >= 1 && N <= 16, "rpn_select: 1..16 images per call");
+  EOSVOS_REQUIRE(pre_nms_top_n >= 1 && pre_nms_top_n <= 2048, "rpn_select: pre_nms_top_n must be in 1..2048");
+  EOSVOS_REQUIRE(anchors && image_hw && scratch && boxes && scores && valid, "rpn_select: null pointer");
+  const long long segs = (long long)N * num_levels;
+  unsigned* hist1 = reinterpret_cast<unsigned*>(scratch);
+  unsigned* hist2 = hist1 + segs * RPN_BINS;
+  unsigned* counters = hist2 + segs * RPN_BINS;
+  unsigned* keys = counters + segs;
+  size_t off = (size_t)(segs * (2 * RPN_BINS + 1) + (long long)N * lv.anchors_per_image) * 4;
+  off = (off + 15) / 16 * 16;
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + off);
+  int max_count = 0;
+  for (int l = 0; l < num_levels; ++l) max_count = hw[l] * A > max_count ? hw[l] * A : max_count;
+  dim3 grid((max_count + RPN_CHUNK - 1) / RPN_CHUNK, num_levels, N);
+  rpn_keys_kernel<<<grid, 256, 0, stream>>>(lv, keys, hist1);
+  EOSVOS_TRY(check_launch("rpn_keys_kernel"));
+  rpn_hist2_kernel<<<grid, 256, 0, stream>>>(lv, keys, hist1, hist2);
+  EOSVOS_TRY(check_launch("rpn_hist2_kernel"));
+  rpn_compact_kernel<<<grid, 256, 0, stream>>>(lv, keys, hist1, hist2, counters, list);
+  EOSVOS_TRY(check_launch("rpn_compact_kernel"));
+  RpnDecodeArgs da;
+  for (int n = 0; n < N; ++n) {
+    da.img_h[n] = image_hw[2 * n];
+    da.img_w[n] = image_hw[2 * n + 1];
+  }
+  da.clip = bbox_clip;
+  da.min_size = min_size;
+  da.score_thresh = score_thresh;
+  rpn_sort_decode_kernel<<<dim3(num_levels, N), 1024, 0, stream>>>(lv, da, counters, list,
+                                                                  reinterpret_cast<const float4*>(anchors),
+                                                                  reinterpret_cast<float4*>(boxes), scores, valid);
+  return check_launch("rpn_sort_decode_kernel");
+}
+
+// Post-NMS selection: the first post_n kept candidates of every image in descending score order, written to
+// out_boxes[n * out_stride + out_offset + rank] (padding rows zeroed), out_count[n] = number of real rows.
+extern "C" int eosvos_rpn_postnms(const int* hw, int num_levels, int A, int N, int pre_nms_top_n, const float* boxes,
+                                  const float* scores, const unsigned char* valid, const unsigned char* keep,
+                                  int post_n, int out_stride, int out_offset, float* out_boxes, float* out_scores,
+                                  int* out_count, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RpnLevels lv;
+  const void* none[RPN_MAX_LEVELS] = {};
+  EOSVOS_REQUIRE(fill_levels(lv, none, hw, num_levels, A, pre_nms_top_n) == 0, "rpn_postnms: 1..8 pyramid levels");
+  EOSVOS_REQUIRE(boxes && scores && valid && keep && out_boxes && out_count, "rpn_postnms: null pointer");
+  EOSVOS_REQUIRE(out_offset >= 0 && out_offset + post_n <= out_stride, "rpn_postnms: output window out of range");
+  const size_t smem = (size_t)lv.cand_per_image * 4 + (size_t)(lv.cand_per_image + num_levels) * 4;
+  EOSVOS_REQUIRE(smem <= 200 * 1024, "rpn_postnms: too many candidates per image for shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(rpn_postnms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  rpn_postnms_kernel<<<N, 1024, smem, stream>>>(lv, reinterpret_cast<const float4*>(boxes), scores, valid, keep, post_n,
+                                                out_stride, out_offset, reinterpret_cast<float4*>(out_boxes),
+                                                out_scores, out_count);
+  return check_launch("rpn_postnms_kernel");
+}
+
+extern "C" int eosvos_extend_boxes(const int* stats, const int* fallback_stats, const float* rnd, int B, int G,
+                                   int n_aug, float ratio_w, float ratio_h, float img_w, float img_h, float share,
+                                   int out_stride, int out_offset, float* out_boxes, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(stats && rnd && out_boxes, "extend_boxes: null pointer");
+  EOSVOS_REQUIRE(out_offset >= 0 && out_offset + G * n_aug <= out_stride, "extend_boxes: output window out of range");
+  dim3 grid((n_aug + 255) / 256, B, G);
+  extend_boxes_kernel<<<grid, 256, 0, stream>>>(stats, fallback_stats, rnd, ratio_w, ratio_h, img_w, img_h, share, G,
+                                                n_aug, out_stride, out_offset, reinterpret_cast<float4*>(out_boxes));
+  return check_launch("extend_boxes_kernel");
+}
+
+extern "C" int eosvos_det_top1(const float* head, const float* proposals, int B, int R, int num_classes,
+                               const float* coder_weights4, float bbox_clip, float score_thresh, float min_size,
+                               float img_w, float img_h, float back_w, float back_h, float* det_box, float* det_score,
+                               long long* det_label, int* det_row, float* det_roi, int* chan, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(head && proposals && det_box && det_score && det_label && det_row && det_roi && chan,
+                 "det_top1: null pointer");
+  EOSVOS_REQUIRE(num_classes >= 2 && num_classes * 5 <= 16, "det_top1: the fused head row holds at most 3 classes");
+  DetArgs a;
+  a.wx = coder_weights4[0];
+  a.wy = coder_weights4[1];
+  a.ww = coder_weights4[2];
+  a.wh = coder_weights4[3];
+  a.clip = bbox_clip;
+  a.score_thresh = score_thresh;
+  a.min_size = min_size;
+  a.img_w = img_w;
+  a.img_h = img_h;
+  a.back_w = back_w;
+  a.back_h = back_h;
+  det_top1_kernel<<<B, 1024, 0, stream>>>(head, reinterpret_cast<const float4*>(proposals), a, R, num_classes, det_box,
+                                          det_score, det_label, det_row, det_roi, chan);
+  return check_launch("det_top1_kernel");
+}
+
+extern "C" int eosvos_roi_match(const float* proposals, const int* count, const float* gt_boxes,
+                                const long long* gt_labels, const int* gt_off, int B, int P, int max_gt, float iou_thresh,
+                                float* all_boxes, long long* labels, long long* matched, int* counts,
+                                eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(proposals && count && gt_boxes && gt_labels && gt_off && all_boxes && labels && matched && counts,
+                 "roi_match: null pointer");
+  const int rows = P + max_gt;
+  dim3 grid((rows + 255) / 256, B);
+  roi_match_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(proposals), count,
+                                             reinterpret_cast<const float4*>(gt_boxes), gt_labels, gt_off, P, rows,
+                                             iou_thresh, reinterpret_cast<float4*>(all_boxes), labels, matched, counts);
+  return check_launch("roi_match_kernel");
+}
+
+extern "C" int eosvos_roi_encode(const float* all_boxes, const long long* labels, const long long* matched,
+                                 const float* gt_boxes, const int* gt_off, const long long* inds, int B, int S,
+                                 int rows_per_image, const float* coder_weights4, float* rois5, long long* out_labels,
+                                 long long* out_matched, float* reg_targets, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(all_boxes && labels && matched && gt_boxes && gt_off && inds && rois5 && out_labels && out_matched &&
+                     reg_targets,
+                 "roi_encode: null pointer");
+  dim3 grid((S + 255) / 256, B);
+  roi_encode_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(all_boxes), labels, matched,
+                                              reinterpret_cast<const float4*>(gt_boxes), gt_off, inds, S, rows_per_image,
+                                              coder_weights4[0], coder_weights4[1], coder_weights4[2], coder_weights4[3],
+                                              rois5, out_labels, out_matched, reinterpret_cast<float4*>(reg_targets));
+  return check_launch("roi_encode_kernel");
+}

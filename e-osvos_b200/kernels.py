@@ -113,6 +113,16 @@ class TargetStatsCache:
         del self.entries[id(t)]
         return None
 
+    def get_host(self, t):
+        hit = self.get(t)
+        return hit if hit is not None and not hit[0].is_cuda else None
+
+    def get_device(self, t):
+        """(stats int32 [B,K,5] ON THE DEVICE, fallback stats or None): the sync-free inference path -- the boxes of
+        the propagated target never visit the host (put with a CUDA `stats` tensor; `ign` carries the fallback)."""
+        hit = self.get(t)
+        return hit if hit is not None and hit[0].is_cuda else None
+
 
 target_stats = TargetStatsCache()
 
@@ -455,6 +465,113 @@ def nms_segments(boxes_sorted, seg_offsets, num_segments, max_seg, thresh):
     call("eosvos_nms_segments", _ptr(boxes_sorted), _ptr(seg_offsets), num_segments, max_seg, float(thresh),
          _ptr(scratch), _ptr(keep), _stream())
     return keep
+
+
+# ------------------------------------------------------------------------------------------- K5/K6 (rpn.cu)
+def _int_array(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def rpn_select(head_outs, hw, A, N, anchors, image_sizes, pre_nms_top_n, bbox_clip, min_size, score_thresh):
+    """Per-(image, level) top-k of the objectness logits + decoding of the selected anchors only.
+    head_outs: per level fp32 [N*hw_l, 16]; anchors fp32 [sum hw_l*A, 4]; image_sizes [(h, w)] * N.
+    -> (boxes [N,C,4] (invalid ones zeroed), scores [N,C] (sigmoid), valid uint8 [N,C], per-level k list)."""
+    L = len(head_outs)
+    dev = head_outs[0].device
+    for h in head_outs:
+        _chk(h, torch.float32, "rpn head output")
+    _chk(anchors, torch.float32, "anchors")
+    ks = [min(pre_nms_top_n, n * A) for n in hw]
+    C = sum(ks)
+    hw_c = _int_array(hw)
+    lib = _lib.load()
+    nbytes = lib.eosvos_rpn_scratch_bytes(N, hw_c, L, A)
+    zbytes = lib.eosvos_rpn_scratch_zero_bytes(N, L)
+    scratch = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+    scratch[:zbytes].zero_()
+    boxes = torch.empty((N, C, 4), device=dev, dtype=torch.float32)
+    scores = torch.empty((N, C), device=dev, dtype=torch.float32)
+    valid = torch.empty((N, C), device=dev, dtype=torch.uint8)
+    ptrs = (ctypes.c_void_p * L)(*[h.data_ptr() for h in head_outs])
+    sizes = (ctypes.c_float * (2 * N))(*[float(v) for s in image_sizes for v in s])
+    call("eosvos_rpn_select", ptrs, hw_c, L, A, N, _ptr(anchors), sizes, int(pre_nms_top_n), float(bbox_clip),
+         float(min_size), float(score_thresh), _ptr(scratch), _ptr(boxes), _ptr(scores), _ptr(valid), _stream())
+    return boxes, scores, valid, ks
+
+
+def rpn_postnms(hw, A, N, pre_nms_top_n, boxes, scores, valid, keep, post_n, out_boxes=None, out_offset=0,
+                want_scores=False):
+    """First post_n NMS survivors of every image in descending score order -> rows [out_offset, out_offset+post_n) of
+    out_boxes [N, stride, 4] (padding rows zero), count int32 [N]."""
+    dev = boxes.device
+    if out_boxes is None:
+        out_boxes = torch.empty((N, post_n, 4), device=dev, dtype=torch.float32)
+    stride = out_boxes.shape[1]
+    out_scores = torch.empty((N, stride), device=dev, dtype=torch.float32) if want_scores else None
+    count = torch.empty((N,), device=dev, dtype=torch.int32)
+    call("eosvos_rpn_postnms", _int_array(hw), len(hw), A, N, int(pre_nms_top_n), _ptr(boxes), _ptr(scores), _ptr(valid),
+         _ptr(_chk(keep, torch.uint8, "keep")), int(post_n), int(stride), int(out_offset), _ptr(out_boxes),
+         _ptr(out_scores), _ptr(count), _stream())
+    return out_boxes, out_scores, count
+
+
+def extend_boxes(stats, fallback, rnd, n_aug, ratio_w, ratio_h, img_w, img_h, share, out_boxes, out_offset):
+    """Jittered copies of the target boxes (stats int32 [B,G,5], input-frame pixels) into out_boxes [B, stride, 4]
+    at rows [out_offset, out_offset + G*n_aug); rnd fp32 [B,G,4,n_aug] (host-drawn uniforms, already on the device)."""
+    _chk(stats, torch.int32, "stats")
+    _chk(rnd, torch.float32, "rnd")
+    B, G = stats.shape[0], stats.shape[1]
+    call("eosvos_extend_boxes", _ptr(stats), _ptr(fallback), _ptr(rnd), B, G, int(n_aug), float(ratio_w), float(ratio_h),
+         float(img_w), float(img_h), float(share), int(out_boxes.shape[1]), int(out_offset), _ptr(out_boxes), _stream())
+    return out_boxes
+
+
+def det_top1(head, proposals, B, R, num_classes, weights, bbox_clip, score_thresh, min_size, img_w, img_h, back_w, back_h):
+    """Best valid (row, class) candidate per image from the fused box head output [B*R, 16] and proposals [B*R, 4].
+    -> dict(box [B,4] input-frame coords, score [B], label int64 [B], row int32 [B] (-1 = none), roi [B,5], chan
+    int32 [B*(ncls-1)])."""
+    dev = head.device
+    _chk(head, torch.float32, "box head output")
+    _chk(proposals, torch.float32, "proposals")
+    out = dict(box=torch.empty((B, 4), device=dev), score=torch.empty((B,), device=dev),
+               label=torch.empty((B,), device=dev, dtype=torch.int64), row=torch.empty((B,), device=dev, dtype=torch.int32),
+               roi=torch.empty((B, 5), device=dev), chan=torch.empty((B * (num_classes - 1),), device=dev, dtype=torch.int32))
+    w = (ctypes.c_float * 4)(*[float(v) for v in weights])
+    call("eosvos_det_top1", _ptr(head), _ptr(proposals), B, R, num_classes, w, float(bbox_clip), float(score_thresh),
+         float(min_size), float(img_w), float(img_h), float(back_w), float(back_h), _ptr(out["box"]), _ptr(out["score"]),
+         _ptr(out["label"]), _ptr(out["row"]), _ptr(out["roi"]), _ptr(out["chan"]), _stream())
+    return out
+
+
+def roi_match(proposals, count, gt_boxes, gt_labels, gt_off, max_gt, iou_thresh):
+    """proposals [B,P,4] (first count[b] real) + the image's ground-truth boxes appended at rows P.. ->
+    (all_boxes [B,P+max_gt,4], labels int64 (class / 0 background / -1 padding), matched int64, counts int32 [B,2])."""
+    dev = proposals.device
+    B, P = proposals.shape[0], proposals.shape[1]
+    rows = P + max_gt
+    all_boxes = torch.empty((B, rows, 4), device=dev, dtype=torch.float32)
+    labels = torch.empty((B, rows), device=dev, dtype=torch.int64)
+    matched = torch.empty((B, rows), device=dev, dtype=torch.int64)
+    counts = torch.zeros((B, 2), device=dev, dtype=torch.int32)
+    call("eosvos_roi_match", _ptr(_chk(proposals, torch.float32)), _ptr(_chk(count, torch.int32)),
+         _ptr(_chk(gt_boxes, torch.float32)), _ptr(_chk(gt_labels, torch.int64)), _ptr(_chk(gt_off, torch.int32)), B, P,
+         int(max_gt), float(iou_thresh), _ptr(all_boxes), _ptr(labels), _ptr(matched), _ptr(counts), _stream())
+    return all_boxes, labels, matched, counts
+
+
+def roi_encode(all_boxes, labels, matched, gt_boxes, gt_off, inds, weights):
+    """Sampled rows inds int64 [B,S] -> (rois5 [B*S,5], labels [B*S], matched [B*S], regression targets [B*S,4])."""
+    dev = all_boxes.device
+    B, S = inds.shape
+    rois5 = torch.empty((B * S, 5), device=dev, dtype=torch.float32)
+    out_l = torch.empty((B * S,), device=dev, dtype=torch.int64)
+    out_m = torch.empty((B * S,), device=dev, dtype=torch.int64)
+    reg = torch.empty((B * S, 4), device=dev, dtype=torch.float32)
+    w = (ctypes.c_float * 4)(*[float(v) for v in weights])
+    call("eosvos_roi_encode", _ptr(all_boxes), _ptr(labels), _ptr(matched), _ptr(gt_boxes), _ptr(gt_off),
+         _ptr(_chk(inds, torch.int64, "inds")), B, S, int(all_boxes.shape[1]), w, _ptr(rois5), _ptr(out_l), _ptr(out_m),
+         _ptr(reg), _stream())
+    return rois5, out_l, out_m, reg
 
 
 # ------------------------------------------------------------------------------------------- K9

@@ -166,7 +166,7 @@ class MaskRCNN(_MaskRCNN):
         B = targets.shape[0]
         Kc = max(self.num_classes - 1, 1)
         t32 = targets.to(torch.float32).contiguous()
-        pre = K.target_stats.get(targets) if not flip_label else None
+        pre = K.target_stats.get_host(targets) if not flip_label else None
         if pre is not None and tuple(pre[0].shape) == (B, Kc, 5):
             # fast path: the producer of `targets` already knows the per-id boxes / counts on the HOST (the
             # augmentation thread, or the previous frame's fused tail kernel via run_frames) -> no kernel, no sync
@@ -468,7 +468,7 @@ class MaskRCNN(_MaskRCNN):
             # never continue in a zero block it touched
             K.zero_pool.reset()
             ent = (graphed, per_call, plan, vals)
-            if len(self._graphs) >= 12:         # bounded: graphs pin their activation pools
+            if len(self._graphs) >= 16:         # bounded: graphs pin their activation pools
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = ent
         from .. import _lib
@@ -543,49 +543,127 @@ class MaskRCNN(_MaskRCNN):
                                         [head.cls_logits.bias, head.bbox_pred.bias]))
         return outs
 
-    def _rpn(self, feats, image_shape, image_sizes, targets, head_outs=None):
+    def _rpn_early_targets(self, feats, image_shape, image_sizes, targets):
+        """Anchor labelling + sampling (tv rpn.py assign_targets_to_anchors, box_coder.encode, fg_bg_sampler) depend only
+        on the anchors and the ground truth, not on the network: run them on a side stream now, so their host syncs
+        (nonzero) do not wait for the trunk that is still executing on the main stream.  RNG order is unchanged (RPN
+        sampler before RoI sampler)."""
         rpn = self.rpn
-        head = rpn.head
+        fs = [(f.shape[1], f.shape[2]) for f in feats]
+        anchors = self._anchors(image_shape, image_sizes, fs, feats[0].device)
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=feats[0].device)
+        with torch.cuda.stream(self._side_stream):
+            # the ground-truth boxes are uploaded again on THIS stream (from their host copy), so nothing here
+            # is ordered behind the main stream's queue
+            side_targets = [{"boxes": K.stager.put(t["boxes_cpu"], feats[0].device)} for t in targets]
+            labels, matched_gt_boxes = rpn.assign_targets_to_anchors(anchors, side_targets)
+            regression_targets = rpn.box_coder.encode(matched_gt_boxes, anchors)
+            pos, neg = rpn.fg_bg_sampler(labels)
+            pos = torch.where(torch.cat(pos, dim=0))[0]
+            neg = torch.where(torch.cat(neg, dim=0))[0]
+            early = (torch.cat(labels, dim=0), torch.cat(regression_targets, dim=0), pos, neg)
+            done = torch.cuda.Event()
+            done.record(self._side_stream)
+        for t in early:
+            t.record_stream(main)
+        return early + (done,)
+
+    def _rpn_cat_outputs(self, feats, head_outs):
+        head = self.rpn.head
         N = feats[0].shape[0]
-        early = None
-        if self.training:
-            # Anchor labelling + sampling depend only on the anchors and the ground truth, not on the network: run
-            # them on a side stream now, so their host syncs (nonzero) do not wait for the trunk that is still
-            # executing on the main stream.  RNG order is unchanged (RPN sampler before RoI sampler).
-            fs = [(f.shape[1], f.shape[2]) for f in feats]
-            anchors = self._anchors(image_shape, image_sizes, fs, feats[0].device)
-            main = torch.cuda.current_stream()
-            if self._side_stream is None:
-                self._side_stream = torch.cuda.Stream(device=feats[0].device)
-            with torch.cuda.stream(self._side_stream):
-                # the ground-truth boxes are uploaded again on THIS stream (from their host copy), so nothing here
-                # is ordered behind the main stream's queue
-                side_targets = [{"boxes": K.stager.put(t["boxes_cpu"], feats[0].device)} for t in targets]
-                labels, matched_gt_boxes = rpn.assign_targets_to_anchors(anchors, side_targets)
-                regression_targets = rpn.box_coder.encode(matched_gt_boxes, anchors)
-                pos, neg = rpn.fg_bg_sampler(labels)
-                pos = torch.where(torch.cat(pos, dim=0))[0]
-                neg = torch.where(torch.cat(neg, dim=0))[0]
-                early = (torch.cat(labels, dim=0), torch.cat(regression_targets, dim=0), pos, neg)
-                done = torch.cuda.Event()
-                done.record(self._side_stream)
-            for t in early:
-                t.record_stream(main)
-            early = early + (done,)
+        A = head.cls_logits.weight.shape[0]
         obj, dlt, feat_shapes = [], [], []
-        if head_outs is None:
-            head_outs = self._rpn_head(feats)
-        elif head_outs[0].dtype != torch.float32:          # debug split: only the shared conv ran inside the graph
-            head_outs = self._rpn_head(head_outs, stage=2)
         for f, o in zip(feats, head_outs):
             _, H, W, C = f.shape
-            A = head.cls_logits.weight.shape[0]
             obj.append(o[:, :A].reshape(N, H * W * A, 1))
             dlt.append(o[:, A:A + 4 * A].reshape(N, H * W * A, 4))
             feat_shapes.append((H, W))
         num_anchors_per_level = [o.shape[1] for o in obj]
         objectness = torch.cat(obj, dim=1).flatten(0, -2)
         pred_bbox_deltas = torch.cat(dlt, dim=1).flatten(0, -2)
+        return objectness, pred_bbox_deltas, feat_shapes, num_anchors_per_level
+
+    @staticmethod
+    def _rpn_losses(early, objectness, pred_bbox_deltas):
+        """tv rpn.py compute_loss with the indices sampled on the side stream."""
+        labels_c, reg_c, pos, neg, done = early
+        torch.cuda.current_stream().wait_event(done)
+        sampled = torch.cat([pos, neg], dim=0)
+        loss_rpn_box_reg = F.smooth_l1_loss(pred_bbox_deltas[pos], reg_c[pos], beta=1 / 9,
+                                            reduction="sum") / (sampled.numel())
+        loss_objectness = F.binary_cross_entropy_with_logits(objectness.flatten()[sampled], labels_c[sampled])
+        return {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
+
+    def _segment_offsets(self, N, sizes, device):
+        key = (N, tuple(sizes), str(device))
+        if getattr(self, "_seg_cache_key", None) != key:
+            offs = [0]
+            for _ in range(N):
+                for k in sizes:
+                    offs.append(offs[-1] + k)
+            self._seg_cache = torch.tensor(offs, dtype=torch.int32, device=device)
+            self._seg_cache_key = key
+        return self._seg_cache
+
+    def _rpn_fast(self, feats, image_shape, image_sizes, head_outs, post_n, out=None, out_offset=0):
+        """tv rpn.py filter_proposals on statically shaped buffers (csrc/rpn.cu): per-level top-k + decode of the
+        selected anchors only, segmented NMS, post-NMS top-n -> (boxes [N, stride, 4] with the first count[n] of the
+        post_n slots at out_offset real and the rest zero, count int32 [N] on the device).  No host synchronisation."""
+        rpn = self.rpn
+        N = feats[0].shape[0]
+        device = feats[0].device
+        A = rpn.head.cls_logits.weight.shape[0]
+        feat_shapes = [(f.shape[1], f.shape[2]) for f in feats]
+        hw = [h * w for h, w in feat_shapes]
+        anchors = self._anchors(image_shape, image_sizes, feat_shapes, device)[0]
+        pre = rpn.pre_nms_top_n()
+        boxes_c, scores_c, valid_c, ks = K.rpn_select([o.detach() for o in head_outs], hw, A, N, anchors, image_sizes, pre,
+                                                      rpn.box_coder.bbox_xform_clip, rpn.min_size, rpn.score_thresh)
+        seg = self._segment_offsets(N, ks, device)
+        keep = K.nms_segments(boxes_c.view(-1, 4), seg, N * len(ks), max(ks), rpn.nms_thresh)
+        boxes, _, count = K.rpn_postnms(hw, A, N, pre, boxes_c, scores_c, valid_c, keep, post_n, out, out_offset)
+        return boxes, count
+
+    def _extend_rands(self, B, G, n_aug, device):
+        """The CPU uniform numbers of reference mask_rcnn.py:270-273, drawn call by call in the reference's order
+        (x_min, y_min, x_max, y_max per target box) into pinned memory, uploaded asynchronously."""
+        ring = getattr(self, "_rand_ring", None)
+        if ring is None or ring[0].shape != (B, G, 4, n_aug):
+            ring = [torch.empty((B, G, 4, n_aug), dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._rand_ring, self._rand_events, self._rand_i = ring, [None] * 4, 0
+        j = self._rand_i % 4
+        self._rand_i += 1
+        if self._rand_events[j] is not None:
+            self._rand_events[j].synchronize()
+        buf = ring[j]
+        for b in range(B):
+            for g in range(G):
+                for c in range(4):
+                    torch.rand((n_aug,), out=buf[b, g, c])
+        dev = buf.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._rand_events[j] = ev
+        return dev
+
+    def _proposal_list(self, padded, count, n_front):
+        """padded proposals -> the reference's per-image lists (host sync; checkers and the general path only)."""
+        cnt = count.tolist()
+        return [torch.cat([padded[i, :min(c, n_front)], padded[i, n_front:]], dim=0) for i, c in enumerate(cnt)]
+
+    def _rpn(self, feats, image_shape, image_sizes, targets, head_outs=None):
+        rpn = self.rpn
+        N = feats[0].shape[0]
+        early = None
+        if self.training:
+            early = self._rpn_early_targets(feats, image_shape, image_sizes, targets)
+        if head_outs is None:
+            head_outs = self._rpn_head(feats)
+        elif head_outs[0].dtype != torch.float32:          # debug split: only the shared conv ran inside the graph
+            head_outs = self._rpn_head(head_outs, stage=2)
+        objectness, pred_bbox_deltas, feat_shapes, num_anchors_per_level = self._rpn_cat_outputs(feats, head_outs)
         if self.capture is not None:
             self.capture.update(objectness=objectness.detach(), deltas=pred_bbox_deltas.detach())
         anchors = self._anchors(image_shape, image_sizes, feat_shapes, feats[0].device)
@@ -621,14 +699,7 @@ class MaskRCNN(_MaskRCNN):
 
         losses = {}
         if self.training:
-            # tv rpn.py compute_loss with the indices sampled above
-            labels_c, reg_c, pos, neg, done = early
-            torch.cuda.current_stream().wait_event(done)
-            sampled = torch.cat([pos, neg], dim=0)
-            loss_rpn_box_reg = F.smooth_l1_loss(pred_bbox_deltas[pos], reg_c[pos], beta=1 / 9,
-                                                reduction="sum") / (sampled.numel())
-            loss_objectness = F.binary_cross_entropy_with_logits(objectness.flatten()[sampled], labels_c[sampled])
-            losses = {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
+            losses = self._rpn_losses(early, objectness, pred_bbox_deltas)
         return boxes, losses
 
     @staticmethod
@@ -675,14 +746,7 @@ class MaskRCNN(_MaskRCNN):
         prob = torch.sigmoid(objectness[batch_idx, top_n_idx])
         props = proposals[batch_idx, top_n_idx]
         Ktot = top_n_idx.shape[1]
-        key = (N, tuple(sizes), str(device))
-        if getattr(self, "_seg_cache_key", None) != key:
-            offs = [0]
-            for _ in range(N):
-                for k in sizes:
-                    offs.append(offs[-1] + k)
-            self._seg_cache = torch.tensor(offs, dtype=torch.int32, device=device)
-            self._seg_cache_key = key
+        seg_offsets = self._segment_offsets(N, sizes, device)
         hw = K.stager.put(torch.tensor([[s[0], s[1]] for s in image_sizes], dtype=props.dtype), device)
         hmax, wmax = hw[:, 0:1], hw[:, 1:2]
         x1 = torch.minimum(props[..., 0].clamp(min=0), wmax)
@@ -692,7 +756,7 @@ class MaskRCNN(_MaskRCNN):
         valid = ((x2 - x1) >= rpn.min_size) & ((y2 - y1) >= rpn.min_size) & (prob >= rpn.score_thresh)
         clipped = torch.stack([x1, y1, x2, y2], dim=-1)
         nms_in = (clipped * valid[..., None]).reshape(N * Ktot, 4).contiguous()
-        flags = K.nms_segments(nms_in, self._seg_cache, N * len(sizes), max(sizes), rpn.nms_thresh)
+        flags = K.nms_segments(nms_in, seg_offsets, N * len(sizes), max(sizes), rpn.nms_thresh)
         flags = flags.view(N, Ktot).bool() & valid
         ranked = torch.where(flags, prob, torch.full_like(prob, -1.0))
         order = ranked.argsort(dim=1, descending=True, stable=True)
@@ -737,7 +801,7 @@ class MaskRCNN(_MaskRCNN):
         pred_scores = F.softmax(class_logits, -1)
         pred_boxes = pred_boxes.split(boxes_per_image, 0)
         pred_scores = pred_scores.split(boxes_per_image, 0)
-        all_boxes, all_scores, all_labels = [], [], []
+        all_boxes, all_scores, all_labels, all_rows = [], [], [], []
         for boxes, scores, image_shape in zip(pred_boxes, pred_scores, image_shapes):
             boxes = box_ops.clip_boxes_to_image(boxes, image_shape)
             labels = torch.arange(num_classes, device=device).view(1, -1).expand_as(scores)
@@ -746,12 +810,16 @@ class MaskRCNN(_MaskRCNN):
             inds = torch.nonzero(scores > rh.score_thresh).squeeze(1)
             boxes, scores, labels = boxes[inds], scores[inds], labels[inds]
             keep = box_ops.remove_small_boxes(boxes, min_size=1e-2)
-            boxes, scores, labels = boxes[keep], scores[keep], labels[keep]
+            boxes, scores, labels, inds = boxes[keep], scores[keep], labels[keep], inds[keep]
             keep = self._nms_by_label(boxes, scores, labels, rh.nms_thresh)
             keep = keep[:rh.detections_per_img]
             all_boxes.append(boxes[keep])
             all_scores.append(scores[keep])
             all_labels.append(labels[keep])
+            all_rows.append(inds[keep])
+        # row (proposal index * (num_classes - 1) + class - 1) every kept detection came from: lets a checker tell
+        # "another box" from "the same box, numerically different"
+        self.last_detection_rows = all_rows
         return all_boxes, all_scores, all_labels
 
     def _mask_branch(self, feats, mask_proposals):
@@ -918,6 +986,298 @@ class MaskRCNN(_MaskRCNN):
                                   list(feats[:4]) + [rois5.contiguous(), lab.contiguous(), gt_masks, tro.contiguous(), w],
                                   self._mask_slots, kinds, True, alias_inputs=4)
 
+    # ---- statically shaped fast paths (csrc/rpn.cu) -----------------------------------------------
+    def _fast_ok(self):
+        w = self.rpn.box_coder.weights
+        return (os.environ.get("EOSVOS_FAST_PATH", "1") != "0" and self.capture is None and self.fixed_proposals is None
+                and self.fixed_detections is None and tuple(float(x) for x in w) == (1.0, 1.0, 1.0, 1.0))
+
+    def _sample_rois_fast(self, padded, count, targets):
+        """tv roi_heads.py:642-678 (select_training_samples: add_gt_proposals, assign_targets_to_proposals,
+        BalancedPositiveNegativeSampler, box_coder.encode) on the padded proposal buffer: one matching kernel, ONE
+        host synchronisation (the foreground / background counts the sampler's `torch.randperm(n)` calls need -- same
+        calls, same order as the reference), one gather / encode kernel.
+        -> dict(rois5 [R,5], labels [R], matched [R], reg [R,4], sizes [per image], pos_in [per image])."""
+        rh = self.roi_heads
+        device = padded.device
+        B, P = padded.shape[0], padded.shape[1]
+        gt_boxes = [t["boxes"].to(torch.float32) for t in targets]
+        gt_labels = [t["labels"] for t in targets]
+        Gs = [g.shape[0] for g in gt_boxes]
+        gt_cat = torch.cat(gt_boxes, 0).contiguous()
+        gl_cat = torch.cat(gt_labels, 0).contiguous()
+        offs = [0]
+        for g in Gs:
+            offs.append(offs[-1] + g)
+        gt_off = K.stager.put(torch.tensor(offs, dtype=torch.int32), device)
+        m = rh.proposal_matcher
+        if m.high_threshold != m.low_threshold or m.allow_low_quality_matches:
+            raise NotImplementedError("RoI matcher with a between-threshold band")
+        all_boxes, labels, matched, counts2 = K.roi_match(padded, count, gt_cat, gl_cat, gt_off, max(Gs), m.high_threshold)
+        cnt = counts2.tolist()                                   # the one host sync on the main stream
+        sampler = rh.fg_bg_sampler
+        S = sampler.batch_size_per_image
+        inds = []
+        num_pos_list = []
+        for i, (npos, nneg) in enumerate(cnt):
+            l = labels[i]
+            positive = torch.nonzero_static(l >= 1, size=npos).squeeze(1)
+            negative = torch.nonzero_static(l == 0, size=nneg).squeeze(1)
+            num_pos = min(npos, int(S * sampler.positive_fraction))
+            num_neg = min(nneg, S - num_pos)
+            perm1 = torch.randperm(npos, device=device)[:num_pos]
+            perm2 = torch.randperm(nneg, device=device)[:num_neg]
+            mask = torch.zeros_like(l, dtype=torch.bool)
+            mask[positive[perm1]] = True
+            mask[negative[perm2]] = True
+            inds.append(torch.nonzero_static(mask, size=num_pos + num_neg).squeeze(1))
+            num_pos_list.append(num_pos)
+        sizes = [int(x.shape[0]) for x in inds]
+        wts = rh.box_coder.weights
+        if all(sz == sizes[0] for sz in sizes):
+            rois5, lab_c, m_c, reg_c = K.roi_encode(all_boxes, labels, matched, gt_cat, gt_off, torch.stack(inds).contiguous(), wts)
+        else:
+            parts = []
+            for i, ind in enumerate(inds):
+                r5, lc, mc, rc = K.roi_encode(all_boxes[i:i + 1], labels[i:i + 1], matched[i:i + 1], gt_cat, gt_off[i:i + 2],
+                                              ind[None].contiguous(), wts)
+                r5[:, 0] = i
+                parts.append((r5, lc, mc, rc))
+            rois5, lab_c, m_c, reg_c = [torch.cat(x, 0) for x in zip(*parts)]
+        pos_in, off = [], 0
+        for sz, npos in zip(sizes, num_pos_list):
+            pos_in.append(torch.nonzero_static(lab_c[off:off + sz] > 0, size=npos).squeeze(1) + off)
+            off += sz
+        return dict(rois5=rois5, labels=lab_c, matched=m_c, reg=reg_c, sizes=sizes, pos_in=pos_in)
+
+    def _roi_heads_train_fast(self, feats, padded, count, targets):
+        rh = self.roi_heads
+        smp = self._sample_rois_fast(padded, count, targets)
+        rois5, lab_c, reg_c = smp["rois5"], smp["labels"], smp["reg"]
+        S = rh.fg_bg_sampler.batch_size_per_image
+        graphed_box = (self.use_cuda_graphs and torch.is_grad_enabled() and os.environ.get("EOSVOS_GRAPH_BOX", "1") != "0"
+                       and all(sz == S for sz in smp["sizes"]))
+        if graphed_box:
+            loss_classifier, loss_box_reg = self._box_loss_graphed(feats, rois5, lab_c, reg_c)
+        else:
+            o = self._box_branch(feats[:4], rois5)
+            nc = rh.box_predictor.cls_score.weight.shape[0]
+            loss_classifier, loss_box_reg = self._fastrcnn_loss_static(o[:, :nc], o[:, nc:nc + 4 * nc], lab_c, reg_c)
+        losses = dict(loss_classifier=loss_classifier, loss_box_reg=loss_box_reg)
+        pos = torch.cat(smp["pos_in"], 0)
+        n_mask = int(pos.shape[0])
+        self.last_num_positives = n_mask
+        kind = rh.maskrcnn_loss
+        if kind not in ('BCE', 'LOVASZ'):
+            raise NotImplementedError
+        if n_mask == 0:
+            losses["loss_mask"] = torch.zeros((), device=feats[0].device)
+            return losses
+        mask_rois5 = rois5[pos].contiguous()
+        mask_logits = self._mask_branch_rois(feats, mask_rois5)
+        # mask targets: row (matched ground truth + offset of the image's masks in the concatenated list, box)
+        g_off = [0]
+        for t in targets:
+            g_off.append(g_off[-1] + t["masks"].shape[0])
+        img_off = K.stager.put(torch.tensor(g_off[:-1], dtype=torch.float32), feats[0].device)
+        gt_row = smp["matched"][pos].to(torch.float32) + img_off[mask_rois5[:, 0].to(torch.int64)]
+        tgt_rois = torch.cat([gt_row[:, None], mask_rois5[:, 1:]], dim=1).contiguous()
+        tg = K.mask_targets(torch.cat([t["masks"] for t in targets], 0).contiguous(), tgt_rois, mask_logits.shape[-1])
+        losses["loss_mask"] = ops.mask_loss(mask_logits, lab_c[pos].contiguous(), tg, kind)
+        return losses
+
+    def _box_loss_graphed(self, feats, rois5, lab_c, reg_c):
+        """Box branch + tv fastrcnn_loss and their backward as one CUDA-graph pair (static shapes: 512 RoIs / image)."""
+        rh = self.roi_heads
+        if self._box_slots is None:
+            mods = (rh.box_head, rh.box_predictor)
+            self._box_slots = [(m, n) for mod in mods for _, m in mod.named_modules()
+                               for n, p in m._parameters.items() if p is not None and p.requires_grad]
+        C = feats[0].shape[-1]
+        fc6 = rh.box_head.fc6
+
+        def kinds(m, n, t):
+            if n != "weight" or not isinstance(m, nn.Linear) or t.shape[0] < 64:
+                return ()
+            inner = C if m is fc6 else 0
+            return (("lf", inner), ("lt", inner))
+        key = ("box", tuple(rois5.shape), tuple(tuple(f.shape) for f in feats[:4]), feats[0].device.index)
+        return self._graphed_call(key, self._box_train_functional, list(feats[:4]) + [rois5, lab_c, reg_c],
+                                  self._box_slots, kinds, True, alias_inputs=4)
+
+    def _box_eval_functional(self, f0, f1, f2, f3, rois5, *theta):
+        slots = self._box_slots_eval
+        saved = [m._parameters[n] for m, n in slots]
+        for (m, n), t in zip(slots, theta):
+            m._parameters[n] = t
+        if self._active_plan is not None:
+            self._active_plan.launch()
+            for k in [k for k in ops._scope if isinstance(k[1], tuple) and k[1][0] == "head"]:
+                del ops._scope[k]
+        try:
+            return self._box_branch([f0, f1, f2, f3], rois5)
+        finally:
+            for (m, n), t in zip(slots, saved):
+                m._parameters[n] = t
+
+    def _mask_eval_functional(self, f0, f1, f2, f3, rois5, *theta):
+        slots = self._mask_slots_eval
+        saved = [m._parameters[n] for m, n in slots]
+        for (m, n), t in zip(slots, theta):
+            m._parameters[n] = t
+        if self._active_plan is not None:
+            self._active_plan.launch()
+            for k in [k for k in ops._scope if isinstance(k[1], tuple) and k[1][0] == "head"]:
+                del ops._scope[k]
+        try:
+            return self._mask_branch_rois([f0, f1, f2, f3], rois5)
+        finally:
+            for (m, n), t in zip(slots, saved):
+                m._parameters[n] = t
+
+    def _heads_eval_fast(self, feats, padded, image_sizes, in_hw):
+        """Box branch on the padded proposals (CUDA graph) -> best detection per image (det_top1_kernel:
+        postprocess_detections with detections_per_img == 1) -> mask branch on that one RoI (CUDA graph).  Nothing
+        here waits for the device: a frame without a detection carries a padding RoI (image index -1) and channel -1
+        through the mask branch and the paste kernel, which then writes zeros."""
+        rh = self.roi_heads
+        device = feats[0].device
+        B, R = padded.shape[0], padded.shape[1]
+        img_idx = getattr(self, "_img_idx_cache", None)
+        if img_idx is None or img_idx.shape != (B, R, 1) or img_idx.device != device:
+            img_idx = torch.arange(B, device=device, dtype=torch.float32).view(B, 1, 1).expand(B, R, 1).contiguous()
+            self._img_idx_cache = img_idx
+        rois5 = torch.cat([img_idx, padded], dim=2).view(B * R, 5)
+        C = feats[0].shape[-1]
+        fc6 = rh.box_head.fc6
+        if getattr(self, "_box_slots_eval", None) is None:
+            mods = (rh.box_head, rh.box_predictor)
+            self._box_slots_eval = [(m, n) for mod in mods for _, m in mod.named_modules()
+                                    for n, p in m._parameters.items() if p is not None]
+            mods = (rh.mask_head, rh.mask_predictor)
+            self._mask_slots_eval = [(m, n) for mod in mods for _, m in mod.named_modules()
+                                     for n, p in m._parameters.items() if p is not None]
+
+        def box_kinds(m, n, t):
+            if n != "weight" or not isinstance(m, nn.Linear) or t.shape[0] < 64:
+                return ()
+            return (("lf", C if m is fc6 else 0),)
+
+        def mask_kinds(m, n, t):
+            if n != "weight":
+                return ()
+            if isinstance(m, nn.ConvTranspose2d):
+                return ("dc",)
+            if isinstance(m, nn.Conv2d) and t.shape[0] >= 64:
+                return ("f",)
+            return ()
+        fkey = (tuple(tuple(f.shape) for f in feats[:4]), feats[0].data_ptr(), device.index)
+        head = self._graphed_call(("box_eval", B * R) + fkey, self._box_eval_functional, list(feats[:4]) + [rois5],
+                                  self._box_slots_eval, box_kinds, False, alias_inputs=4)
+        oh, ow = image_sizes[0]
+        h, w = in_hw
+        back_h = float(torch.tensor(h, dtype=torch.float32) / torch.tensor(oh, dtype=torch.float32))
+        back_w = float(torch.tensor(w, dtype=torch.float32) / torch.tensor(ow, dtype=torch.float32))
+        nc = rh.box_predictor.cls_score.weight.shape[0]
+        det = K.det_top1(head, padded.view(B * R, 4), B, R, nc, rh.box_coder.weights, rh.box_coder.bbox_xform_clip,
+                         rh.score_thresh, 1e-2, float(ow), float(oh), back_w, back_h)
+        mask_logits = self._graphed_call(("mask_eval", B) + fkey, self._mask_eval_functional, list(feats[:4]) + [det["roi"]],
+                                         self._mask_slots_eval, mask_kinds, False, alias_inputs=4)
+        return det, mask_logits
+
+    def _forward_eval_fast(self, inputs, targets, dev_stats):
+        """Inference frame without a host synchronisation (helper_func.py:100-126 body): transform, trunk graph,
+        proposal kernels, EXTEND / REPLACE boxes from the device-resident target box, box graph, arg-max detection,
+        mask graph, fused paste / threshold / next-target tail."""
+        device = inputs.device
+        B, _, h, w = inputs.shape
+        K.zero_pool.reset()
+        pre = None
+        if self._prefetched:
+            pf = self._prefetched.pop(id(inputs), None)
+            if pf is not None and pf[0] is inputs and pf[5] == inputs._version and pf[6] == inputs.data_ptr():
+                pre = (pf[1], pf[2], pf[3])
+                pre_feats = pf[4]
+        x8, _, (oh, ow), (Hp, Wp) = self._transform(inputs, None, pre)
+        image_sizes = [(oh, ow)] * B
+        image_shape = (B, 3, Hp, Wp)
+        with torch.no_grad():
+            feats = pre_feats if pre is not None else self._backbone(x8)
+            feats, head_outs = feats[:5], feats[5:]
+            rpn = self.rpn
+            post = rpn.post_nms_top_n()
+            mode = rpn._eval_augment_proposals_mode
+            Kc = self.num_classes - 1
+            if targets is not None and mode is not None:
+                stats, fallback = dev_stats
+                if mode not in ('EXTEND', 'REPLACE'):
+                    raise NotImplementedError
+                n_aug = post // 2 if mode == 'EXTEND' else post
+                n_front = post // 2 if mode == 'EXTEND' else 0
+                padded = torch.empty((B, n_front + n_aug * Kc, 4), device=device, dtype=torch.float32)
+                count = None
+                if n_front:
+                    _, count = self._rpn_fast(feats, image_shape, image_sizes, head_outs, n_front, padded, 0)
+                rnd = self._extend_rands(B, Kc, n_aug, device)
+                rw = float(torch.tensor(ow, dtype=torch.float32) / torch.tensor(w, dtype=torch.float32))
+                rh_ = float(torch.tensor(oh, dtype=torch.float32) / torch.tensor(h, dtype=torch.float32))
+                K.extend_boxes(stats, fallback, rnd, n_aug, rw, rh_, float(Wp), float(Hp), 0.1, padded, n_front)
+            else:
+                n_front = post
+                padded, count = self._rpn_fast(feats, image_shape, image_sizes, head_outs, post)
+            self._last_padded = (padded, count, n_front)
+            det, mask_logits = self._heads_eval_fast(feats, padded, image_sizes, (h, w))
+        self._last_det = det
+        probs, tgt, stats_out = K.mask_paste_threshold(mask_logits, det["chan"], det["label"], det["box"], B, Kc, h, w, 0.5,
+                                                       want_target=True)
+        self.last_propagated_target = tgt
+        self.last_target_stats = stats_out
+        return probs, det["box"].view(B, Kc, 4)
+
+    @property
+    def last_proposals(self):
+        """Proposals that entered the RoI heads in the last forward, as the reference's per-image lists (observation
+        point for checkers; converting the padded buffer synchronises)."""
+        lp = getattr(self, "_last_padded", None)
+        if lp is None:
+            return getattr(self, "_last_proposal_list", None)
+        padded, count, n_front = lp
+        if count is None:
+            return [p for p in padded]
+        return self._proposal_list(padded, count, n_front)
+
+    @last_proposals.setter
+    def last_proposals(self, value):
+        self._last_padded = None
+        self._last_proposal_list = value
+
+    @property
+    def last_detection_rows(self):
+        """Candidate row (proposal index * (num_classes - 1) + class - 1) of every kept detection, per image."""
+        det = getattr(self, "_last_det", None)
+        if det is None:
+            return getattr(self, "_last_detection_rows", None)
+        rows = det["row"].cpu()
+        lp = self._last_padded
+        out = []
+        if lp is not None and lp[1] is not None:
+            cnt = lp[1].tolist()
+        else:
+            cnt = None
+        for b, r in enumerate(rows.tolist()):
+            if r < 0:
+                out.append(torch.zeros((0,), dtype=torch.int64))
+                continue
+            if cnt is not None and r >= lp[2]:       # rows of the EXTEND half: shift by the unused RPN slots
+                r = r - (lp[2] - min(cnt[b], lp[2]))
+            out.append(torch.tensor([r], dtype=torch.int64))
+        return out
+
+    @last_detection_rows.setter
+    def last_detection_rows(self, value):
+        self._last_det = None
+        self._last_detection_rows = value
+
     def _roi_heads(self, feats, proposals, image_sizes, targets):
         rh = self.roi_heads
         if self.training:
@@ -1029,10 +1389,26 @@ class MaskRCNN(_MaskRCNN):
         device = inputs.device
         if device.type != "cuda":
             raise RuntimeError("eosvos_b200.MaskRCNN runs on sm_100 CUDA devices only (no CPU fallback)")
-        if targets is not None:
-            targets = self._build_targets(targets, flip_label, device)
         if self.training and targets is None:
             raise ValueError("targets should not be None in training mode")
+        fast = self._fast_ok()
+        if not self.training and fast and self.use_cuda_graphs and self.num_classes == 2 \
+                and self.roi_heads.detections_per_img == 1 and not flip_label:
+            # sync-free inference frame: the target's box stays on the DEVICE (run_frames hands over the one the
+            # previous frame's tail kernel produced)
+            # (the target only contributes its bounding box at inference time: mask_rcnn.py:251-285)
+            dev_stats = None
+            if targets is not None and self.rpn._eval_augment_proposals_mode is not None:
+                dev_stats = K.target_stats.get_device(targets)
+                if dev_stats is None:
+                    # box of the target on the device (mask_tail.cu::mask_to_bbox_kernel), never read back.  The
+                    # reference asserts here that the target holds at least one object (mask_rcnn.py:623); without
+                    # the read-back an empty target yields degenerate boxes and no detection instead of raising.
+                    dev_stats = (K.mask_to_bbox(targets.to(torch.float32).contiguous(), self.num_classes - 1), None)
+            return self._forward_eval_fast(inputs, targets, dev_stats)
+        self._last_padded, self._last_det = None, None
+        if targets is not None:
+            targets = self._build_targets(targets, flip_label, device)
         B, _, h, w = inputs.shape
         K.zero_pool.reset()          # one zeroed block per forward(+backward) serves all accumulate-into outputs
         self._prepare_operands()
@@ -1052,9 +1428,22 @@ class MaskRCNN(_MaskRCNN):
         with grad_ctx:
             feats = pre_feats if pre is not None else self._backbone(x8)
             feats, head_outs = feats[:5], (feats[5:] if len(feats) > 5 else None)
+            if self.training and fast and head_outs is not None and head_outs[0].dtype == torch.float32:
+                # statically shaped proposal / sampling pipeline: ONE host sync (RoI sampler counts) per iteration
+                early = self._rpn_early_targets(feats, image_shape, image_sizes, targets_t)
+                padded, count = self._rpn_fast(feats, image_shape, image_sizes, head_outs, self.rpn.post_nms_top_n())
+                self._last_padded = (padded, count, padded.shape[1])
+                det_losses = self._roi_heads_train_fast(feats, padded, count, targets_t)
+                objectness, pred_bbox_deltas, _, _ = self._rpn_cat_outputs(feats, head_outs)
+                raw = dict(det_losses)
+                raw.update(self._rpn_losses(early, objectness, pred_bbox_deltas))
+                losses = {n: l for n, l in raw.items() if l.requires_grad}
+                return sum([l for l in losses.values()]), losses
             proposals, rpn_losses = self._rpn(feats, image_shape, image_sizes, targets_t, head_outs)
             if self.fixed_proposals is not None:
                 proposals = [p.to(device).clone() for p in self.fixed_proposals]
+            self.last_proposals = proposals          # observation point for checkers (device tensors, no copy)
+            self.last_num_positives = None
             if self.capture is not None:
                 self.capture.update(feats=feats, proposals=[p.detach() for p in proposals], x8=x8)
             detections, det_losses, mask_logits = self._roi_heads(feats, proposals, image_sizes, targets_t)

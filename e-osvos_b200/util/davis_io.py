@@ -24,8 +24,8 @@ def load_sequence(root, seq, resolution="480p", pin=False):
     frame names, has_label [T] bool)."""
     import cv2
     from PIL import Image
-    img_dir = os.path.join(root, "JPEGImages", resolution, seq)
-    lab_dir = os.path.join(root, "Annotations", resolution, seq)
+    img_dir = os.path.join(root, "JPEGImages", *([resolution] if resolution else []), seq)
+    lab_dir = os.path.join(root, "Annotations", *([resolution] if resolution else []), seq)
     names = sorted(os.path.splitext(f)[0] for f in os.listdir(img_dir) if f.lower().endswith((".jpg", ".jpeg", ".png")))
     if not names:
         raise FileNotFoundError(f"no frames under {img_dir}")
@@ -52,6 +52,109 @@ def load_sequence(root, seq, resolution="480p", pin=False):
     if pin and torch.cuda.is_available():
         fr = fr.pin_memory()
     return fr, torch.from_numpy(lab), names, np.array(has, dtype=bool)
+
+
+class VideoSequence:
+    """One sequence in memory, with the per-object label rules of the reference's datasets under
+    multi_object='single_id' (src/data/vos_dataset.py:193-339, src/data/youtube.py:107-185).
+    frames float32 [T,3,H,W] RGB in [0,1]; labels uint8 [T,H,W] ids (zeros where a frame has no annotation);
+    annotated [T] bool; objects: None (DAVIS: ids 1..K of the first annotation) or [(label id, first annotated
+    frame)] sorted by id (YouTube-VOS meta.json); test_mode: only first annotations exist (youtube.py:47-48)."""
+
+    def __init__(self, frames, labels, names=None, annotated=None, objects=None, test_mode=None, multi_object=True):
+        self.frames, self.labels = frames, labels
+        T = frames.shape[0]
+        self.names = names if names is not None else [f"{i:05d}" for i in range(T)]
+        self.annotated = np.ones(T, bool) if annotated is None else np.asarray(annotated, bool)
+        self.label_frames = [i for i in range(T) if self.annotated[i]]
+        self.objects = objects
+        self.test_mode = (not self.annotated.all()) if test_mode is None else test_mode
+        self.multi_object = multi_object
+        if not multi_object:
+            self.num_objects = 1
+        elif objects is None:
+            self.num_objects = int((torch.unique(labels[self.label_frames[0]]) != 0).sum())
+        else:
+            self.num_objects = len(objects)
+
+    def __len__(self):
+        return self.frames.shape[0]
+
+    def gt_frame_id(self, obj):
+        """(frame id, label-file index) of the object's first annotation: frame 0 for DAVIS (vos_dataset.py:193-194),
+        meta.json's first frame for YouTube-VOS (youtube.py:131-143)."""
+        if self.objects is None:
+            return 0, None
+        f = self.objects[obj][1]
+        return f, self.label_frames.index(f)
+
+    def label(self, idx, obj, label_idx=None):
+        """Binary float label [H,W] of object `obj` as the dataset would hand it out for frame `idx`
+        (vos_dataset.py:236-245: which label file; :288-339: single-id selection)."""
+        if label_idx is not None:
+            raw = self.labels[self.label_frames[label_idx]]
+        elif self.test_mode:
+            raw = self.labels[self.label_frames[0]]
+        else:
+            raw = self.labels[idx]
+        if self.multi_object and self.num_objects > 1:
+            want = obj + 1 if self.objects is None else self.objects[obj][0]
+            return (raw == want).float()
+        return (raw != 0).float()
+
+
+class Dataset:
+    """The sequences of one split in the reference's on-disk layouts (src/data/davis.py:30-66,
+    src/data/youtube.py:27-95), rooted at `data/<name>` under the working directory (helper_func.py:265-273)."""
+
+    def __init__(self, name, split, multi_object='single_id', full_resolution=False, root=None):
+        self.name, self.split, self.multi_object = name, split, multi_object
+        self.root = root or os.path.join('data', name)
+        self.youtube = name == 'YouTube-VOS'
+        if not self.youtube and not name.startswith('DAVIS'):
+            raise NotImplementedError(name)
+        seqs_file = os.path.join(self.root, f"{split}.txt")
+        if os.path.exists(seqs_file):
+            with open(seqs_file) as f:
+                self.seq_names = [ln.strip() for ln in f if ln.strip()]
+        elif self.youtube:
+            raise NotImplementedError
+        else:
+            self.seq_names = [split]
+        self.all_frames = False
+        if self.youtube:
+            import json
+            self.part = split.split('_')[0]
+            self.test_mode = self.part in ('valid', 'test', 'valid-all-frames', 'test-all-frames')
+            self.all_frames = 'all-frames' in self.part
+            with open(os.path.join(self.root, self.part, 'meta.json')) as f:
+                self.meta = json.load(f)
+            self.resolution = None
+        else:
+            self.test_mode = 'test' in split
+            year = int(''.join(c for c in name if c.isdigit()))
+            self.resolution = '480p' if not full_resolution else ('1080p' if year == 2016 else 'Full-Resolution')
+            if year == 2016:
+                self.multi_object = False
+
+    def load(self, seq_name, pin=False):
+        if not self.youtube:
+            fr, lab, names, has = load_sequence(self.root, seq_name, self.resolution, pin=pin)
+            return VideoSequence(fr, lab, names, has, None, self.test_mode, multi_object=bool(self.multi_object))
+        base = os.path.join(self.root, self.part)
+        fr, lab, names, has = load_sequence(base, seq_name, None, pin=pin)
+        info = self.meta['videos'][seq_name]['objects']
+        objects = []
+        for oid in sorted(info.keys()):
+            first = info[oid][0] if 'test' in self.split else info[oid]["frames"][0]
+            objects.append((int(oid), names.index(first)))
+        if self.all_frames:           # labels of un-annotated frames repeat the first one (youtube.py:78-79)
+            pass
+        return VideoSequence(fr, lab, names, has, objects, self.test_mode, multi_object=bool(self.multi_object))
+
+
+def open_dataset(name, split, multi_object='single_id', full_resolution=False, root=None):
+    return Dataset(name, split, multi_object, full_resolution, root)
 
 
 def sequence_meta(root, seq, resolution="480p"):

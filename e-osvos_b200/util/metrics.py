@@ -79,7 +79,7 @@ def sequence_statistics(per_frame):
     return mean, recall, decay
 
 
-def evaluate_sequence_jf(pred, labels, num_objects):
+def evaluate_sequence_jf(pred, labels, num_objects, measures=("J", "F")):
     """pred, labels: [T,H,W] object ids -> {"J": [...], "F": [...]} with one (mean, recall, decay) per object,
     frames 1 .. T-2 (the DAVIS protocol drops the first and the last frame)."""
     pred, labels = np.asarray(pred), np.asarray(labels)
@@ -87,10 +87,10 @@ def evaluate_sequence_jf(pred, labels, num_objects):
     frames = range(1, max(T - 1, 2))
     out = {"J": [], "F": []}
     for k in range(1, num_objects + 1):
-        js = [jaccard(pred[f] == k, labels[f] == k) for f in frames]
-        fs = [f_measure(pred[f] == k, labels[f] == k) for f in frames]
-        out["J"].append(sequence_statistics(js))
-        out["F"].append(sequence_statistics(fs))
+        if "J" in measures:
+            out["J"].append(sequence_statistics([jaccard(pred[f] == k, labels[f] == k) for f in frames]))
+        if "F" in measures:
+            out["F"].append(sequence_statistics([f_measure(pred[f] == k, labels[f] == k) for f in frames]))
     return out
 
 

@@ -109,6 +109,34 @@ long long eosvos_nms_scratch_bytes(int num_segments, int max_seg);
 int eosvos_nms_segments(const float* boxes, const int* seg_off, int num_segments, int max_seg, float thresh,
                         void* scratch, unsigned char* keep, eosvos_stream_t stream);
 
+/* ---- K5/K6: proposal / detection post-processing on padded, statically shaped buffers (reference:
+ *      mask_rcnn.py:237-249 decode + tv rpn.py filter_proposals; :251-332 EXTEND / REPLACE augmentation; :347-420
+ *      postprocess_detections; tv roi_heads.py:642-678 assign_targets_to_proposals + box_coder.encode).  See
+ *      csrc/rpn.cu for the layouts. */
+long long eosvos_rpn_scratch_bytes(int N, const int* hw, int num_levels, int A);
+long long eosvos_rpn_scratch_zero_bytes(int N, int num_levels);
+int eosvos_rpn_select(const void* const* heads, const int* hw, int num_levels, int A, int N, const float* anchors,
+                      const float* image_hw, int pre_nms_top_n, float bbox_clip, float min_size, float score_thresh,
+                      void* scratch, float* boxes, float* scores, unsigned char* valid, eosvos_stream_t stream);
+int eosvos_rpn_postnms(const int* hw, int num_levels, int A, int N, int pre_nms_top_n, const float* boxes,
+                       const float* scores, const unsigned char* valid, const unsigned char* keep, int post_n,
+                       int out_stride, int out_offset, float* out_boxes, float* out_scores, int* out_count,
+                       eosvos_stream_t stream);
+int eosvos_extend_boxes(const int* stats, const int* fallback_stats, const float* rnd, int B, int G, int n_aug,
+                        float ratio_w, float ratio_h, float img_w, float img_h, float share, int out_stride,
+                        int out_offset, float* out_boxes, eosvos_stream_t stream);
+int eosvos_det_top1(const float* head, const float* proposals, int B, int R, int num_classes,
+                    const float* coder_weights4, float bbox_clip, float score_thresh, float min_size, float img_w,
+                    float img_h, float back_w, float back_h, float* det_box, float* det_score, long long* det_label,
+                    int* det_row, float* det_roi, int* chan, eosvos_stream_t stream);
+int eosvos_roi_match(const float* proposals, const int* count, const float* gt_boxes, const long long* gt_labels,
+                     const int* gt_off, int B, int P, int max_gt, float iou_thresh, float* all_boxes, long long* labels,
+                     long long* matched, int* counts, eosvos_stream_t stream);
+int eosvos_roi_encode(const float* all_boxes, const long long* labels, const long long* matched, const float* gt_boxes,
+                      const int* gt_off, const long long* inds, int B, int S, int rows_per_image,
+                      const float* coder_weights4, float* rois5, long long* out_labels, long long* out_matched,
+                      float* reg_targets, eosvos_stream_t stream);
+
 /* ---- K9: MetaOptimizer update (reference: meta_optim.py:177-214, meta_model.py:78-80) */
 /* table_dev: int64 [T][8] = (p, g, lr, out, numel, elements per lr row, g_taps, g_cin); g_taps > 1 means the gradient
  * of a [Cout][Cin][taps] filter is stored [Cout][taps][Cin] (channels_last, eosvos_conv2d_wgrad dw_layout 1);

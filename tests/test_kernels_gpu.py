@@ -509,3 +509,193 @@ def test_device_augmentation_matches_cv2_family():
         assert torch.equal(g[b, 0].cpu(), torch.from_numpy(np.ascontiguousarray(ref[b][1])))
         d = (x[b].cpu() - ri).abs()
         assert d.mean().item() < 2e-3 and d.max().item() < 0.25, (d.mean().item(), d.max().item())
+
+
+# ------------------------------------------------------------------------------------------------ K5/K6 (rpn.cu)
+def _rpn_case(N, feat_shapes, seed):
+    from torchvision.models.detection.anchor_utils import AnchorGenerator
+    g = torch.Generator().manual_seed(seed)
+    A = 3
+    heads = [(torch.randn(N * h * w, 16, generator=g) * torch.tensor([2.0] * 3 + [0.3] * 12 + [0.0])).to(dev())
+             for h, w in feat_shapes]
+    ag = AnchorGenerator(((32,), (64,), (128,), (256,), (512,)), ((0.5, 1.0, 2.0),) * 5)
+
+    class IL:
+        pass
+    il = IL()
+    stride = 4
+    Hp, Wp = feat_shapes[0][0] * stride, feat_shapes[0][1] * stride
+    il.tensors = torch.empty((N, 3, Hp, Wp), device="meta")
+    il.image_sizes = [(Hp - 19, Wp - 11)] * N
+    fms = [torch.empty((N, 1, h, w), device=dev()) for h, w in feat_shapes]
+    anchors = ag(il, fms)[0].contiguous()
+    return heads, anchors, il.image_sizes, A
+
+
+@pytest.mark.parametrize("N,pre,post", [(3, 2000, 2000), (1, 1000, 500)])
+def test_rpn_select_nms_postnms_match_torchvision(N, pre, post):
+    """rpn_select + nms_segments + rpn_postnms (csrc/rpn.cu) against tv rpn.py filter_proposals restated with torch /
+    torchvision ops (decode of ALL anchors, per-level top-k, clip, filters, batched_nms, top-n): same boxes in the same
+    order.  Box arithmetic follows the ATen op sequence (no FMA contraction) => equal to float rounding of exp()."""
+    import torchvision
+    from torchvision.models.detection._utils import BoxCoder
+    feat_shapes = [(192, 336), (96, 168), (48, 84), (24, 42), (12, 21)]
+    heads, anchors, image_sizes, A = _rpn_case(N, feat_shapes, 5)
+    hw = [h * w for h, w in feat_shapes]
+    clip = math.log(1000.0 / 16)
+    boxes_c, scores_c, valid_c, ks = K().rpn_select(heads, hw, A, N, anchors, image_sizes, pre, clip, 1e-3, 0.0)
+    C = sum(ks)
+    offs = [0]
+    for _ in range(N):
+        for k in ks:
+            offs.append(offs[-1] + k)
+    seg = torch.tensor(offs, dtype=torch.int32, device=dev())
+    keep = K().nms_segments(boxes_c.view(-1, 4), seg, N * len(ks), max(ks), 0.7)
+    out, _, count = K().rpn_postnms(hw, A, N, pre, boxes_c, scores_c, valid_c, keep, post)
+    # reference
+    coder = BoxCoder((1.0, 1.0, 1.0, 1.0))
+    obj = torch.cat([h[:, :A].reshape(N, -1) for h in heads], 1)
+    dlt = torch.cat([h[:, A:5 * A].reshape(N, -1, 4) for h in heads], 1)
+    for n in range(N):
+        props = coder.decode_single(dlt[n], anchors)
+        lvl_boxes, lvl_scores, lvl_ids = [], [], []
+        o = 0
+        for l, cnt in enumerate(hw):
+            cnt *= A
+            k = min(pre, cnt)
+            sc, idx = obj[n, o:o + cnt].topk(k)
+            lvl_boxes.append(props[o + idx])
+            lvl_scores.append(torch.sigmoid(sc))
+            lvl_ids.append(torch.full((k,), l, device=dev()))
+            # the kernel's per-level selection: same set, same order (descending objectness)
+            got = boxes_c[n, sum(ks[:l]):sum(ks[:l]) + k]
+            o += cnt
+        b, s, ids = torch.cat(lvl_boxes), torch.cat(lvl_scores), torch.cat(lvl_ids)
+        b = torchvision.ops.clip_boxes_to_image(b, image_sizes[n])
+        kp = torchvision.ops.remove_small_boxes(b, 1e-3)
+        b, s, ids = b[kp], s[kp], ids[kp]
+        kp = torchvision.ops.batched_nms(b, s, ids, 0.7)[:post]
+        want = b[kp]
+        c = int(count[n])
+        assert c == want.shape[0], (c, want.shape[0])
+        d = (out[n, :c] - want).abs().max().item()
+        assert d <= 2e-3, d
+        assert out[n, c:].abs().sum().item() == 0
+
+
+def test_extend_boxes_bit_equal_to_reference_arithmetic():
+    """extend_boxes_kernel against reference mask_rcnn.py:262-285 evaluated with torch CPU ops on the same uniforms."""
+    g = torch.Generator().manual_seed(3)
+    B, G, n_aug = 2, 1, 500
+    stats = torch.tensor([[[100, 50, 420, 330, 9000]], [[0, 0, 853, 479, 1]]], dtype=torch.int32)
+    rnd = torch.rand(B, G, 4, n_aug, generator=g)
+    h, w, oh, ow, Hp, Wp = 480, 854, 749, 1333, 768, 1344
+    rw = float(torch.tensor(ow, dtype=torch.float32) / torch.tensor(w, dtype=torch.float32))
+    rh = float(torch.tensor(oh, dtype=torch.float32) / torch.tensor(h, dtype=torch.float32))
+    out = torch.zeros(B, 1000, 4, device=dev())
+    K().extend_boxes(stats.to(dev()), None, rnd.to(dev()), n_aug, rw, rh, Wp, Hp, 0.1, out, 500)
+    for b in range(B):
+        st = stats[b, 0]
+        box = torch.tensor([st[0], st[1], st[2] + 1, st[3] + 1], dtype=torch.float32)
+        box = torch.stack((box[0] * rw, box[1] * rh, box[2] * rw, box[3] * rh))
+        bw, bh = box[2] - box[0], box[3] - box[1]
+        x_mins = box[0] - rnd[b, 0, 0] * bw * 0.1
+        y_mins = box[1] - rnd[b, 0, 1] * bh * 0.1
+        x_maxs = box[2] + rnd[b, 0, 2] * bw * 0.1
+        y_maxs = box[3] + rnd[b, 0, 3] * bh * 0.1
+        want = torch.stack([x_mins.clamp(0, Wp), y_mins.clamp(0, Hp), x_maxs.clamp(0, Wp), y_maxs.clamp(0, Hp)], dim=1)
+        assert torch.equal(out[b, 500:].cpu(), want)
+        assert out[b, :500].abs().sum().item() == 0
+    # empty target -> fallback box
+    empty = torch.tensor([[[2147483647, 2147483647, -1, -1, 0]]], dtype=torch.int32).to(dev())
+    out2 = torch.zeros(1, 500, 4, device=dev())
+    K().extend_boxes(empty, stats[:1].to(dev()), rnd[:1].to(dev()), n_aug, rw, rh, Wp, Hp, 0.1, out2, 0)
+    assert torch.equal(out2[0], out[0, 500:])
+
+
+def test_det_top1_matches_postprocess_detections():
+    """det_top1_kernel against tv-style postprocess_detections (softmax, decode, clip, score / size filter, NMS, first
+    detection) evaluated with torch / torchvision ops."""
+    import torchvision
+    from torchvision.models.detection._utils import BoxCoder
+    g = torch.Generator().manual_seed(9)
+    B, R, nc = 2, 1000, 2
+    head = torch.zeros(B * R, 16)
+    head[:, :nc] = torch.randn(B * R, nc, generator=g) * 2
+    head[:, nc:nc + 4 * nc] = torch.randn(B * R, 4 * nc, generator=g)
+    ctr = torch.rand(B * R, 2, generator=g) * torch.tensor([1333.0, 749.0])
+    wh = torch.rand(B * R, 2, generator=g) * 300 + 2
+    props = torch.cat([ctr - wh / 2, ctr + wh / 2], 1).clamp(min=0)
+    props[7] = 0                       # a padding row
+    coder = BoxCoder((10.0, 10.0, 5.0, 5.0))
+    for thr in (0.05, 0.5, 0.9999):
+        det = K().det_top1(head.to(dev()), props.to(dev()), B, R, nc, (10.0, 10.0, 5.0, 5.0), math.log(1000.0 / 16), thr,
+                           1e-2, 1333.0, 749.0, 0.64, 0.64)
+        for b in range(B):
+            hb, pb = head[b * R:(b + 1) * R], props[b * R:(b + 1) * R]
+            boxes = coder.decode(hb[:, nc:nc + 4 * nc], [pb]).reshape(R, nc, 4)
+            scores = F.softmax(hb[:, :nc], -1)
+            boxes = torchvision.ops.clip_boxes_to_image(boxes, (749, 1333))[:, 1:].reshape(-1, 4)
+            scores = scores[:, 1:].flatten()
+            inds = torch.nonzero(scores > thr).squeeze(1)
+            bx, sc = boxes[inds], scores[inds]
+            kp = torchvision.ops.remove_small_boxes(bx, 1e-2)
+            bx, sc, inds = bx[kp], sc[kp], inds[kp]
+            if sc.numel() == 0:
+                assert int(det["row"][b]) == -1 and int(det["chan"][b]) == -1 and float(det["roi"][b, 0]) == -1.0
+                assert det["box"][b].abs().sum().item() == 0
+                continue
+            top = sc.argsort(descending=True, stable=True)[0]
+            assert int(det["row"][b]) == int(inds[top])
+            assert abs(float(det["score"][b]) - float(sc[top])) <= 1e-6
+            assert (det["roi"][b, 1:].cpu() - bx[top]).abs().max().item() <= 1e-3
+            assert (det["box"][b].cpu() - bx[top] * 0.64).abs().max().item() <= 1e-3
+            assert int(det["label"][b]) == 1 and int(det["chan"][b]) == b and float(det["roi"][b, 0]) == float(b)
+
+
+def test_roi_match_and_encode_match_torchvision():
+    """roi_match_kernel / roi_encode_kernel against tv roi_heads.py assign_targets_to_proposals (box_iou + Matcher 0.5 /
+    0.5) and box_coder.encode on the same padded proposal list with the ground-truth boxes appended."""
+    import torchvision
+    from torchvision.models.detection._utils import BoxCoder, Matcher
+    g = torch.Generator().manual_seed(4)
+    B, P = 3, 2000
+    gts = [torch.tensor([[100.0, 80.0, 400.0, 300.0]]), torch.tensor([[50.0, 60.0, 300.0, 500.0], [600.0, 100.0, 900.0, 400.0]]),
+           torch.tensor([[700.0, 300.0, 1200.0, 700.0]])]
+    gls = [torch.tensor([1]), torch.tensor([1, 1]), torch.tensor([1])]
+    counts = torch.tensor([2000, 1500, 37], dtype=torch.int32)
+    props = torch.zeros(B, P, 4)
+    for b in range(B):
+        n = int(counts[b])
+        gt = gts[b][torch.randint(0, gts[b].shape[0], (n,), generator=g)]
+        props[b, :n] = (gt + torch.randn(n, 4, generator=g) * 60).clamp(min=0)
+        props[b, :n, 2:] = torch.maximum(props[b, :n, 2:], props[b, :n, :2] + 1)
+    gt_cat, gl_cat = torch.cat(gts), torch.cat(gls)
+    gt_off = torch.tensor([0, 1, 3, 4], dtype=torch.int32)
+    all_boxes, labels, matched, cnt = K().roi_match(props.to(dev()), counts.to(dev()), gt_cat.to(dev()), gl_cat.to(dev()),
+                                                    gt_off.to(dev()), 2, 0.5)
+    matcher = Matcher(0.5, 0.5, allow_low_quality_matches=False)
+    for b in range(B):
+        n, G = int(counts[b]), gts[b].shape[0]
+        pl = torch.cat([props[b, :n], gts[b]])
+        m = matcher(torchvision.ops.box_iou(gts[b], pl))
+        lab = gls[b][m.clamp(min=0)]
+        lab[m == Matcher.BELOW_LOW_THRESHOLD] = 0
+        got_l = torch.cat([labels[b, :n], labels[b, P:P + G]]).cpu()
+        got_m = torch.cat([matched[b, :n], matched[b, P:P + G]]).cpu()
+        assert torch.equal(got_l, lab)
+        fg = lab > 0
+        assert torch.equal(got_m[fg], m[fg])
+        assert (labels[b, n:P] == -1).all() and (labels[b, P + G:] == -1).all()
+        assert cnt[b].tolist() == [int(fg.sum()), int((lab == 0).sum())]
+    inds = torch.stack([torch.randperm(int(counts[b]), generator=g)[:32] for b in range(B)]).to(dev())
+    rois5, ol, om, reg = K().roi_encode(all_boxes, labels, matched, gt_cat.to(dev()), gt_off.to(dev()), inds,
+                                       (10.0, 10.0, 5.0, 5.0))
+    coder = BoxCoder((10.0, 10.0, 5.0, 5.0))
+    for b in range(B):
+        pb = props[b][inds[b].cpu()]
+        mb = matched[b].cpu()[inds[b].cpu()]
+        want = coder.encode_single(gts[b][mb], pb)
+        got = reg[b * 32:(b + 1) * 32].cpu()
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+        assert torch.equal(rois5[b * 32:(b + 1) * 32, 1:].cpu(), pb) and (rois5[b * 32:(b + 1) * 32, 0] == b).all()
