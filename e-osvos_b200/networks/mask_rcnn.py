@@ -1391,6 +1391,10 @@ class MaskRCNN(_MaskRCNN):
             raise RuntimeError("eosvos_b200.MaskRCNN runs on sm_100 CUDA devices only (no CPU fallback)")
         if self.training and targets is None:
             raise ValueError("targets should not be None in training mode")
+        if targets is not None and targets.device != device:
+            # the reference's callers hand over the first-frame label as a host tensor (evaluate.py:297-301): its
+            # forward reads targets on the host anyway (mask_rcnn.py:593-632)
+            targets = targets.to(device, non_blocking=True)
         fast = self._fast_ok()
         if not self.training and fast and self.use_cuda_graphs and self.num_classes == 2 \
                 and self.roi_heads.detections_per_img == 1 and not flip_label:

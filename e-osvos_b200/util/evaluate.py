@@ -280,7 +280,7 @@ def evaluate_sequence(model, meta_optim, meta_optim_state_dict, frames, first_la
         num_frames += T
 
     pred = torch.zeros(T, H, W, dtype=torch.uint8)
-    for f in range(T):                                   # evaluate.py:323-326
+    for f in range(T if num_objects else 0):             # evaluate.py:323-326
         bg = masks[f].max(dim=0)[0].lt(0.5)
         m = masks[f].argmax(dim=0) + 1
         m[bg] = 0

@@ -210,6 +210,40 @@ def install_full():
     _full_installed = True
 
 
+class _RandOnDevice:
+    """`torch` as seen by the reference's networks.mask_rcnn when it runs on a CUDA device.  The reference mixes
+    `torch.rand(n)` (CPU) with 0-dim CUDA tensors (mask_rcnn.py:270-273), which torch 1.2 accepted and torch 2 rejects:
+    draw from the same CPU generator (same random stream), then move the numbers to the model's device."""
+
+    def __init__(self, device):
+        self._device = torch.device(device)
+
+    def rand(self, *a, **k):
+        return torch.rand(*a, **k).to(self._device)
+
+    def arange(self, *a, **k):
+        # mask_rcnn.py:381 builds a CPU index vector and indexes it with a CUDA tensor (accepted by torch 1.2)
+        k.setdefault("device", self._device)
+        return torch.arange(*a, **k)
+
+    def __getattr__(self, k):
+        return getattr(torch, k)
+
+
+@contextlib.contextmanager
+def reference_on_device(device):
+    """Context in which the reference's model code can run on `device` (no-op for the CPU)."""
+    install_full()
+    import networks.mask_rcnn as ref_mr
+    saved = ref_mr.torch
+    if torch.device(device).type == "cuda":
+        ref_mr.torch = _RandOnDevice(device)
+    try:
+        yield
+    finally:
+        ref_mr.torch = saved
+
+
 def reference_workers():
     """-> (util.evaluate, util.helper_func, util.meta_run, util.radam) of the unmodified reference."""
     install_full()
@@ -448,7 +482,7 @@ def run_reference_evaluate(config, dataset_key, workdir, device="cpu", meta_opti
         ev.torch = _TorchProxy(device)
         ev.MaskRCNN = hf.MaskRCNN = model_cls
         ev.MetaOptimizer = optim_spy
-        with _cwd(workdir):
+        with _cwd(workdir), reference_on_device(device):
             if meta_optim_state_dict is None:
                 hf.set_random_seeds(config["seed"])
                 model, _ = hf.init_parent_model(**config["parent_model"])

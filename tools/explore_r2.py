@@ -48,7 +48,7 @@ def ref_gpu(tf32):
     model.eval()
     tgt = gt0[None, None].to(dev)
     frames = [fr[1 + i:2 + i].to(dev) for i in range(3)]
-    with torch.no_grad():
+    with torch.no_grad(), RH.reference_on_device(dev):
         for f in frames:
             model(f, tgt)
         torch.cuda.synchronize()
