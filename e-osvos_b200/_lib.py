@@ -52,6 +52,9 @@ SIGNATURES = {
     "eosvos_extend_boxes": [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _F, _I, _I, _P, _P],
     "eosvos_det_top1": [_P, _P, _I, _I, _I, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "eosvos_roi_match": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P],
+    "eosvos_rpn_anchor_match": [_P, _I, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P],
+    "eosvos_rpn_loss": [_P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P],
+    "eosvos_roi_sample": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
     "eosvos_roi_encode": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "eosvos_meta_update_chunk_elems": [],
     "eosvos_meta_update": [_P, _P, _I, _I, _P],

@@ -518,6 +518,106 @@ roi_match_kernel(const float4* __restrict__ props, const int* __restrict__ count
   }
 }
 
+// tv _utils.py BalancedPositiveNegativeSampler for one image per CTA, given the two `torch.randperm` draws the
+// reference makes (perm_pos over the foreground candidates, perm_neg over the background candidates, in index order):
+// selected = { fg[perm_pos[j]] : j < num_pos } U { bg[perm_neg[j]] : j < num_neg }, emitted in ascending row order
+// (== torch.where(mask) of the reference), plus the positions of the foreground rows inside that list.
+// table int64 [B][4] = (perm_pos ptr, perm_neg ptr, num_pos, num_neg).  inds int64 [B][S] (-1 padded),
+// pos_in int64 [B][Pmax] (-1 padded).  flags: scratch, 2 * rows bytes per image (global memory: the RPN sampler runs
+// this over 257,796 anchors per image).
+__global__ void __launch_bounds__(1024)
+roi_sample_kernel(const long long* __restrict__ labels, const long long* __restrict__ table, int rows, int S, int Pmax,
+                  unsigned char* __restrict__ flags, long long* __restrict__ inds, long long* __restrict__ pos_in) {
+  unsigned char* flag_pos = flags + (size_t)blockIdx.x * 2 * rows;   // [rows]: rank r of the foreground candidates is drawn
+  unsigned char* flag_neg = flag_pos + rows;                         // [rows]
+  __shared__ int s_warp[32];
+  __shared__ int s_carry[3];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long* lab = labels + (size_t)b * rows;
+  const long long* perm_pos = reinterpret_cast<const long long*>(table[b * 4 + 0]);
+  const long long* perm_neg = reinterpret_cast<const long long*>(table[b * 4 + 1]);
+  const int num_pos = (int)table[b * 4 + 2], num_neg = (int)table[b * 4 + 3];
+  for (int i = tid; i < rows; i += blockDim.x) {
+    flag_pos[i] = 0;
+    flag_neg[i] = 0;
+  }
+  for (int i = tid; i < S; i += blockDim.x) inds[(size_t)b * S + i] = -1;
+  for (int i = tid; i < Pmax; i += blockDim.x) pos_in[(size_t)b * Pmax + i] = -1;
+  if (tid < 3) s_carry[tid] = 0;
+  __syncthreads();
+  for (int j = tid; j < num_pos; j += blockDim.x) flag_pos[perm_pos[j]] = 1;
+  for (int j = tid; j < num_neg; j += blockDim.x) flag_neg[perm_neg[j]] = 1;
+  __syncthreads();
+  // one pass over the rows in blocks of blockDim: running ranks among fg / bg candidates, running output position
+  for (int base = 0; base < rows; base += blockDim.x) {
+    const int i = base + tid;
+    const long long l = i < rows ? lab[i] : -1;
+    const int is_fg = l >= 1, is_bg = l == 0;
+    // three block-wide exclusive scans: fg rank, bg rank, output slot
+    int v[3] = {is_fg, is_bg, 0};
+    int exc[3];
+    for (int q = 0; q < 2; ++q) {
+      int inc = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) s_warp[warp] = inc;
+      __syncthreads();
+      int wb = 0;
+      for (int w = 0; w < warp; ++w) wb += s_warp[w];
+      exc[q] = s_carry[q] + wb + inc - v[q];
+      __syncthreads();
+      if (tid == blockDim.x - 1) s_carry[q] = exc[q] + v[q];
+      __syncthreads();
+    }
+    const int sel = (is_fg && flag_pos[exc[0]]) || (is_bg && flag_neg[exc[1]]);
+    v[2] = sel;
+    {
+      int inc = sel;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) s_warp[warp] = inc;
+      __syncthreads();
+      int wb = 0;
+      for (int w = 0; w < warp; ++w) wb += s_warp[w];
+      exc[2] = s_carry[2] + wb + inc - sel;
+      __syncthreads();
+      if (tid == blockDim.x - 1) s_carry[2] = exc[2] + sel;
+      __syncthreads();
+    }
+    if (sel && exc[2] < S) inds[(size_t)b * S + exc[2]] = i;
+  }
+  __syncthreads();
+  // positions of the foreground rows inside the sampled list (second, small compaction; S <= 1024 per round)
+  if (tid == 0) s_carry[0] = 0;
+  __syncthreads();
+  for (int base = 0; base < S; base += blockDim.x) {
+    const int j = base + tid;
+    const long long r = j < S ? inds[(size_t)b * S + j] : -1;
+    const int f = r >= 0 && lab[r] >= 1;
+    int inc = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int wb = 0;
+    for (int w = 0; w < warp; ++w) wb += s_warp[w];
+    const int slot = s_carry[0] + wb + inc - f;
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry[0] = slot + f;
+    if (f && slot < Pmax) pos_in[(size_t)b * Pmax + slot] = j;
+    __syncthreads();
+  }
+}
+
 // Sampled RoIs -> (image, box) rows, labels, regression targets (tv _utils.py encode_boxes, weights wx..wh).
 // inds int64 [B][S]: row inside the image's candidate list (roi_match_kernel layout).
 __global__ void roi_encode_kernel(const float4* __restrict__ all_boxes, const long long* __restrict__ labels,
@@ -553,6 +653,160 @@ __global__ void roi_encode_kernel(const float4* __restrict__ all_boxes, const lo
   e.z = __fmul_rn(ww, logf(gt_w / ex_w));
   e.w = __fmul_rn(wh, logf(gt_h / ex_h));
   reg[o] = e;
+}
+
+// tv rpn.py assign_targets_to_anchors: box_iou(gt, anchors) + Matcher(0.7, 0.3, allow_low_quality_matches=True).
+// Pass 1: per ground-truth box the highest IoU over all anchors (IoU >= 0: the float bit pattern orders like an
+// unsigned int, so atomicMax works).  Pass 2: labels (1 foreground / 0 background / -1 between the thresholds, as int64
+// for the sampler), arg-max ground truth, per-image counts.  An anchor that attains a box's highest IoU keeps its
+// arg-max match even below the thresholds (tv _utils.py Matcher.set_low_quality_matches_).
+__device__ __forceinline__ float box_iou_tv(const float4 g, const float ga, const float4 a, const float aa) {
+  const float w = fmaxf(__fsub_rn(fminf(g.z, a.z), fmaxf(g.x, a.x)), 0.f);
+  const float h = fmaxf(__fsub_rn(fminf(g.w, a.w), fmaxf(g.y, a.y)), 0.f);
+  const float inter = __fmul_rn(w, h);
+  return inter / __fsub_rn(__fadd_rn(ga, aa), inter);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256)
+anchor_match_kernel(const float4* __restrict__ anchors, int num_anchors, const float4* __restrict__ gt,
+                    const int* __restrict__ gt_off, float hi, float lo, unsigned* __restrict__ gt_best,
+                    long long* __restrict__ labels, int* __restrict__ matched, int* __restrict__ counts) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g0 = gt_off[b], G = gt_off[b + 1] - g0;
+  int fg = 0, bg = 0;
+  if (i < num_anchors) {
+    const float4 a = anchors[i];
+    const float aa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    float best = -1.f;
+    int mi = 0;
+    bool low_quality = false;
+    for (int g = 0; g < G; ++g) {
+      const float4 t = gt[g0 + g];
+      const float ta = __fmul_rn(__fsub_rn(t.z, t.x), __fsub_rn(t.w, t.y));
+      const float iou = box_iou_tv(t, ta, a, aa);
+      if (PASS == 1) {
+        atomicMax(&gt_best[g0 + g], __float_as_uint(iou));
+      } else {
+        if (iou > best) {
+          best = iou;
+          mi = g;
+        }
+        low_quality |= __float_as_uint(iou) == gt_best[g0 + g];
+      }
+    }
+    if (PASS == 2) {
+      long long lab;
+      if (G == 0) lab = 0;
+      else if (best >= hi || low_quality) lab = 1;
+      else if (best < lo) lab = 0;
+      else lab = -1;
+      labels[(size_t)b * num_anchors + i] = lab;
+      matched[(size_t)b * num_anchors + i] = mi;
+      fg = lab == 1;
+      bg = lab == 0;
+    }
+  }
+  if (PASS == 2) {
+    fg = __reduce_add_sync(0xffffffffu, fg);
+    bg = __reduce_add_sync(0xffffffffu, bg);
+    if ((threadIdx.x & 31) == 0) {
+      if (fg) atomicAdd(&counts[b * 2 + 0], fg);
+      if (bg) atomicAdd(&counts[b * 2 + 1], bg);
+    }
+  }
+}
+
+// tv rpn.py compute_loss on the sampled anchors, read straight from the per-level head outputs (no concatenated
+// [N * 257,796] tensors, no index / cat autograd nodes).  idx: positions in the reference's flattened order
+// (image, level, pixel, anchor); the first n_pos entries are the foreground samples.
+// out[0] = BCE-with-logits mean over the n_pos + n_neg samples, out[1] = smooth-L1(beta) sum over the foreground / M.
+struct RpnLossLevels {
+  const float* head[RPN_MAX_LEVELS];
+  float* dy[RPN_MAX_LEVELS];
+  int hw[RPN_MAX_LEVELS];
+  int anchor_off[RPN_MAX_LEVELS];
+  int num_levels, A, anchors_per_image;
+};
+
+__device__ __forceinline__ size_t rpn_locate(const RpnLossLevels& lv, long long idx, int& l, int& a) {
+  const int n = (int)(idx / lv.anchors_per_image);
+  const int r = (int)(idx - (long long)n * lv.anchors_per_image);
+  l = 0;
+  while (l + 1 < lv.num_levels && r >= lv.anchor_off[l + 1]) ++l;
+  const int i = r - lv.anchor_off[l];
+  const int row = i / lv.A;
+  a = i - row * lv.A;
+  return ((size_t)n * lv.hw[l] + row) * 16;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(1024)
+rpn_loss_kernel(const RpnLossLevels lv, const long long* __restrict__ sampled, int M, const long long* __restrict__ labels,
+                const int* __restrict__ matched, const float4* __restrict__ anchors, const float4* __restrict__ gt,
+                const int* __restrict__ gt_off, float beta, float* __restrict__ out, const float* __restrict__ g_obj,
+                const float* __restrict__ g_box) {
+  const float inv_m = 1.f / (float)M;
+  float bce = 0.f, box = 0.f;
+  const float go = BWD ? g_obj[0] * inv_m : 0.f, gb = BWD ? g_box[0] * inv_m : 0.f;
+  for (int s = threadIdx.x; s < M; s += blockDim.x) {
+    const long long idx = sampled[s];
+    if (idx < 0) continue;                               // padding of a short sample
+    int l, a;
+    const size_t base = rpn_locate(lv, idx, l, a);
+    const float* h = lv.head[l] + base;
+    const long long lab = labels[idx];
+    const float x = h[a], y = lab >= 1 ? 1.f : 0.f;
+    if (BWD) {
+      lv.dy[l][base + a] = go * (1.f / (1.f + expf(-x)) - y);
+    } else {
+      bce += fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
+    }
+    if (lab >= 1) {
+      // regression target of this anchor (tv _utils.py encode_boxes, weights 1): only the sampled foreground needs it
+      const int n = (int)(idx / lv.anchors_per_image);
+      const float4 an = anchors[idx - (long long)n * lv.anchors_per_image];
+      const float4 t = gt[gt_off[n] + matched[idx]];
+      const float ew = __fsub_rn(an.z, an.x), eh = __fsub_rn(an.w, an.y);
+      const float ecx = __fadd_rn(an.x, __fmul_rn(0.5f, ew)), ecy = __fadd_rn(an.y, __fmul_rn(0.5f, eh));
+      const float gw = __fsub_rn(t.z, t.x), gh = __fsub_rn(t.w, t.y);
+      const float gcx = __fadd_rn(t.x, __fmul_rn(0.5f, gw)), gcy = __fadd_rn(t.y, __fmul_rn(0.5f, gh));
+      const float tv[4] = {__fsub_rn(gcx, ecx) / ew, __fsub_rn(gcy, ecy) / eh, logf(gw / ew), logf(gh / eh)};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float d = h[lv.A + a * 4 + c] - tv[c];
+        const float ad = fabsf(d);
+        if (BWD) {
+          lv.dy[l][base + lv.A + a * 4 + c] = gb * (ad < beta ? d / beta : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)));
+        } else {
+          box += ad < beta ? 0.5f * d * d / beta : ad - 0.5f * beta;
+        }
+      }
+    }
+  }
+  if (!BWD) {
+    __shared__ float s_a[32], s_b[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bce += __shfl_xor_sync(0xffffffffu, bce, o);
+      box += __shfl_xor_sync(0xffffffffu, box, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_a[threadIdx.x >> 5] = bce;
+      s_b[threadIdx.x >> 5] = box;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float ta = 0.f, tb = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        ta += s_a[w];
+        tb += s_b[w];
+      }
+      out[0] = ta * inv_m;
+      out[1] = tb * inv_m;
+    }
+  }
 }
 
 }  // namespace eosvos
@@ -711,6 +965,72 @@ extern "C" int eosvos_roi_match(const float* proposals, const int* count, const 
                                              reinterpret_cast<const float4*>(gt_boxes), gt_labels, gt_off, P, rows,
                                              iou_thresh, reinterpret_cast<float4*>(all_boxes), labels, matched, counts);
   return check_launch("roi_match_kernel");
+}
+
+// Anchor labelling for the RPN losses.  anchors fp32 [A_total][4] (one image's anchors); gt boxes concatenated over the
+// images with gt_off [N + 1]; gt_best: scratch, one unsigned per ground-truth box, ZEROED by the caller; counts int32
+// [N][2] = (#foreground, #background), ZEROED by the caller.
+extern "C" int eosvos_rpn_anchor_match(const float* anchors, int num_anchors, const float* gt_boxes, const int* gt_off,
+                                       int N, float fg_iou, float bg_iou, unsigned* gt_best, long long* labels,
+                                       int* matched, int* counts, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(anchors && gt_boxes && gt_off && gt_best && labels && matched && counts, "rpn_anchor_match: null pointer");
+  dim3 grid((num_anchors + 255) / 256, N);
+  anchor_match_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(anchors), num_anchors,
+                                                   reinterpret_cast<const float4*>(gt_boxes), gt_off, fg_iou, bg_iou,
+                                                   gt_best, labels, matched, counts);
+  EOSVOS_TRY(check_launch("anchor_match_kernel<1>"));
+  anchor_match_kernel<2><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(anchors), num_anchors,
+                                                   reinterpret_cast<const float4*>(gt_boxes), gt_off, fg_iou, bg_iou,
+                                                   gt_best, labels, matched, counts);
+  return check_launch("anchor_match_kernel<2>");
+}
+
+// mode 0: out[2] = (loss_objectness, loss_rpn_box_reg) over the M sampled anchors (entries < 0 are padding; M counts
+// them out: pass the number of REAL samples as `m_norm`).  mode 1: scatter d loss / d head into the ZEROED fp32 buffers
+// dys[l] ([N * hw[l]][16], same layout as heads[l]) scaled by the upstream gradients *g_obj / *g_box (device scalars).
+extern "C" int eosvos_rpn_loss(const void* const* heads, void* const* dys, const int* hw, int num_levels, int A,
+                               const long long* sampled, int num_sampled, const long long* labels, const int* matched,
+                               const float* anchors, const float* gt_boxes, const int* gt_off, float beta, int mode,
+                               float* out, const float* g_obj, const float* g_box, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(num_levels >= 1 && num_levels <= RPN_MAX_LEVELS, "rpn_loss: 1..8 pyramid levels");
+  EOSVOS_REQUIRE(sampled && labels && matched && anchors && gt_boxes && gt_off, "rpn_loss: null pointer");
+  EOSVOS_REQUIRE(num_sampled > 0, "rpn_loss: no sampled anchors");
+  RpnLossLevels lv;
+  lv.num_levels = num_levels;
+  lv.A = A;
+  int off = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    lv.head[l] = reinterpret_cast<const float*>(heads[l]);
+    lv.dy[l] = dys ? reinterpret_cast<float*>(dys[l]) : nullptr;
+    lv.hw[l] = hw[l];
+    lv.anchor_off[l] = off;
+    off += hw[l] * A;
+  }
+  lv.anchors_per_image = off;
+  const float4* an = reinterpret_cast<const float4*>(anchors);
+  const float4* gt = reinterpret_cast<const float4*>(gt_boxes);
+  if (mode == 0) {
+    EOSVOS_REQUIRE(out, "rpn_loss: null output");
+    rpn_loss_kernel<false><<<1, 1024, 0, stream>>>(lv, sampled, num_sampled, labels, matched, an, gt, gt_off, beta, out,
+                                                   nullptr, nullptr);
+    return check_launch("rpn_loss_kernel<fwd>");
+  }
+  EOSVOS_REQUIRE(dys && g_obj && g_box, "rpn_loss: backward needs gradient buffers and upstream gradients");
+  rpn_loss_kernel<true><<<1, 1024, 0, stream>>>(lv, sampled, num_sampled, labels, matched, an, gt, gt_off, beta, nullptr,
+                                                g_obj, g_box);
+  return check_launch("rpn_loss_kernel<bwd>");
+}
+
+extern "C" int eosvos_roi_sample(const long long* labels, const long long* table, int B, int rows, int S, int Pmax,
+                                 void* scratch, long long* inds, long long* pos_in, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(labels && table && inds && pos_in && scratch, "roi_sample: null pointer");
+  EOSVOS_REQUIRE(rows >= 1, "roi_sample: no candidate rows");
+  roi_sample_kernel<<<B, 1024, 0, stream>>>(labels, table, rows, S, Pmax, reinterpret_cast<unsigned char*>(scratch), inds,
+                                            pos_in);
+  return check_launch("roi_sample_kernel");
 }
 
 extern "C" int eosvos_roi_encode(const float* all_boxes, const long long* labels, const long long* matched,

@@ -559,6 +559,55 @@ def roi_match(proposals, count, gt_boxes, gt_labels, gt_off, max_gt, iou_thresh)
     return all_boxes, labels, matched, counts
 
 
+def rpn_anchor_match(anchors, gt_boxes, gt_off, N, fg_iou, bg_iou):
+    """tv rpn.py assign_targets_to_anchors (Matcher with low-quality matches) for all images: -> (labels int64
+    [N, A_total] in {1, 0, -1}, matched int32 [N, A_total], counts int32 [N, 2] = (#fg, #bg))."""
+    dev = anchors.device
+    na = anchors.shape[0]
+    zero = torch.zeros((gt_boxes.shape[0] + 2 * N,), device=dev, dtype=torch.int32)
+    gt_best, counts = zero[:gt_boxes.shape[0]], zero[gt_boxes.shape[0]:].view(N, 2)
+    labels = torch.empty((N, na), device=dev, dtype=torch.int64)
+    matched = torch.empty((N, na), device=dev, dtype=torch.int32)
+    call("eosvos_rpn_anchor_match", _ptr(_chk(anchors, torch.float32, "anchors")), na, _ptr(_chk(gt_boxes, torch.float32)),
+         _ptr(_chk(gt_off, torch.int32)), N, float(fg_iou), float(bg_iou), _ptr(gt_best), _ptr(labels), _ptr(matched),
+         _ptr(counts), _stream())
+    return labels, matched, counts
+
+
+def rpn_loss(head_outs, hw, A, sampled, labels, matched, anchors, gt_boxes, gt_off, beta, dys=None, g_obj=None,
+             g_box=None):
+    """tv rpn.py compute_loss on the sampled anchors straight from the per-level head outputs.  Forward (dys None) ->
+    fp32 [2] = (loss_objectness, loss_rpn_box_reg); backward: scatters d loss / d head into the zeroed `dys`."""
+    L = len(head_outs)
+    ptrs = (ctypes.c_void_p * L)(*[h.data_ptr() for h in head_outs])
+    dptr = (ctypes.c_void_p * L)(*[d.data_ptr() for d in dys]) if dys is not None else None
+    out = torch.empty((2,), device=labels.device, dtype=torch.float32) if dys is None else None
+    call("eosvos_rpn_loss", ptrs, dptr, _int_array(hw), L, int(A), _ptr(_chk(sampled, torch.int64, "sampled")),
+         int(sampled.numel()), _ptr(_chk(labels, torch.int64, "labels")), _ptr(_chk(matched, torch.int32, "matched")),
+         _ptr(anchors), _ptr(gt_boxes), _ptr(gt_off), float(beta), 0 if dys is None else 1, _ptr(out), _ptr(g_obj),
+         _ptr(g_box), _stream())
+    return out
+
+
+def roi_sample(labels, perms, num_pos, num_neg, S, Pmax):
+    """BalancedPositiveNegativeSampler selection for all images in one launch.  labels int64 [B, rows]; perms =
+    [(perm_pos, perm_neg)] per image (the reference's two device `torch.randperm` draws); num_pos / num_neg per image.
+    -> (inds int64 [B,S] ascending rows, -1 padded; pos_in int64 [B,Pmax] positions of the foreground rows, -1 padded)."""
+    import numpy as np
+    dev = labels.device
+    B, rows = labels.shape
+    tab = np.empty((B, 4), dtype=np.int64)
+    for b, ((pp, pn), a, c) in enumerate(zip(perms, num_pos, num_neg)):
+        tab[b] = (pp.data_ptr(), pn.data_ptr(), a, c)
+    table = stager.put(tab, dev)
+    inds = torch.empty((B, S), device=dev, dtype=torch.int64)
+    pos_in = torch.empty((B, Pmax), device=dev, dtype=torch.int64)
+    scratch = torch.empty((B, 2 * rows), device=dev, dtype=torch.uint8)
+    call("eosvos_roi_sample", _ptr(_chk(labels, torch.int64, "labels")), _ptr(table), B, rows, int(S), int(Pmax),
+         _ptr(scratch), _ptr(inds), _ptr(pos_in), _stream())
+    return inds, pos_in
+
+
 def roi_encode(all_boxes, labels, matched, gt_boxes, gt_off, inds, weights):
     """Sampled rows inds int64 [B,S] -> (rois5 [B*S,5], labels [B*S], matched [B*S], regression targets [B*S,4])."""
     dev = all_boxes.device

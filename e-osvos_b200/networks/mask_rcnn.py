@@ -992,15 +992,71 @@ class MaskRCNN(_MaskRCNN):
         return (os.environ.get("EOSVOS_FAST_PATH", "1") != "0" and self.capture is None and self.fixed_proposals is None
                 and self.fixed_detections is None and tuple(float(x) for x in w) == (1.0, 1.0, 1.0, 1.0))
 
-    def _sample_rois_fast(self, padded, count, targets):
-        """tv roi_heads.py:642-678 (select_training_samples: add_gt_proposals, assign_targets_to_proposals,
-        BalancedPositiveNegativeSampler, box_coder.encode) on the padded proposal buffer: one matching kernel, ONE
-        host synchronisation (the foreground / background counts the sampler's `torch.randperm(n)` calls need -- same
-        calls, same order as the reference), one gather / encode kernel.
-        -> dict(rois5 [R,5], labels [R], matched [R], reg [R,4], sizes [per image], pos_in [per image])."""
+    def _pyramid_shapes(self, Hp, Wp):
+        """Spatial sizes of P2..P6 for a padded input (strides 4..32, then the stride-2 sub-sampling of P5)."""
+        shapes = [(Hp // s, Wp // s) for s in (4, 8, 16, 32)]
+        shapes.append(((shapes[-1][0] - 1) // 2 + 1, (shapes[-1][1] - 1) // 2 + 1))
+        return shapes
+
+    def _anchor_match_async(self, image_shape, image_sizes, targets, device):
+        """tv rpn.py assign_targets_to_anchors as two kernels (csrc/rpn.cu::anchor_match_kernel), queued BEFORE the
+        trunk: labels depend only on the anchors and the ground truth.  The foreground / background counts travel to
+        pinned memory asynchronously; `_sample_anchors_fast` picks them up after the trunk has been queued."""
+        rpn = self.rpn
+        N = image_shape[0]
+        feat_shapes = self._pyramid_shapes(image_shape[2], image_shape[3])
+        anchors = self._anchors(image_shape, image_sizes, feat_shapes, device)[0]
+        gt_boxes = torch.cat([t["boxes"].to(torch.float32) for t in targets], 0).contiguous()
+        offs = [0]
+        for t in targets:
+            offs.append(offs[-1] + t["boxes"].shape[0])
+        gt_off = K.stager.put(torch.tensor(offs, dtype=torch.int32), device)
+        m = rpn.proposal_matcher
+        if not m.allow_low_quality_matches:
+            raise NotImplementedError("RPN matcher without low-quality matches")
+        labels, matched, counts = K.rpn_anchor_match(anchors, gt_boxes, gt_off, N, m.high_threshold, m.low_threshold)
+        pin = getattr(self, "_anchor_count_pin", None)
+        if pin is None or pin.shape[0] != N:
+            pin = self._anchor_count_pin = torch.empty((N, 2), dtype=torch.int32).pin_memory()
+        pin.copy_(counts, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return dict(labels=labels, matched=matched, anchors=anchors, gt_boxes=gt_boxes, gt_off=gt_off, pin=pin, ev=ev)
+
+    def _sample_anchors_fast(self, am):
+        """tv rpn.py fg_bg_sampler (BalancedPositiveNegativeSampler(256, 0.5)): the reference's two `torch.randperm`
+        draws per image, then one selection kernel -> int64 positions of the sampled anchors in the flattened
+        (image, level, pixel, anchor) order."""
+        sampler = self.rpn.fg_bg_sampler
+        labels = am["labels"]
+        device = labels.device
+        am["ev"].synchronize()            # queued before the trunk: long done
+        S = sampler.batch_size_per_image
+        Pmax = int(S * sampler.positive_fraction)
+        perms, num_pos_list, num_neg_list = [], [], []
+        for npos, nneg in am["pin"].tolist():
+            num_pos = min(npos, Pmax)
+            num_neg = min(nneg, S - num_pos)
+            perms.append((torch.randperm(npos, device=device), torch.randperm(nneg, device=device)))
+            num_pos_list.append(num_pos)
+            num_neg_list.append(num_neg)
+        inds, _ = K.roi_sample(labels, perms, num_pos_list, num_neg_list, S, Pmax)
+        A_total = labels.shape[1]
+        sizes = [a + b for a, b in zip(num_pos_list, num_neg_list)]
+        if all(sz == S for sz in sizes):
+            key = (len(sizes), A_total, str(device))
+            if getattr(self, "_anchor_base_key", None) != key:
+                self._anchor_base = (torch.arange(len(sizes), device=device, dtype=torch.int64) * A_total)[:, None]
+                self._anchor_base_key = key
+            return (inds + self._anchor_base).reshape(-1)
+        return torch.cat([inds[i, :sz] + i * A_total for i, sz in enumerate(sizes)], 0)
+
+    def _match_rois_fast(self, padded, count, targets):
+        """Phase 1 of tv roi_heads.py:642-678 (add_gt_proposals + assign_targets_to_proposals) on the padded proposal
+        buffer: one kernel, then an asynchronous read-back of the foreground / background counts into pinned memory.
+        Nothing waits here, so the caller can do host work (RPN anchor targets) until `_sample_rois_fast` needs them."""
         rh = self.roi_heads
         device = padded.device
-        B, P = padded.shape[0], padded.shape[1]
         gt_boxes = [t["boxes"].to(torch.float32) for t in targets]
         gt_labels = [t["labels"] for t in targets]
         Gs = [g.shape[0] for g in gt_boxes]
@@ -1014,45 +1070,57 @@ class MaskRCNN(_MaskRCNN):
         if m.high_threshold != m.low_threshold or m.allow_low_quality_matches:
             raise NotImplementedError("RoI matcher with a between-threshold band")
         all_boxes, labels, matched, counts2 = K.roi_match(padded, count, gt_cat, gl_cat, gt_off, max(Gs), m.high_threshold)
-        cnt = counts2.tolist()                                   # the one host sync on the main stream
+        B = padded.shape[0]
+        pin = getattr(self, "_count_pin", None)
+        if pin is None or pin.shape[0] != B:
+            pin = self._count_pin = torch.empty((B, 2), dtype=torch.int32).pin_memory()
+        pin.copy_(counts2, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return dict(all_boxes=all_boxes, labels=labels, matched=matched, gt_cat=gt_cat, gt_off=gt_off, pin=pin, ev=ev)
+
+    def _sample_rois_fast(self, mt):
+        """Phase 2: BalancedPositiveNegativeSampler + box_coder.encode.  ONE host synchronisation (the counts the
+        sampler's `torch.randperm(n)` calls need -- same calls, same order as the reference), then one selection kernel
+        for all images and one gather / encode kernel.
+        -> dict(rois5 [R,5], labels [R], matched [R], reg [R,4], sizes [per image], pos [positions of positives])."""
+        rh = self.roi_heads
+        labels, all_boxes, matched = mt["labels"], mt["all_boxes"], mt["matched"]
+        device = labels.device
+        mt["ev"].synchronize()                                   # the one host sync on the main stream
+        cnt = mt["pin"].tolist()
         sampler = rh.fg_bg_sampler
         S = sampler.batch_size_per_image
-        inds = []
-        num_pos_list = []
-        for i, (npos, nneg) in enumerate(cnt):
-            l = labels[i]
-            positive = torch.nonzero_static(l >= 1, size=npos).squeeze(1)
-            negative = torch.nonzero_static(l == 0, size=nneg).squeeze(1)
-            num_pos = min(npos, int(S * sampler.positive_fraction))
+        Pmax = int(S * sampler.positive_fraction)
+        perms, num_pos_list, num_neg_list = [], [], []
+        for npos, nneg in cnt:
+            num_pos = min(npos, Pmax)
             num_neg = min(nneg, S - num_pos)
-            perm1 = torch.randperm(npos, device=device)[:num_pos]
-            perm2 = torch.randperm(nneg, device=device)[:num_neg]
-            mask = torch.zeros_like(l, dtype=torch.bool)
-            mask[positive[perm1]] = True
-            mask[negative[perm2]] = True
-            inds.append(torch.nonzero_static(mask, size=num_pos + num_neg).squeeze(1))
+            perms.append((torch.randperm(npos, device=device), torch.randperm(nneg, device=device)))
             num_pos_list.append(num_pos)
-        sizes = [int(x.shape[0]) for x in inds]
+            num_neg_list.append(num_neg)
+        inds, pos_in = K.roi_sample(labels, perms, num_pos_list, num_neg_list, S, Pmax)
+        sizes = [a + b for a, b in zip(num_pos_list, num_neg_list)]
         wts = rh.box_coder.weights
-        if all(sz == sizes[0] for sz in sizes):
-            rois5, lab_c, m_c, reg_c = K.roi_encode(all_boxes, labels, matched, gt_cat, gt_off, torch.stack(inds).contiguous(), wts)
+        if all(sz == S for sz in sizes):
+            rois5, lab_c, m_c, reg_c = K.roi_encode(all_boxes, labels, matched, mt["gt_cat"], mt["gt_off"], inds, wts)
+            pos = torch.cat([pos_in[i, :n] + i * S for i, n in enumerate(num_pos_list)], 0)
         else:
-            parts = []
-            for i, ind in enumerate(inds):
-                r5, lc, mc, rc = K.roi_encode(all_boxes[i:i + 1], labels[i:i + 1], matched[i:i + 1], gt_cat, gt_off[i:i + 2],
-                                              ind[None].contiguous(), wts)
+            parts, pos_parts, off = [], [], 0
+            for i, sz in enumerate(sizes):
+                r5, lc, mc, rc = K.roi_encode(all_boxes[i:i + 1], labels[i:i + 1], matched[i:i + 1], mt["gt_cat"],
+                                              mt["gt_off"][i:i + 2], inds[i:i + 1, :sz].contiguous(), wts)
                 r5[:, 0] = i
                 parts.append((r5, lc, mc, rc))
+                pos_parts.append(pos_in[i, :num_pos_list[i]] + off)
+                off += sz
             rois5, lab_c, m_c, reg_c = [torch.cat(x, 0) for x in zip(*parts)]
-        pos_in, off = [], 0
-        for sz, npos in zip(sizes, num_pos_list):
-            pos_in.append(torch.nonzero_static(lab_c[off:off + sz] > 0, size=npos).squeeze(1) + off)
-            off += sz
-        return dict(rois5=rois5, labels=lab_c, matched=m_c, reg=reg_c, sizes=sizes, pos_in=pos_in)
+            pos = torch.cat(pos_parts, 0)
+        return dict(rois5=rois5, labels=lab_c, matched=m_c, reg=reg_c, sizes=sizes, pos=pos)
 
-    def _roi_heads_train_fast(self, feats, padded, count, targets):
+    def _roi_heads_train_fast(self, feats, mt, targets):
         rh = self.roi_heads
-        smp = self._sample_rois_fast(padded, count, targets)
+        smp = self._sample_rois_fast(mt)
         rois5, lab_c, reg_c = smp["rois5"], smp["labels"], smp["reg"]
         S = rh.fg_bg_sampler.batch_size_per_image
         graphed_box = (self.use_cuda_graphs and torch.is_grad_enabled() and os.environ.get("EOSVOS_GRAPH_BOX", "1") != "0"
@@ -1064,7 +1132,7 @@ class MaskRCNN(_MaskRCNN):
             nc = rh.box_predictor.cls_score.weight.shape[0]
             loss_classifier, loss_box_reg = self._fastrcnn_loss_static(o[:, :nc], o[:, nc:nc + 4 * nc], lab_c, reg_c)
         losses = dict(loss_classifier=loss_classifier, loss_box_reg=loss_box_reg)
-        pos = torch.cat(smp["pos_in"], 0)
+        pos = smp["pos"]
         n_mask = int(pos.shape[0])
         self.last_num_positives = n_mask
         kind = rh.maskrcnn_loss
@@ -1429,18 +1497,26 @@ class MaskRCNN(_MaskRCNN):
         image_shape = (B, 3, Hp, Wp)
 
         grad_ctx = torch.enable_grad() if self.training else torch.no_grad()
+        fast_train = (self.training and fast and self.use_cuda_graphs and os.environ.get("EOSVOS_GRAPH_HEAD", "2") == "2")
         with grad_ctx:
+            if fast_train:
+                am = self._anchor_match_async(image_shape, image_sizes, targets_t, device)
             feats = pre_feats if pre is not None else self._backbone(x8)
             feats, head_outs = feats[:5], (feats[5:] if len(feats) > 5 else None)
-            if self.training and fast and head_outs is not None and head_outs[0].dtype == torch.float32:
+            if fast_train and head_outs is not None and head_outs[0].dtype == torch.float32:
                 # statically shaped proposal / sampling pipeline: ONE host sync (RoI sampler counts) per iteration
-                early = self._rpn_early_targets(feats, image_shape, image_sizes, targets_t)
+                # the proposal kernels and the RoI matching only need the trunk: queue them first, label the anchors
+                # on the host / side stream meanwhile (RNG order unchanged: RPN sampler, then RoI sampler)
                 padded, count = self._rpn_fast(feats, image_shape, image_sizes, head_outs, self.rpn.post_nms_top_n())
                 self._last_padded = (padded, count, padded.shape[1])
-                det_losses = self._roi_heads_train_fast(feats, padded, count, targets_t)
-                objectness, pred_bbox_deltas, _, _ = self._rpn_cat_outputs(feats, head_outs)
+                mt = self._match_rois_fast(padded, count, targets_t)
+                sampled = self._sample_anchors_fast(am)
+                det_losses = self._roi_heads_train_fast(feats, mt, targets_t)
                 raw = dict(det_losses)
-                raw.update(self._rpn_losses(early, objectness, pred_bbox_deltas))
+                lo, lb = ops.rpn_loss(head_outs, [f.shape[1] * f.shape[2] for f in feats],
+                                      self.rpn.head.cls_logits.weight.shape[0], sampled, am["labels"], am["matched"],
+                                      am["anchors"], am["gt_boxes"], am["gt_off"])
+                raw.update({"loss_objectness": lo, "loss_rpn_box_reg": lb})
                 losses = {n: l for n, l in raw.items() if l.requires_grad}
                 return sum([l for l in losses.values()]), losses
             proposals, rpn_losses = self._rpn(feats, image_shape, image_sizes, targets_t, head_outs)

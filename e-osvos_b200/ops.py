@@ -644,3 +644,36 @@ class MaskLossWeightedFn(torch.autograd.Function):
 
 def mask_loss_weighted(logits, labels, targets, weights):
     return MaskLossWeightedFn.apply(logits, labels, targets, weights)
+
+
+# --------------------------------------------------------------------------------------------
+# RPN losses on the sampled anchors (tv rpn.py compute_loss), straight from the per-level head outputs
+# --------------------------------------------------------------------------------------------
+class RpnLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sampled, labels, matched, anchors, gt_boxes, gt_off, hw, A, beta, *head_outs):
+        heads = [h.detach() for h in head_outs]
+        out = K.rpn_loss(heads, hw, A, sampled, labels, matched, anchors, gt_boxes, gt_off, beta)
+        ctx.save_for_backward(sampled, labels, matched, anchors, gt_boxes, gt_off, *heads)
+        ctx.cfg = (list(hw), A, beta)
+        return out[0], out[1]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_obj, g_box):
+        sampled, labels, matched, anchors, gt_boxes, gt_off, *heads = ctx.saved_tensors
+        hw, A, beta = ctx.cfg
+        dys = [K.zero_pool.take(tuple(h.shape), h.device) for h in heads]
+        zero = None
+        if g_obj is None or g_box is None:
+            zero = torch.zeros((), device=labels.device)
+        K.rpn_loss(heads, hw, A, sampled, labels, matched, anchors, gt_boxes, gt_off, beta, dys=dys,
+                   g_obj=(g_obj if g_obj is not None else zero).contiguous(),
+                   g_box=(g_box if g_box is not None else zero).contiguous())
+        return (None,) * 9 + tuple(dys)
+
+
+def rpn_loss(head_outs, hw, A, sampled, labels, matched, anchors, gt_boxes, gt_off, beta=1.0 / 9):
+    """(loss_objectness, loss_rpn_box_reg) of tv rpn.py compute_loss.  sampled: int64 positions in the flattened
+    (image, level, pixel, anchor) order, -1 = padding (the mean runs over `sampled.numel()`: pass exactly the samples)."""
+    return RpnLossFn.apply(sampled, labels, matched, anchors, gt_boxes, gt_off, hw, A, beta, *head_outs)

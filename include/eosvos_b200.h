@@ -132,6 +132,15 @@ int eosvos_det_top1(const float* head, const float* proposals, int B, int R, int
 int eosvos_roi_match(const float* proposals, const int* count, const float* gt_boxes, const long long* gt_labels,
                      const int* gt_off, int B, int P, int max_gt, float iou_thresh, float* all_boxes, long long* labels,
                      long long* matched, int* counts, eosvos_stream_t stream);
+int eosvos_rpn_anchor_match(const float* anchors, int num_anchors, const float* gt_boxes, const int* gt_off, int N,
+                            float fg_iou, float bg_iou, unsigned* gt_best, long long* labels, int* matched, int* counts,
+                            eosvos_stream_t stream);
+int eosvos_rpn_loss(const void* const* heads, void* const* dys, const int* hw, int num_levels, int A,
+                    const long long* sampled, int num_sampled, const long long* labels, const int* matched,
+                    const float* anchors, const float* gt_boxes, const int* gt_off, float beta, int mode, float* out,
+                    const float* g_obj, const float* g_box, eosvos_stream_t stream);
+int eosvos_roi_sample(const long long* labels, const long long* table, int B, int rows, int S, int Pmax, void* scratch,
+                      long long* inds, long long* pos_in, eosvos_stream_t stream);
 int eosvos_roi_encode(const float* all_boxes, const long long* labels, const long long* matched, const float* gt_boxes,
                       const int* gt_off, const long long* inds, int B, int S, int rows_per_image,
                       const float* coder_weights4, float* rois5, long long* out_labels, long long* out_matched,

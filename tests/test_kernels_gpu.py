@@ -699,3 +699,75 @@ def test_roi_match_and_encode_match_torchvision():
         got = reg[b * 32:(b + 1) * 32].cpu()
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
         assert torch.equal(rois5[b * 32:(b + 1) * 32, 1:].cpu(), pb) and (rois5[b * 32:(b + 1) * 32, 0] == b).all()
+
+
+def test_rpn_anchor_match_sampler_and_loss_match_torchvision():
+    """anchor_match_kernel (tv rpn.py assign_targets_to_anchors: box_iou + Matcher(0.7, 0.3, low-quality matches)),
+    roi_sample_kernel as the RPN sampler over 257,796 anchors per image, and rpn_loss_kernel (forward + gradient, with
+    the regression targets encoded on the fly) against the torchvision / torch formulation on concatenated tensors."""
+    import torchvision
+    from torchvision.models.detection._utils import BoxCoder, Matcher
+    from eosvos_b200 import ops
+    N, A = 2, 3
+    feat_shapes = [(192, 336), (96, 168), (48, 84), (24, 42), (12, 21)]
+    heads, anchors, image_sizes, _ = _rpn_case(N, feat_shapes, 6)
+    heads = [h.requires_grad_(True) for h in heads]
+    hw = [h * w for h, w in feat_shapes]
+    gts = [torch.tensor([[300.0, 200.0, 700.0, 520.0]]), torch.tensor([[50.0, 60.0, 180.0, 400.0], [900.0, 100.0, 1300.0, 700.0]])]
+    gt_cat = torch.cat(gts).to(dev())
+    gt_off = torch.tensor([0, 1, 3], dtype=torch.int32, device=dev())
+    labels, matched, counts = K().rpn_anchor_match(anchors, gt_cat, gt_off, N, 0.7, 0.3)
+    matcher = Matcher(0.7, 0.3, allow_low_quality_matches=True)
+    ref_labels, ref_reg = [], []
+    coder = BoxCoder((1.0, 1.0, 1.0, 1.0))
+    for b in range(N):
+        g = gts[b].to(dev())
+        m = matcher(torchvision.ops.box_iou(g, anchors))
+        lab = (m >= 0).to(torch.int64)
+        lab[m == Matcher.BELOW_LOW_THRESHOLD] = 0
+        lab[m == Matcher.BETWEEN_THRESHOLDS] = -1
+        assert torch.equal(labels[b], lab)
+        fg = lab == 1
+        assert torch.equal(matched[b][fg].to(torch.int64), m[fg])
+        assert counts[b].tolist() == [int(fg.sum()), int((lab == 0).sum())]
+        ref_labels.append(lab)
+        ref_reg.append(coder.encode_single(g[m.clamp(min=0)], anchors))
+    # sampler: the reference's where(mask) of randperm draws
+    gen = torch.Generator().manual_seed(2)
+    perms, npos_l, nneg_l, want = [], [], [], []
+    A_total = anchors.shape[0]
+    for b in range(N):
+        npos, nneg = counts[b].tolist()
+        num_pos = min(npos, 128)
+        num_neg = min(nneg, 256 - num_pos)
+        pp, pn = torch.randperm(npos, generator=gen).to(dev()), torch.randperm(nneg, generator=gen).to(dev())
+        perms.append((pp, pn))
+        npos_l.append(num_pos)
+        nneg_l.append(num_neg)
+        positive = torch.where(ref_labels[b] >= 1)[0]
+        negative = torch.where(ref_labels[b] == 0)[0]
+        mask = torch.zeros(A_total, dtype=torch.bool, device=dev())
+        mask[positive[pp[:num_pos]]] = True
+        mask[negative[pn[:num_neg]]] = True
+        want.append(torch.where(mask)[0])
+    inds, pos_in = K().roi_sample(labels, perms, npos_l, nneg_l, 256, 128)
+    for b in range(N):
+        sz = npos_l[b] + nneg_l[b]
+        assert torch.equal(inds[b, :sz], want[b]) and (inds[b, sz:] == -1).all()
+        assert torch.equal(pos_in[b, :npos_l[b]], torch.where(ref_labels[b][want[b]] >= 1)[0])
+    sampled = torch.cat([want[b] + b * A_total for b in range(N)])
+    lo, lb = ops.rpn_loss(heads, hw, A, sampled, labels, matched, anchors, gt_cat, gt_off)
+    (lo * 1.3 + lb * 0.7).backward()
+    got = [h.grad.clone() for h in heads]
+    ref_heads = [h.detach().clone().requires_grad_(True) for h in heads]
+    obj = torch.cat([h[:, :A].reshape(N, -1, 1) for h in ref_heads], 1).flatten(0, -2)
+    dlt = torch.cat([h[:, A:5 * A].reshape(N, -1, 4) for h in ref_heads], 1).flatten(0, -2)
+    lab_c = torch.cat(ref_labels).float()
+    reg_c = torch.cat(ref_reg)
+    pos = sampled[lab_c[sampled] >= 1]
+    rb = F.smooth_l1_loss(dlt[pos], reg_c[pos], beta=1 / 9, reduction="sum") / sampled.numel()
+    ro = F.binary_cross_entropy_with_logits(obj.flatten()[sampled], lab_c[sampled])
+    (ro * 1.3 + rb * 0.7).backward()
+    assert torch.allclose(lo, ro, rtol=1e-5) and torch.allclose(lb, rb, rtol=1e-4)
+    for a_, b_ in zip(got, ref_heads):
+        assert torch.allclose(a_, b_.grad, rtol=1e-3, atol=1e-8)

