@@ -54,6 +54,7 @@ SIGNATURES = {
     "eosvos_roi_match": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "eosvos_rpn_anchor_match": [_P, _I, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P],
     "eosvos_rpn_loss": [_P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P],
+    "eosvos_roi_sample_scratch_bytes": [_I, _I],
     "eosvos_roi_sample": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
     "eosvos_roi_encode": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "eosvos_meta_update_chunk_elems": [],
@@ -76,7 +77,7 @@ SIGNATURES = {
     "eosvos_colsum": [_P, _P, _L, _I, _F, _P],
 }
 _RESTYPES = {"eosvos_nms_scratch_bytes": c_longlong, "eosvos_rpn_scratch_bytes": c_longlong,
-             "eosvos_rpn_scratch_zero_bytes": c_longlong, "eosvos_last_error": c_char_p, "eosvos_launch_count": ctypes.c_ulonglong}
+             "eosvos_rpn_scratch_zero_bytes": c_longlong, "eosvos_roi_sample_scratch_bytes": c_longlong, "eosvos_last_error": c_char_p, "eosvos_launch_count": ctypes.c_ulonglong}
 
 
 class EosvosError(RuntimeError):

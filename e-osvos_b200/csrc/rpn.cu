@@ -518,102 +518,173 @@ roi_match_kernel(const float4* __restrict__ props, const int* __restrict__ count
   }
 }
 
-// tv _utils.py BalancedPositiveNegativeSampler for one image per CTA, given the two `torch.randperm` draws the
-// reference makes (perm_pos over the foreground candidates, perm_neg over the background candidates, in index order):
+// tv _utils.py BalancedPositiveNegativeSampler given the two `torch.randperm` draws the reference makes per image
+// (perm_pos over the foreground candidates, perm_neg over the background candidates, both in row order):
 // selected = { fg[perm_pos[j]] : j < num_pos } U { bg[perm_neg[j]] : j < num_neg }, emitted in ascending row order
 // (== torch.where(mask) of the reference), plus the positions of the foreground rows inside that list.
-// table int64 [B][4] = (perm_pos ptr, perm_neg ptr, num_pos, num_neg).  inds int64 [B][S] (-1 padded),
-// pos_in int64 [B][Pmax] (-1 padded).  flags: scratch, 2 * rows bytes per image (global memory: the RPN sampler runs
-// this over 257,796 anchors per image).
-__global__ void __launch_bounds__(1024)
-roi_sample_kernel(const long long* __restrict__ labels, const long long* __restrict__ table, int rows, int S, int Pmax,
-                  unsigned char* __restrict__ flags, long long* __restrict__ inds, long long* __restrict__ pos_in) {
-  unsigned char* flag_pos = flags + (size_t)blockIdx.x * 2 * rows;   // [rows]: rank r of the foreground candidates is drawn
-  unsigned char* flag_neg = flag_pos + rows;                         // [rows]
-  __shared__ int s_warp[32];
-  __shared__ int s_carry[3];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// table int64 [B][4] = (perm_pos ptr, perm_neg ptr, num_pos, num_neg).  Three passes (the RPN runs this over 257,796
+// anchors per image): per-chunk candidate counts -> ranks + selection bitmap -> compaction by one CTA per image.
+constexpr int SMP_CHUNK = 4096;
+
+__global__ void __launch_bounds__(256)
+sample_count_kernel(const long long* __restrict__ labels, int rows, int nchunks, int* __restrict__ chunk_cnt) {
+  const int c = blockIdx.x, b = blockIdx.y;
   const long long* lab = labels + (size_t)b * rows;
+  int fg = 0, bg = 0;
+  const int end = min((c + 1) * SMP_CHUNK, rows);
+  for (int i = c * SMP_CHUNK + threadIdx.x; i < end; i += 256) {
+    const long long l = lab[i];
+    fg += l >= 1;
+    bg += l == 0;
+  }
+  fg = __reduce_add_sync(0xffffffffu, fg);
+  bg = __reduce_add_sync(0xffffffffu, bg);
+  __shared__ int s_f[8], s_b[8];
+  if ((threadIdx.x & 31) == 0) {
+    s_f[threadIdx.x >> 5] = fg;
+    s_b[threadIdx.x >> 5] = bg;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int f = 0, g = 0;
+    for (int w = 0; w < 8; ++w) {
+      f += s_f[w];
+      g += s_b[w];
+    }
+    chunk_cnt[((size_t)b * nchunks + c) * 2 + 0] = f;
+    chunk_cnt[((size_t)b * nchunks + c) * 2 + 1] = g;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sample_select_kernel(const long long* __restrict__ labels, const long long* __restrict__ table, int rows, int nchunks,
+                     const int* __restrict__ chunk_cnt, unsigned* __restrict__ selbits) {
+  const int c = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long* lab = labels + (size_t)b * rows;
+  __shared__ unsigned fgsel[SMP_CHUNK / 32], bgsel[SMP_CHUNK / 32];   // drawn ranks that fall into this chunk
+  __shared__ int s_f[8], s_b[8];
+  for (int i = tid; i < SMP_CHUNK / 32; i += 256) {
+    fgsel[i] = 0;
+    bgsel[i] = 0;
+  }
+  int pre_f = 0, pre_b = 0;
+  for (int k = 0; k < c; ++k) {
+    pre_f += chunk_cnt[((size_t)b * nchunks + k) * 2 + 0];
+    pre_b += chunk_cnt[((size_t)b * nchunks + k) * 2 + 1];
+  }
+  __syncthreads();
   const long long* perm_pos = reinterpret_cast<const long long*>(table[b * 4 + 0]);
   const long long* perm_neg = reinterpret_cast<const long long*>(table[b * 4 + 1]);
   const int num_pos = (int)table[b * 4 + 2], num_neg = (int)table[b * 4 + 3];
-  for (int i = tid; i < rows; i += blockDim.x) {
-    flag_pos[i] = 0;
-    flag_neg[i] = 0;
+  for (int j = tid; j < num_pos; j += 256) {
+    const long long r = perm_pos[j] - pre_f;
+    if (r >= 0 && r < SMP_CHUNK) atomicOr(&fgsel[r >> 5], 1u << (r & 31));
   }
+  for (int j = tid; j < num_neg; j += 256) {
+    const long long r = perm_neg[j] - pre_b;
+    if (r >= 0 && r < SMP_CHUNK) atomicOr(&bgsel[r >> 5], 1u << (r & 31));
+  }
+  // every warp owns SMP_CHUNK / 8 consecutive rows: first its candidate counts, then ranks by ballots
+  constexpr int PER_WARP = SMP_CHUNK / 8;
+  const int w0 = c * SMP_CHUNK + warp * PER_WARP;
+  int cf = 0, cb = 0;
+  for (int o = 0; o < PER_WARP; o += 32) {
+    const int i = w0 + o + lane;
+    const long long l = i < rows ? lab[i] : -1;
+    cf += __popc(__ballot_sync(0xffffffffu, l >= 1));
+    cb += __popc(__ballot_sync(0xffffffffu, l == 0));
+  }
+  if (lane == 0) {
+    s_f[warp] = cf;
+    s_b[warp] = cb;
+  }
+  __syncthreads();
+  int rf = 0, rb = 0;                                   // chunk-local rank of the warp's first candidate
+  for (int w = 0; w < warp; ++w) {
+    rf += s_f[w];
+    rb += s_b[w];
+  }
+  const unsigned below = (1u << lane) - 1u;
+  for (int o = 0; o < PER_WARP; o += 32) {
+    const int i = w0 + o + lane;
+    const long long l = i < rows ? lab[i] : -1;
+    const unsigned mf = __ballot_sync(0xffffffffu, l >= 1), mb = __ballot_sync(0xffffffffu, l == 0);
+    bool sel = false;
+    if (l >= 1) {
+      const int r = rf + __popc(mf & below);
+      sel = (fgsel[r >> 5] >> (r & 31)) & 1u;
+    } else if (l == 0) {
+      const int r = rb + __popc(mb & below);
+      sel = (bgsel[r >> 5] >> (r & 31)) & 1u;
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0 && w0 + o < rows) selbits[(size_t)b * ((rows + 31) / 32) + (w0 + o) / 32] = word;
+    rf += __popc(mf);
+    rb += __popc(mb);
+  }
+}
+
+// one CTA per image: ascending rows of the set bits -> inds [S] (-1 padded); foreground positions -> pos_in [Pmax]
+__global__ void __launch_bounds__(1024)
+sample_compact_kernel(const long long* __restrict__ labels, const unsigned* __restrict__ selbits, int rows, int S,
+                      int Pmax, long long* __restrict__ inds, long long* __restrict__ pos_in) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int words = (rows + 31) / 32;
+  const int per = (words + blockDim.x - 1) / blockDim.x;
+  const unsigned* bits = selbits + (size_t)b * words;
+  const long long* lab = labels + (size_t)b * rows;
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
   for (int i = tid; i < S; i += blockDim.x) inds[(size_t)b * S + i] = -1;
   for (int i = tid; i < Pmax; i += blockDim.x) pos_in[(size_t)b * Pmax + i] = -1;
-  if (tid < 3) s_carry[tid] = 0;
-  __syncthreads();
-  for (int j = tid; j < num_pos; j += blockDim.x) flag_pos[perm_pos[j]] = 1;
-  for (int j = tid; j < num_neg; j += blockDim.x) flag_neg[perm_neg[j]] = 1;
-  __syncthreads();
-  // one pass over the rows in blocks of blockDim: running ranks among fg / bg candidates, running output position
-  for (int base = 0; base < rows; base += blockDim.x) {
-    const int i = base + tid;
-    const long long l = i < rows ? lab[i] : -1;
-    const int is_fg = l >= 1, is_bg = l == 0;
-    // three block-wide exclusive scans: fg rank, bg rank, output slot
-    int v[3] = {is_fg, is_bg, 0};
-    int exc[3];
-    for (int q = 0; q < 2; ++q) {
-      int inc = v[q];
+  int cnt = 0;
+  for (int k = 0; k < per; ++k) {
+    const int wd = tid * per + k;
+    if (wd < words) cnt += __popc(bits[wd]);
+  }
+  int inc = cnt;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (lane == 31) s_warp[warp] = inc;
-      __syncthreads();
-      int wb = 0;
-      for (int w = 0; w < warp; ++w) wb += s_warp[w];
-      exc[q] = s_carry[q] + wb + inc - v[q];
-      __syncthreads();
-      if (tid == blockDim.x - 1) s_carry[q] = exc[q] + v[q];
-      __syncthreads();
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  int slot = inc - cnt;
+  for (int w = 0; w < warp; ++w) slot += s_warp[w];
+  for (int k = 0; k < per; ++k) {
+    const int wd = tid * per + k;
+    if (wd >= words) break;
+    unsigned m = bits[wd];
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      if (slot < S) inds[(size_t)b * S + slot] = (long long)wd * 32 + bit;
+      ++slot;
     }
-    const int sel = (is_fg && flag_pos[exc[0]]) || (is_bg && flag_neg[exc[1]]);
-    v[2] = sel;
-    {
-      int inc = sel;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (lane == 31) s_warp[warp] = inc;
-      __syncthreads();
-      int wb = 0;
-      for (int w = 0; w < warp; ++w) wb += s_warp[w];
-      exc[2] = s_carry[2] + wb + inc - sel;
-      __syncthreads();
-      if (tid == blockDim.x - 1) s_carry[2] = exc[2] + sel;
-      __syncthreads();
-    }
-    if (sel && exc[2] < S) inds[(size_t)b * S + exc[2]] = i;
   }
   __syncthreads();
-  // positions of the foreground rows inside the sampled list (second, small compaction; S <= 1024 per round)
-  if (tid == 0) s_carry[0] = 0;
+  if (tid == 0) s_carry = 0;
   __syncthreads();
   for (int base = 0; base < S; base += blockDim.x) {
     const int j = base + tid;
     const long long r = j < S ? inds[(size_t)b * S + j] : -1;
     const int f = r >= 0 && lab[r] >= 1;
-    int inc = f;
+    int in2 = f;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
+      const int t = __shfl_up_sync(0xffffffffu, in2, o);
+      if (lane >= o) in2 += t;
     }
-    if (lane == 31) s_warp[warp] = inc;
+    if (lane == 31) s_warp[warp] = in2;
     __syncthreads();
     int wb = 0;
     for (int w = 0; w < warp; ++w) wb += s_warp[w];
-    const int slot = s_carry[0] + wb + inc - f;
+    const int sl = s_carry + wb + in2 - f;
     __syncthreads();
-    if (tid == blockDim.x - 1) s_carry[0] = slot + f;
-    if (f && slot < Pmax) pos_in[(size_t)b * Pmax + slot] = j;
+    if (tid == blockDim.x - 1) s_carry = sl + f;
+    if (f && sl < Pmax) pos_in[(size_t)b * Pmax + sl] = j;
     __syncthreads();
   }
 }
@@ -1023,14 +1094,26 @@ extern "C" int eosvos_rpn_loss(const void* const* heads, void* const* dys, const
   return check_launch("rpn_loss_kernel<bwd>");
 }
 
+extern "C" long long eosvos_roi_sample_scratch_bytes(int B, int rows) {
+  const long long nchunks = (rows + SMP_CHUNK - 1) / SMP_CHUNK;
+  return (long long)B * nchunks * 2 * 4 + (long long)B * ((rows + 31) / 32) * 4 + 64;
+}
+
 extern "C" int eosvos_roi_sample(const long long* labels, const long long* table, int B, int rows, int S, int Pmax,
                                  void* scratch, long long* inds, long long* pos_in, eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   EOSVOS_REQUIRE(labels && table && inds && pos_in && scratch, "roi_sample: null pointer");
   EOSVOS_REQUIRE(rows >= 1, "roi_sample: no candidate rows");
-  roi_sample_kernel<<<B, 1024, 0, stream>>>(labels, table, rows, S, Pmax, reinterpret_cast<unsigned char*>(scratch), inds,
-                                            pos_in);
-  return check_launch("roi_sample_kernel");
+  const int nchunks = (rows + SMP_CHUNK - 1) / SMP_CHUNK;
+  int* chunk_cnt = reinterpret_cast<int*>(scratch);
+  unsigned* selbits = reinterpret_cast<unsigned*>(chunk_cnt + (size_t)B * nchunks * 2);
+  dim3 grid(nchunks, B);
+  sample_count_kernel<<<grid, 256, 0, stream>>>(labels, rows, nchunks, chunk_cnt);
+  EOSVOS_TRY(check_launch("sample_count_kernel"));
+  sample_select_kernel<<<grid, 256, 0, stream>>>(labels, table, rows, nchunks, chunk_cnt, selbits);
+  EOSVOS_TRY(check_launch("sample_select_kernel"));
+  sample_compact_kernel<<<B, 1024, 0, stream>>>(labels, selbits, rows, S, Pmax, inds, pos_in);
+  return check_launch("sample_compact_kernel");
 }
 
 extern "C" int eosvos_roi_encode(const float* all_boxes, const long long* labels, const long long* matched,

@@ -602,7 +602,7 @@ def roi_sample(labels, perms, num_pos, num_neg, S, Pmax):
     table = stager.put(tab, dev)
     inds = torch.empty((B, S), device=dev, dtype=torch.int64)
     pos_in = torch.empty((B, Pmax), device=dev, dtype=torch.int64)
-    scratch = torch.empty((B, 2 * rows), device=dev, dtype=torch.uint8)
+    scratch = torch.empty((_lib.load().eosvos_roi_sample_scratch_bytes(B, rows),), device=dev, dtype=torch.uint8)
     call("eosvos_roi_sample", _ptr(_chk(labels, torch.int64, "labels")), _ptr(table), B, rows, int(S), int(Pmax),
          _ptr(scratch), _ptr(inds), _ptr(pos_in), _stream())
     return inds, pos_in

@@ -32,9 +32,19 @@ class MetaModel:
     # ---- meta_model.py:62-71
     def detach_param_groups(self):
         for _, module, n_p, p in self.param_groups():
+            if p.grad_fn is None and not isinstance(p, nn.Parameter):
+                continue                    # already a plain leaf (the fused evaluation-time update installs those)
             d = p.detach()
             d.requires_grad = True
             module._parameters[n_p] = d
+
+    def grad_slots(self):
+        """(module, parameter name) of every fine-tuned tensor, in param_groups() order (cached: the set is fixed
+        once the model is built)."""
+        gs = getattr(self, "_grad_slots", None)
+        if gs is None:
+            gs = self._grad_slots = [(module, n_p) for _, module, n_p, _ in self.param_groups()]
+        return gs
 
     def init_param_groups(self, group_inits):
         for n_m, module, n_p, _ in self.param_groups():

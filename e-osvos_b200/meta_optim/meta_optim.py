@@ -231,8 +231,58 @@ class MetaOptimizer(nn.Module):
             train_loss = train_loss.detach()
         self._train_loss = train_loss
 
+    def _step_eval(self, train_loss):
+        """Evaluation-time step (no graph is kept through the update): theta <- theta - lr (.) grad in ONE kernel,
+        in place in the model's parameter arena, without the autograd Function and with the pointer table cached
+        while the addresses of parameters / gradients / learning rates stay the same.  Returns False (nothing done)
+        when the model's arena does not match the current parameters."""
+        model = self.meta_model.model
+        slots = self.meta_model.grad_slots()
+        params = [m._parameters[n] for m, n in slots]
+        dev = params[0].device
+        arena, offs, shapes, index = model.theta_home()
+        hv = getattr(self, "_home_views", None)
+        if hv is None or hv[0] is not arena:
+            idx = [index.get((id(m), n)) for m, n in slots]
+            if arena.device != dev or any(i is None or shapes[i] != tuple(p.shape) for i, p in zip(idx, params)):
+                return False
+            views = [arena[offs[i]:offs[i] + p.numel()].view(shapes[i]).requires_grad_(True) for i, p in zip(idx, params)]
+            hv = self._home_views = (arena, views)
+            self._plan_cache = {}
+        outs = hv[1]
+        lrs = self.state["log_lr"]
+        if not isinstance(lrs, list):
+            lrs = [lrs[i] for i in range(len(params))]
+        if any(l.device != dev for l in lrs):
+            return False
+        grads = torch.autograd.grad(train_loss, params)
+        key = (tuple(p.data_ptr() for p in params), tuple((g.data_ptr(), g.stride(1) if g.dim() == 4 else 0) for g in grads),
+               tuple(l.data_ptr() for l in lrs))
+        plan = self._plan_cache.get(key)
+        if plan is None:
+            gs = [g.detach() if (g.is_contiguous() or (g.dim() == 4 and g.is_contiguous(memory_format=torch.channels_last)))
+                  else g.detach().contiguous() for g in grads]
+            plan = K.MetaUpdatePlan([p.detach() for p in params], gs, [l.detach() for l in lrs], [o.detach() for o in outs])
+            plan.keep = gs
+            if all(a.data_ptr() == b.data_ptr() for a, b in zip(gs, grads)):
+                if len(self._plan_cache) > 8:
+                    self._plan_cache.clear()
+                self._plan_cache[key] = plan
+        K.meta_update(plan, bool(self._use_log_init_lr))
+        if params[0] is not outs[0]:
+            for (m, n), o in zip(slots, outs):
+                m._parameters[n] = o
+        # values changed behind the same tensor objects: the per-tensor operand cache must not survive
+        from .. import ops
+        ops.clear_prep_cache()
+        self.state["num_steps"] += 1
+        return True
+
     # ---- meta_optim.py:177-214, fused
     def step(self, train_loss):
+        if not self.training and callable(getattr(self.meta_model.model, "theta_home", None)):
+            if self._step_eval(train_loss):
+                return
         if self.training and self._second_order_gradients:
             raise NotImplementedError(
                 "second_order_gradients=True needs create_graph through hand-written backward kernels; "

@@ -210,31 +210,37 @@ class MaskRCNN(_MaskRCNN):
                         "iscrowd": torch.zeros((num_objs,), dtype=torch.int64, device=device)})
         return out
 
-    def _prepare_operands(self):
-        """All 16-bit tensor-core operand layouts of the current parameters in ONE launch (cached per live tensor)."""
+    def _prepare_operands(self, skip_box=False):
+        """All 16-bit tensor-core operand layouts of the current parameters of the EAGER modules in ONE launch (cached
+        per live tensor).  Graphed parts (trunk; box branch when `skip_box`) build theirs inside their graphs."""
         training = self.training
-        req = []
-        body = self.backbone.body
         graphed = self.use_cuda_graphs and self.capture is None
-        if not graphed:
-            req.append((body.conv1.weight, "stem"))
-        trunk = set(id(m) for mod in (self.backbone, self.rpn.head) for m in mod.modules()) if graphed else set()
-        for m in self.modules():
-            if id(m) in trunk:
-                continue          # the graphed trunk builds its operands inside the graph from its static inputs
-            if isinstance(m, nn.Conv2d) and m is not body.conv1 and m.weight.shape[0] >= 64:
-                req.append((m.weight, "f"))
+        key = (training, graphed, skip_box)
+        plan = getattr(self, "_operand_plan", None)
+        if plan is None or plan[0] != key:
+            body = self.backbone.body
+            ent = []
+            if not graphed:
+                ent.append((body.conv1, "weight", "stem"))
+            trunk = set(id(m) for mod in (self.backbone, self.rpn.head) for m in mod.modules()) if graphed else set()
+            for m in self.modules():
+                if id(m) in trunk:
+                    continue      # the graphed trunk builds its operands inside the graph from its static inputs
+                if isinstance(m, nn.Conv2d) and m is not body.conv1 and m.weight.shape[0] >= 64:
+                    ent.append((m, "weight", "f"))
+                    if training:
+                        ent.append((m, "weight", "t"))
+            rh = self.roi_heads
+            C = self.backbone.out_channels
+            if not skip_box:
+                ent.append((rh.box_head.fc6, "weight", ("lf", C)))
+                ent.append((rh.box_head.fc7, "weight", ("lf", 0)))
                 if training:
-                    req.append((m.weight, "t"))
-        rh = self.roi_heads
-        C = self.backbone.out_channels
-        req.append((rh.box_head.fc6.weight, ("lf", C)))
-        req.append((rh.box_head.fc7.weight, ("lf", 0)))
-        if training:
-            req.append((rh.box_head.fc6.weight, ("lt", C)))
-            req.append((rh.box_head.fc7.weight, ("lt", 0)))
-        req.append((rh.mask_predictor.conv5_mask.weight, "dc"))
-        ops.prep_many(req)
+                    ent.append((rh.box_head.fc6, "weight", ("lt", C)))
+                    ent.append((rh.box_head.fc7, "weight", ("lt", 0)))
+            ent.append((rh.mask_predictor.conv5_mask, "weight", "dc"))
+            plan = self._operand_plan = (key, ent)
+        ops.prep_many([(m._parameters[n], kind) for m, n, kind in plan[1]])
 
     # ---- transform (tv transform.py:119-160, 25-84, 237-255) ------------------------------------
     def _resized_size(self, h, w):
@@ -468,7 +474,7 @@ class MaskRCNN(_MaskRCNN):
             # never continue in a zero block it touched
             K.zero_pool.reset()
             ent = (graphed, per_call, plan, vals)
-            if len(self._graphs) >= 16:         # bounded: graphs pin their activation pools
+            if len(self._graphs) >= 24:         # bounded: graphs pin their activation pools
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = ent
         from .. import _lib
@@ -1142,7 +1148,6 @@ class MaskRCNN(_MaskRCNN):
             losses["loss_mask"] = torch.zeros((), device=feats[0].device)
             return losses
         mask_rois5 = rois5[pos].contiguous()
-        mask_logits = self._mask_branch_rois(feats, mask_rois5)
         # mask targets: row (matched ground truth + offset of the image's masks in the concatenated list, box)
         g_off = [0]
         for t in targets:
@@ -1150,9 +1155,60 @@ class MaskRCNN(_MaskRCNN):
         img_off = K.stager.put(torch.tensor(g_off[:-1], dtype=torch.float32), feats[0].device)
         gt_row = smp["matched"][pos].to(torch.float32) + img_off[mask_rois5[:, 0].to(torch.int64)]
         tgt_rois = torch.cat([gt_row[:, None], mask_rois5[:, 1:]], dim=1).contiguous()
-        tg = K.mask_targets(torch.cat([t["masks"] for t in targets], 0).contiguous(), tgt_rois, mask_logits.shape[-1])
+        gt_masks = torch.cat([t["masks"] for t in targets], 0).contiguous()
+        if (kind == 'LOVASZ' and self.use_cuda_graphs and torch.is_grad_enabled()
+                and os.environ.get("EOSVOS_GRAPH_MASK", "1") != "0"):
+            lm = self._mask_loss_graphed_fast(feats, mask_rois5, lab_c[pos], tgt_rois, gt_masks)
+            if lm is not None:
+                losses["loss_mask"] = lm
+                return losses
+        mask_logits = self._mask_branch_rois(feats, mask_rois5)
+        tg = K.mask_targets(gt_masks, tgt_rois, mask_logits.shape[-1])
         losses["loss_mask"] = ops.mask_loss(mask_logits, lab_c[pos].contiguous(), tg, kind)
         return losses
+
+    _MASK_BUCKETS_FINE = (16, 32, 48, 64, 96, 128, 192, 256, 384)
+
+    def _mask_loss_graphed_fast(self, feats, mask_rois5, lab, tgt_rois, gt_masks):
+        """Mask branch (RoIAlign 28x28, 4 convs, deconv, logits), mask targets and the Lovasz loss -- forward and
+        backward -- as one CUDA-graph pair on the positives padded to the next bucket size (padding rows: image index
+        -1 = zeros through RoIAlign and no contribution backward, loss weight 0).  After the sampler's host sync the
+        GPU is idle until the heads are queued: ~60 launches become two replays."""
+        rh = self.roi_heads
+        device = feats[0].device
+        n = int(mask_rois5.shape[0])
+        R = next((b for b in self._MASK_BUCKETS_FINE if b >= n), None)
+        if R is None:
+            return None
+        pad = R - n
+        fills = getattr(self, "_mask_fill_cache", None)
+        if fills is None or fills[0] != device:
+            fill = torch.zeros((max(self._MASK_BUCKETS_FINE), 5), device=device)
+            fill[:, 0] = -1.0                       # negative image index = padding row (skipped by the kernels)
+            fills = self._mask_fill_cache = (device, fill, torch.ones(max(self._MASK_BUCKETS_FINE), dtype=torch.int64, device=device))
+        w = torch.zeros((R,), device=device, dtype=torch.float32)
+        w[:n] = 1.0 / n
+        if pad:
+            mask_rois5 = torch.cat([mask_rois5, fills[1][:pad]], 0)
+            tgt_rois = torch.cat([tgt_rois, fills[1][:pad]], 0)
+            lab = torch.cat([lab, fills[2][:pad]], 0)
+        if self._mask_slots is None:
+            mods = (rh.mask_head, rh.mask_predictor)
+            self._mask_slots = [(m, n_) for mod in mods for _, m in mod.named_modules()
+                                for n_, p in m._parameters.items() if p is not None and p.requires_grad]
+
+        def kinds(m, n_, t):
+            if n_ != "weight":
+                return ()
+            if isinstance(m, nn.ConvTranspose2d):
+                return ("dc",)
+            if isinstance(m, nn.Conv2d) and t.shape[0] >= 64:
+                return ("f", "t")
+            return ()
+        key = ("mask", R, tuple(gt_masks.shape), tuple(tuple(f.shape) for f in feats[:4]), device.index)
+        return self._graphed_call(key, self._mask_train_functional,
+                                  list(feats[:4]) + [mask_rois5.contiguous(), lab.contiguous(), gt_masks, tgt_rois.contiguous(), w],
+                                  self._mask_slots, kinds, True, alias_inputs=4)
 
     def _box_loss_graphed(self, feats, rois5, lab_c, reg_c):
         """Box branch + tv fastrcnn_loss and their backward as one CUDA-graph pair (static shapes: 512 RoIs / image)."""
@@ -1483,7 +1539,9 @@ class MaskRCNN(_MaskRCNN):
             targets = self._build_targets(targets, flip_label, device)
         B, _, h, w = inputs.shape
         K.zero_pool.reset()          # one zeroed block per forward(+backward) serves all accumulate-into outputs
-        self._prepare_operands()
+        fast_train = (self.training and fast and self.use_cuda_graphs and os.environ.get("EOSVOS_GRAPH_HEAD", "2") == "2")
+        self._prepare_operands(skip_box=fast_train and torch.is_grad_enabled()
+                               and os.environ.get("EOSVOS_GRAPH_BOX", "1") != "0")
         pre = None
         if self._prefetched:
             pf = self._prefetched.pop(id(inputs), None)
@@ -1497,7 +1555,6 @@ class MaskRCNN(_MaskRCNN):
         image_shape = (B, 3, Hp, Wp)
 
         grad_ctx = torch.enable_grad() if self.training else torch.no_grad()
-        fast_train = (self.training and fast and self.use_cuda_graphs and os.environ.get("EOSVOS_GRAPH_HEAD", "2") == "2")
         with grad_ctx:
             if fast_train:
                 am = self._anchor_match_async(image_shape, image_sizes, targets_t, device)

@@ -139,6 +139,7 @@ int eosvos_rpn_loss(const void* const* heads, void* const* dys, const int* hw, i
                     const long long* sampled, int num_sampled, const long long* labels, const int* matched,
                     const float* anchors, const float* gt_boxes, const int* gt_off, float beta, int mode, float* out,
                     const float* g_obj, const float* g_box, eosvos_stream_t stream);
+long long eosvos_roi_sample_scratch_bytes(int B, int rows);
 int eosvos_roi_sample(const long long* labels, const long long* table, int B, int rows, int S, int Pmax, void* scratch,
                       long long* inds, long long* pos_in, eosvos_stream_t stream);
 int eosvos_roi_encode(const float* all_boxes, const long long* labels, const long long* matched, const float* gt_boxes,
