@@ -54,6 +54,9 @@ SIGNATURES = {
     "eosvos_roi_match": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "eosvos_rpn_anchor_match": [_P, _I, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P],
     "eosvos_rpn_loss": [_P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P],
+    "eosvos_rpn_sparse_head": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _F, _P, _P, _P,
+                               _P, _P, _P, _P, _P],
+    "eosvos_rpn_sparse_scatter": [_P, _P, _P, _I, _I, _P, _I, _P, _P],
     "eosvos_roi_sample_scratch_bytes": [_I, _I],
     "eosvos_roi_sample": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
     "eosvos_roi_encode": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],

@@ -24,6 +24,7 @@
 // Arithmetic that feeds discrete decisions uses explicit round-to-nearest multiplies / adds (no FMA contraction), i.e.
 // the operation sequence of the ATen elementwise kernels the reference runs.
 #include "common.h"
+#include "act.cuh"
 #include "../../include/eosvos_b200.h"
 
 namespace eosvos {
@@ -880,6 +881,128 @@ rpn_loss_kernel(const RpnLossLevels lv, const long long* __restrict__ sampled, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sparse backward of the RPN head.  The RPN losses touch only the <= 256 sampled anchors per image, so the gradient
+// that enters the head (1x1 objectness / box convs on the shared 3x3 conv's ReLU output t) is non-zero on <= 768
+// pixel rows out of 257,796 x N / 3: instead of dense dgrad + wgrad over every pyramid level (2 x 102 GFLOP per
+// image in the reference's cuDNN path) the gradient is propagated for those rows only:
+//   rpn_sparse_head_kernel   per sampled anchor ("event"): d loss / d head (as rpn_loss_kernel<true>), the 1x1 heads'
+//                            weight / bias gradients, dt = W_head^T dy masked by t > 0, event pixel coordinates
+//   rpn_sparse_gather_kernel X_g[e][tap][ci] = f[pixel_e + tap][ci]   (the 3x3 conv's input rows, zero outside)
+//   (tensor cores)           dW_conv = dt^T X_g  (eosvos_gemm_wgrad),  G = dt W_conv  (eosvos_conv2d_fprop on rows)
+//   rpn_sparse_scatter_kernel df[pixel_e + tap][ci] += G[e][ci][tap]  (16-bit atomics into the zeroed level maps)
+// Mathematically identical to the dense backward (the skipped terms are exact zeros).
+// ---------------------------------------------------------------------------------------------------------------
+struct RpnSparseLevels {
+  const float* head[RPN_MAX_LEVELS];    // fp32 [N * hw][16]
+  const act_t* t[RPN_MAX_LEVELS];       // RPN conv output after ReLU, [N * hw][C]
+  const act_t* f[RPN_MAX_LEVELS];       // pyramid level (conv input), [N][H][W][C]
+  act_t* df[RPN_MAX_LEVELS];            // gradient of the level, zeroed by the caller
+  int H[RPN_MAX_LEVELS], W[RPN_MAX_LEVELS];
+  int anchor_off[RPN_MAX_LEVELS];
+  int num_levels, A, anchors_per_image, C;
+};
+
+// grid = events, block = C threads (C <= 1024, multiple of 32)
+__global__ void rpn_sparse_head_kernel(const RpnSparseLevels lv, const long long* __restrict__ sampled, int M,
+                                       const long long* __restrict__ labels, const int* __restrict__ matched,
+                                       const float4* __restrict__ anchors, const float4* __restrict__ gt,
+                                       const int* __restrict__ gt_off, float beta, const float* __restrict__ g_obj,
+                                       const float* __restrict__ g_box, const float* __restrict__ w_cls,
+                                       const float* __restrict__ w_box, float scale, act_t* __restrict__ dt,
+                                       int4* __restrict__ ev_pix, float* __restrict__ dw_cls, float* __restrict__ db_cls,
+                                       float* __restrict__ dw_box, float* __restrict__ db_box) {
+  const int e = blockIdx.x, c = threadIdx.x;
+  const long long idx = sampled[e];
+  const int C = lv.C, A = lv.A;
+  if (idx < 0) {                                   // padding event: contributes nothing
+    dt[(size_t)e * C + c] = float2act(0.f);
+    if (c == 0) ev_pix[e] = make_int4(-1, 0, 0, 0);
+    return;
+  }
+  const int n = (int)(idx / lv.anchors_per_image);
+  const int r = (int)(idx - (long long)n * lv.anchors_per_image);
+  int l = 0;
+  while (l + 1 < lv.num_levels && r >= lv.anchor_off[l + 1]) ++l;
+  const int i = r - lv.anchor_off[l];
+  const int row = i / A, a = i - row * A;
+  const size_t prow = (size_t)n * lv.H[l] * lv.W[l] + row;
+  const float* h = lv.head[l] + prow * 16;
+  const long long lab = labels[idx];
+  const float inv_m = 1.f / (float)M;
+  const float go = g_obj[0] * inv_m, gb = g_box[0] * inv_m;
+  // d loss / d head for this anchor: 1 objectness column, 4 box columns when foreground
+  float dy[5];
+  const float x = h[a], y = lab >= 1 ? 1.f : 0.f;
+  dy[0] = go * (1.f / (1.f + expf(-x)) - y);
+  dy[1] = dy[2] = dy[3] = dy[4] = 0.f;
+  if (lab >= 1) {
+    const float4 an = anchors[r];
+    const float4 t4 = gt[gt_off[n] + matched[idx]];
+    const float ew = __fsub_rn(an.z, an.x), eh = __fsub_rn(an.w, an.y);
+    const float ecx = __fadd_rn(an.x, __fmul_rn(0.5f, ew)), ecy = __fadd_rn(an.y, __fmul_rn(0.5f, eh));
+    const float gw = __fsub_rn(t4.z, t4.x), gh = __fsub_rn(t4.w, t4.y);
+    const float gcx = __fadd_rn(t4.x, __fmul_rn(0.5f, gw)), gcy = __fadd_rn(t4.y, __fmul_rn(0.5f, gh));
+    const float tv[4] = {__fsub_rn(gcx, ecx) / ew, __fsub_rn(gcy, ecy) / eh, logf(gw / ew), logf(gh / eh)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = h[A + a * 4 + k] - tv[k];
+      const float ad = fabsf(d);
+      dy[1 + k] = gb * (ad < beta ? d / beta : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)));
+    }
+  }
+  const float tc = (float)lv.t[l][prow * C + c];
+  // heads' parameter gradients (unscaled fp32): dW[col][c] += dy[col] * t[c], db[col] += dy[col]
+  atomicAdd(&dw_cls[(size_t)a * C + c], dy[0] * tc);
+  float acc = dy[0] * w_cls[(size_t)a * C + c];
+  if (lab >= 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&dw_box[(size_t)(a * 4 + k) * C + c], dy[1 + k] * tc);
+      acc += dy[1 + k] * w_box[(size_t)(a * 4 + k) * C + c];
+    }
+  }
+  if (c == 0) {
+    atomicAdd(&db_cls[a], dy[0]);
+    if (lab >= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(&db_box[a * 4 + k], dy[1 + k]);
+    }
+    const int py = row / lv.W[l];
+    ev_pix[e] = make_int4(l, n, py, row - py * lv.W[l]);
+  }
+  // gradient w.r.t. the conv output, through the ReLU, entering the 16-bit domain under the loss scale
+  dt[(size_t)e * C + c] = float2act(tc > 0.f ? acc * scale : 0.f);
+}
+
+// grid (events, 9 taps), block C / 2 threads (two channels each)
+__global__ void rpn_sparse_gather_kernel(const RpnSparseLevels lv, const int4* __restrict__ ev_pix,
+                                         act2_t* __restrict__ xg) {
+  const int e = blockIdx.x, tap = blockIdx.y, c2 = threadIdx.x;
+  const int C2 = lv.C / 2;
+  const int4 p = ev_pix[e];
+  act2_t v = floats2act2(0.f, 0.f);
+  if (p.x >= 0) {
+    const int y = p.z + tap / 3 - 1, x = p.w + tap % 3 - 1;
+    if (y >= 0 && y < lv.H[p.x] && x >= 0 && x < lv.W[p.x])
+      v = reinterpret_cast<const act2_t*>(lv.f[p.x])[(((size_t)p.y * lv.H[p.x] + y) * lv.W[p.x] + x) * C2 + c2];
+  }
+  xg[((size_t)e * 9 + tap) * C2 + c2] = v;
+}
+
+// G [events][C * 9] with column = ci * 9 + tap (rows of the [Cin][KH][KW][Cout] dgrad operand).
+// grid (events, 9 taps), block C threads
+__global__ void rpn_sparse_scatter_kernel(const RpnSparseLevels lv, const int4* __restrict__ ev_pix,
+                                          const act_t* __restrict__ G) {
+  const int e = blockIdx.x, tap = blockIdx.y, ci = threadIdx.x;
+  const int4 p = ev_pix[e];
+  if (p.x < 0) return;
+  const int y = p.z + tap / 3 - 1, x = p.w + tap % 3 - 1;
+  if (y < 0 || y >= lv.H[p.x] || x < 0 || x >= lv.W[p.x]) return;
+  const act_t g = G[(size_t)e * lv.C * 9 + (size_t)ci * 9 + tap];
+  atomicAdd(&lv.df[p.x][(((size_t)p.y * lv.H[p.x] + y) * lv.W[p.x] + x) * lv.C + ci], g);
+}
+
 }  // namespace eosvos
 
 using namespace eosvos;
@@ -1092,6 +1215,66 @@ extern "C" int eosvos_rpn_loss(const void* const* heads, void* const* dys, const
   rpn_loss_kernel<true><<<1, 1024, 0, stream>>>(lv, sampled, num_sampled, labels, matched, an, gt, gt_off, beta, nullptr,
                                                 g_obj, g_box);
   return check_launch("rpn_loss_kernel<bwd>");
+}
+
+static int fill_sparse(RpnSparseLevels& lv, const void* const* heads, const void* const* ts, const void* const* fs,
+                       void* const* dfs, const int* Hs, const int* Ws, int num_levels, int A, int C) {
+  if (num_levels < 1 || num_levels > RPN_MAX_LEVELS) return -1;
+  lv.num_levels = num_levels;
+  lv.A = A;
+  lv.C = C;
+  int off = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    lv.head[l] = heads ? reinterpret_cast<const float*>(heads[l]) : nullptr;
+    lv.t[l] = ts ? reinterpret_cast<const act_t*>(ts[l]) : nullptr;
+    lv.f[l] = fs ? reinterpret_cast<const act_t*>(fs[l]) : nullptr;
+    lv.df[l] = dfs ? reinterpret_cast<act_t*>(dfs[l]) : nullptr;
+    lv.H[l] = Hs[l];
+    lv.W[l] = Ws[l];
+    lv.anchor_off[l] = off;
+    off += Hs[l] * Ws[l] * A;
+  }
+  lv.anchors_per_image = off;
+  return 0;
+}
+
+// Stage 1 of the sparse RPN-head backward (see above).  Outputs: dt [M][C] 16-bit (x grad_scale), ev_pix int32 [M][4],
+// X_g [M][9][C] 16-bit; accumulates into the ZEROED fp32 dw_cls [A][C], db_cls [A], dw_box [4A][C], db_box [4A].
+extern "C" int eosvos_rpn_sparse_head(const void* const* heads, const void* const* ts, const void* const* fs,
+                                      const int* Hs, const int* Ws, int num_levels, int A, int C,
+                                      const long long* sampled, int M, const long long* labels, const int* matched,
+                                      const float* anchors, const float* gt_boxes, const int* gt_off, float beta,
+                                      const float* g_obj, const float* g_box, const float* w_cls, const float* w_box,
+                                      float grad_scale, void* dt, int* ev_pix, void* xg, float* dw_cls, float* db_cls,
+                                      float* dw_box, float* db_box, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RpnSparseLevels lv;
+  EOSVOS_REQUIRE(fill_sparse(lv, heads, ts, fs, nullptr, Hs, Ws, num_levels, A, C) == 0, "rpn_sparse_head: 1..8 levels");
+  EOSVOS_REQUIRE(C % 64 == 0 && C <= 1024, "rpn_sparse_head: channel count must be a multiple of 64, at most 1024");
+  EOSVOS_REQUIRE(sampled && labels && matched && anchors && gt_boxes && gt_off && g_obj && g_box && w_cls && w_box && dt &&
+                     ev_pix && xg && dw_cls && db_cls && dw_box && db_box,
+                 "rpn_sparse_head: null pointer");
+  EOSVOS_REQUIRE(M > 0, "rpn_sparse_head: no sampled anchors");
+  rpn_sparse_head_kernel<<<M, C, 0, stream>>>(lv, sampled, M, labels, matched, reinterpret_cast<const float4*>(anchors),
+                                              reinterpret_cast<const float4*>(gt_boxes), gt_off, beta, g_obj, g_box, w_cls,
+                                              w_box, grad_scale, reinterpret_cast<act_t*>(dt),
+                                              reinterpret_cast<int4*>(ev_pix), dw_cls, db_cls, dw_box, db_box);
+  EOSVOS_TRY(check_launch("rpn_sparse_head_kernel"));
+  rpn_sparse_gather_kernel<<<dim3(M, 9), C / 2, 0, stream>>>(lv, reinterpret_cast<const int4*>(ev_pix),
+                                                             reinterpret_cast<act2_t*>(xg));
+  return check_launch("rpn_sparse_gather_kernel");
+}
+
+// Stage 3: df[level][pixel + tap][ci] += G[e][ci * 9 + tap] into the ZEROED 16-bit level gradient maps.
+extern "C" int eosvos_rpn_sparse_scatter(void* const* dfs, const int* Hs, const int* Ws, int num_levels, int C,
+                                         const int* ev_pix, int M, const void* G, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RpnSparseLevels lv;
+  EOSVOS_REQUIRE(fill_sparse(lv, nullptr, nullptr, nullptr, dfs, Hs, Ws, num_levels, 1, C) == 0, "rpn_sparse_scatter: levels");
+  EOSVOS_REQUIRE(dfs && ev_pix && G && C <= 1024, "rpn_sparse_scatter: bad argument");
+  rpn_sparse_scatter_kernel<<<dim3(M, 9), C, 0, stream>>>(lv, reinterpret_cast<const int4*>(ev_pix),
+                                                          reinterpret_cast<const act_t*>(G));
+  return check_launch("rpn_sparse_scatter_kernel");
 }
 
 extern "C" long long eosvos_roi_sample_scratch_bytes(int B, int rows) {

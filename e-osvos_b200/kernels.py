@@ -589,6 +589,41 @@ def rpn_loss(head_outs, hw, A, sampled, labels, matched, anchors, gt_boxes, gt_o
     return out
 
 
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def rpn_sparse_head(head_outs, ts, feats, A, sampled, labels, matched, anchors, gt_boxes, gt_off, beta, g_obj, g_box,
+                    w_cls, w_box, grad_scale):
+    """Stage 1 of the sparse RPN-head backward -> (dt [M,C] ACT, ev_pix int32 [M,4], xg [M, 9*C] ACT, dw_cls [A,C],
+    db_cls [A], dw_box [4A,C], db_box [4A]) (fp32 gradients unscaled)."""
+    dev = sampled.device
+    M = int(sampled.numel())
+    C = feats[0].shape[-1]
+    Hs, Ws = [f.shape[1] for f in feats], [f.shape[2] for f in feats]
+    dt = torch.empty((M, C), device=dev, dtype=ACT_DTYPE)
+    ev = torch.empty((M, 4), device=dev, dtype=torch.int32)
+    xg = torch.empty((M, 9 * C), device=dev, dtype=ACT_DTYPE)
+    acc = zero_pool.take((5 * A * C + 5 * A + 64,), dev)
+    dw_cls, dw_box = acc[:A * C].view(A, C), acc[A * C:5 * A * C].view(4 * A, C)
+    db_cls, db_box = acc[5 * A * C:5 * A * C + A], acc[5 * A * C + A:5 * A * C + 5 * A]
+    call("eosvos_rpn_sparse_head", _ptr_array(head_outs), _ptr_array(ts), _ptr_array(feats), _int_array(Hs),
+         _int_array(Ws), len(feats), int(A), int(C), _ptr(_chk(sampled, torch.int64, "sampled")), M,
+         _ptr(_chk(labels, torch.int64, "labels")), _ptr(_chk(matched, torch.int32, "matched")), _ptr(anchors),
+         _ptr(gt_boxes), _ptr(gt_off), float(beta), _ptr(g_obj), _ptr(g_box), _ptr(_chk(w_cls, torch.float32, "w_cls")),
+         _ptr(_chk(w_box, torch.float32, "w_box")), float(grad_scale), _ptr(dt), _ptr(ev), _ptr(xg), _ptr(dw_cls),
+         _ptr(db_cls), _ptr(dw_box), _ptr(db_box), _stream())
+    return dt, ev, xg, dw_cls, db_cls, dw_box, db_box
+
+
+def rpn_sparse_scatter(dfs, ev_pix, G):
+    """df[level][pixel + tap][ci] += G[e][ci*9 + tap] into the zeroed ACT maps dfs (NHWC)."""
+    C = dfs[0].shape[-1]
+    call("eosvos_rpn_sparse_scatter", _ptr_array(dfs), _int_array([d.shape[1] for d in dfs]),
+         _int_array([d.shape[2] for d in dfs]), len(dfs), int(C), _ptr(ev_pix), int(ev_pix.shape[0]),
+         _ptr(_chk(G, ACT_DTYPE, "G")), _stream())
+
+
 def roi_sample(labels, perms, num_pos, num_neg, S, Pmax):
     """BalancedPositiveNegativeSampler selection for all images in one launch.  labels int64 [B, rows]; perms =
     [(perm_pos, perm_neg)] per image (the reference's two device `torch.randperm` draws); num_pos / num_neg per image.

@@ -348,6 +348,13 @@ class MaskRCNN(_MaskRCNN):
             lvl = int(os.environ.get("EOSVOS_GRAPH_HEAD", "2"))
             if lvl == 0:
                 return tuple(feats)
+            if lvl == 2 and os.environ.get("EOSVOS_RPN_SPARSE", "1") != "0":
+                # RPN head forward only (no autograd nodes): its backward runs outside the graph, for the sampled
+                # anchors only (ops.RpnSparseFn).  Outputs: levels, shared-conv outputs t, fused head outputs o.
+                with torch.no_grad():
+                    ts = self._rpn_head([f.detach() for f in feats], stage=1)
+                    outs = self._rpn_head(ts, stage=2)
+                return tuple(feats) + tuple(ts) + tuple(outs)
             alias = list(feats)
             if lvl == 1:
                 outs = self._rpn_head(feats, stage=1, alias=alias)
@@ -464,7 +471,9 @@ class MaskRCNN(_MaskRCNN):
             try:
                 if grad_mode:
                     with torch.enable_grad():
-                        graphed = torch.cuda.make_graphed_callables(fn, tuple(sample))
+                        # (parameters whose gradient is produced outside the graph -- the RPN head under the sparse
+                        # backward -- are unused inside)
+                        graphed = torch.cuda.make_graphed_callables(fn, tuple(sample), allow_unused_input=True)
                 else:
                     graphed = self._capture_inference_graph(fn, sample, nin)
             finally:
@@ -1327,7 +1336,7 @@ class MaskRCNN(_MaskRCNN):
         image_shape = (B, 3, Hp, Wp)
         with torch.no_grad():
             feats = pre_feats if pre is not None else self._backbone(x8)
-            feats, head_outs = feats[:5], feats[5:]
+            feats, head_outs = feats[:5], feats[-5:]
             rpn = self.rpn
             post = rpn.post_nms_top_n()
             mode = rpn._eval_augment_proposals_mode
@@ -1559,7 +1568,10 @@ class MaskRCNN(_MaskRCNN):
             if fast_train:
                 am = self._anchor_match_async(image_shape, image_sizes, targets_t, device)
             feats = pre_feats if pre is not None else self._backbone(x8)
-            feats, head_outs = feats[:5], (feats[5:] if len(feats) > 5 else None)
+            rpn_ts = feats[5:10] if len(feats) == 15 else None
+            feats, head_outs = feats[:5], (feats[-5:] if len(feats) > 5 else None)
+            if self.training and rpn_ts is not None and not fast_train:
+                head_outs = None          # forward-only head outputs carry no gradient: recompute with autograd below
             if fast_train and head_outs is not None and head_outs[0].dtype == torch.float32:
                 # statically shaped proposal / sampling pipeline: ONE host sync (RoI sampler counts) per iteration
                 # the proposal kernels and the RoI matching only need the trunk: queue them first, label the anchors
@@ -1570,9 +1582,13 @@ class MaskRCNN(_MaskRCNN):
                 sampled = self._sample_anchors_fast(am)
                 det_losses = self._roi_heads_train_fast(feats, mt, targets_t)
                 raw = dict(det_losses)
-                lo, lb = ops.rpn_loss(head_outs, [f.shape[1] * f.shape[2] for f in feats],
-                                      self.rpn.head.cls_logits.weight.shape[0], sampled, am["labels"], am["matched"],
-                                      am["anchors"], am["gt_boxes"], am["gt_off"])
+                if rpn_ts is not None:
+                    lo, lb = ops.rpn_loss_sparse(feats, rpn_ts, head_outs, self.rpn.head, sampled, am["labels"],
+                                                 am["matched"], am["anchors"], am["gt_boxes"], am["gt_off"])
+                else:
+                    lo, lb = ops.rpn_loss(head_outs, [f.shape[1] * f.shape[2] for f in feats],
+                                          self.rpn.head.cls_logits.weight.shape[0], sampled, am["labels"], am["matched"],
+                                          am["anchors"], am["gt_boxes"], am["gt_off"])
                 raw.update({"loss_objectness": lo, "loss_rpn_box_reg": lb})
                 losses = {n: l for n, l in raw.items() if l.requires_grad}
                 return sum([l for l in losses.values()]), losses

@@ -677,3 +677,56 @@ def rpn_loss(head_outs, hw, A, sampled, labels, matched, anchors, gt_boxes, gt_o
     """(loss_objectness, loss_rpn_box_reg) of tv rpn.py compute_loss.  sampled: int64 positions in the flattened
     (image, level, pixel, anchor) order, -1 = padding (the mean runs over `sampled.numel()`: pass exactly the samples)."""
     return RpnLossFn.apply(sampled, labels, matched, anchors, gt_boxes, gt_off, hw, A, beta, *head_outs)
+
+
+class RpnSparseFn(torch.autograd.Function):
+    """RPN losses (tv rpn.py compute_loss) as a function of the pyramid levels and the RPN head's parameters, given the
+    head's forward results (shared-conv output t and fused head output o per level, computed without autograd inside
+    the trunk graph).  The backward propagates through the 1x1 heads, the ReLU and the shared 3x3 conv for the
+    sampled anchors only (csrc/rpn.cu, "sparse backward of the RPN head"): same gradients as the dense path."""
+
+    @staticmethod
+    def forward(ctx, sampled, labels, matched, anchors, gt_boxes, gt_off, A, beta, ts, os_, w_conv, b_conv, w_cls, b_cls,
+                w_box, b_box, *feats):
+        hw = [f.shape[1] * f.shape[2] for f in feats]
+        out = K.rpn_loss(list(os_), hw, A, sampled, labels, matched, anchors, gt_boxes, gt_off, beta)
+        ctx.save_for_backward(sampled, labels, matched, anchors, gt_boxes, gt_off, w_conv, w_cls, w_box, *ts, *os_, *feats)
+        ctx.cfg = (A, beta, len(feats))
+        return out[0], out[1]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_obj, g_box):
+        A, beta, L = ctx.cfg
+        sv = ctx.saved_tensors
+        sampled, labels, matched, anchors, gt_boxes, gt_off, w_conv, w_cls, w_box = sv[:9]
+        ts, os_, feats = sv[9:9 + L], sv[9 + L:9 + 2 * L], sv[9 + 2 * L:]
+        dev = labels.device
+        zero = torch.zeros((), device=dev) if (g_obj is None or g_box is None) else None
+        g_obj = (g_obj if g_obj is not None else zero).contiguous()
+        g_box = (g_box if g_box is not None else zero).contiguous()
+        C = feats[0].shape[-1]
+        dt, ev, xg, dw_cls, db_cls, dw_box, db_box = K.rpn_sparse_head(
+            list(os_), list(ts), list(feats), A, sampled, labels, matched, anchors, gt_boxes, gt_off, beta, g_obj, g_box,
+            w_cls.detach().reshape(A, C).contiguous(), w_box.detach().reshape(4 * A, C).contiguous(), GRAD_SCALE)
+        M = dt.shape[0]
+        # shared 3x3 conv: weight gradient = dt^T X_g (channels-last filter gradient layout [Cout][KH][KW][Cin]),
+        # bias gradient = column sums, input gradient rows G = dt W (columns (ci, tap)), scattered to the levels
+        dw = K.zero_pool.take((C, 3, 3, C), dev)
+        K.gemm_wgrad(xg, dt, dw.view(C, 9 * C), s_m=9 * C, alpha=_inv_scale())
+        db = K.colsum(dt, alpha=_inv_scale())
+        G = K.conv2d_fprop(dt.view(1, 1, M, C), prep_conv_wt(w_conv).view(9 * C, 1, 1, C)).view(M, 9 * C)
+        dfs = [torch.zeros_like(f) for f in feats]
+        K.rpn_sparse_scatter(dfs, ev, G)
+        return (None,) * 10 + (dw.permute(0, 3, 1, 2), db, dw_cls.view_as(w_cls), db_cls, dw_box.view_as(w_box), db_box,
+                               *dfs)
+
+
+def rpn_loss_sparse(feats, ts, head_outs, head, sampled, labels, matched, anchors, gt_boxes, gt_off, beta=1.0 / 9):
+    """(loss_objectness, loss_rpn_box_reg); `head` = torchvision RPNHead (conv, cls_logits, bbox_pred)."""
+    from torch import nn
+    conv = head.conv[0][0] if isinstance(head.conv, nn.Sequential) else head.conv
+    A = head.cls_logits.weight.shape[0]
+    return RpnSparseFn.apply(sampled, labels, matched, anchors, gt_boxes, gt_off, A, beta, tuple(ts), tuple(head_outs),
+                             conv.weight, conv.bias, head.cls_logits.weight, head.cls_logits.bias, head.bbox_pred.weight,
+                             head.bbox_pred.bias, *feats)

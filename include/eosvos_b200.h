@@ -139,6 +139,16 @@ int eosvos_rpn_loss(const void* const* heads, void* const* dys, const int* hw, i
                     const long long* sampled, int num_sampled, const long long* labels, const int* matched,
                     const float* anchors, const float* gt_boxes, const int* gt_off, float beta, int mode, float* out,
                     const float* g_obj, const float* g_box, eosvos_stream_t stream);
+/* sparse backward of the RPN head over the sampled anchors only (csrc/rpn.cu; the dense equivalent is the cuDNN dgrad +
+ * wgrad of tv rpn.py RPNHead reached from meta_optim.py:202-204) */
+int eosvos_rpn_sparse_head(const void* const* heads, const void* const* ts, const void* const* fs, const int* Hs,
+                           const int* Ws, int num_levels, int A, int C, const long long* sampled, int M,
+                           const long long* labels, const int* matched, const float* anchors, const float* gt_boxes,
+                           const int* gt_off, float beta, const float* g_obj, const float* g_box, const float* w_cls,
+                           const float* w_box, float grad_scale, void* dt, int* ev_pix, void* xg, float* dw_cls,
+                           float* db_cls, float* dw_box, float* db_box, eosvos_stream_t stream);
+int eosvos_rpn_sparse_scatter(void* const* dfs, const int* Hs, const int* Ws, int num_levels, int C, const int* ev_pix,
+                              int M, const void* G, eosvos_stream_t stream);
 long long eosvos_roi_sample_scratch_bytes(int B, int rows);
 int eosvos_roi_sample(const long long* labels, const long long* table, int B, int rows, int S, int Pmax, void* scratch,
                       long long* inds, long long* pos_in, eosvos_stream_t stream);
