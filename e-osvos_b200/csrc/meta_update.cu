@@ -19,7 +19,11 @@ constexpr int MU_CHUNK = 8192;  // elements per CTA
 // kernel's vector-RED epilogue produces); element i = (co, ci, t) of p pairs with g[(co * taps + t) * Cin + ci].  The
 // permuted reads stay inside one filter's Cin*taps window, so they are served by L1 / L2, not HBM.
 __global__ void __launch_bounds__(MU_THREADS)
-meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ chunks, int use_log) {
+meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ chunks, int use_log,
+                   int* __restrict__ nonfinite) {
+  // `nonfinite` (optional): set to 1 when an updated value is Inf / NaN, i.e. when a gradient of the scaled 16-bit
+  // backward overflowed -- checked by the host at its next synchronisation point (MetaOptimizer.check_finite)
+  bool bad = false;
   const int t = chunks[blockIdx.x * 2];
   const long long start = (long long)chunks[blockIdx.x * 2 + 1] * (long long)MU_CHUNK;
   const long long* e = table + (size_t)t * 8;
@@ -66,6 +70,7 @@ meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ 
       o.y = __fsub_rn(pv.y, __fmul_rn(gq[1], lq[1]));
       o.z = __fsub_rn(pv.z, __fmul_rn(gq[2], lq[2]));
       o.w = __fsub_rn(pv.w, __fmul_rn(gq[3], lq[3]));
+      bad |= !(isfinite(o.x) && isfinite(o.y) && isfinite(o.z) && isfinite(o.w));
       *reinterpret_cast<float4*>(out + i) = o;
     }
     for (unsigned i = (unsigned)start + (nv << 2) + threadIdx.x; i < end; i += MU_THREADS) {
@@ -75,8 +80,11 @@ meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ 
       const unsigned tp = rem - ci * (unsigned)g_taps;
       float lv = __ldg(lr + i / rl);
       if (use_log) lv = expf(lv);
-      out[i] = __fsub_rn(p[i], __fmul_rn(__ldg(g + (size_t)co * filt + tp * (unsigned)g_cin + ci), lv));
+      const float o = __fsub_rn(p[i], __fmul_rn(__ldg(g + (size_t)co * filt + tp * (unsigned)g_cin + ci), lv));
+      bad |= !isfinite(o);
+      out[i] = o;
     }
+    if (bad && nonfinite) atomicOr(nonfinite, 1);
     return;
   }
   const bool aligned = (((e[0] | e[1] | e[3]) & 15) == 0);
@@ -103,20 +111,26 @@ meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ 
       o.y = __fsub_rn(pv.y, __fmul_rn(gv.y, l[1]));
       o.z = __fsub_rn(pv.z, __fmul_rn(gv.z, l[2]));
       o.w = __fsub_rn(pv.w, __fmul_rn(gv.w, l[3]));
+      bad |= !(isfinite(o.x) && isfinite(o.y) && isfinite(o.z) && isfinite(o.w));
       *reinterpret_cast<float4*>(out + i) = o;
     }
     for (long long i = start + (nv << 2) + threadIdx.x; i < start + n; i += MU_THREADS) {
       float lv = __ldg(lr + i / row_len);
       if (use_log) lv = expf(lv);
-      out[i] = __fsub_rn(p[i], __fmul_rn(g[i], lv));
+      const float o = __fsub_rn(p[i], __fmul_rn(g[i], lv));
+      bad |= !isfinite(o);
+      out[i] = o;
     }
   } else {
     for (long long i = start + threadIdx.x; i < start + n; i += MU_THREADS) {
       float lv = __ldg(lr + i / row_len);
       if (use_log) lv = expf(lv);
-      out[i] = __fsub_rn(p[i], __fmul_rn(g[i], lv));
+      const float o = __fsub_rn(p[i], __fmul_rn(g[i], lv));
+      bad |= !isfinite(o);
+      out[i] = o;
     }
   }
+  if (bad && nonfinite) atomicOr(nonfinite, 1);
 }
 
 // Flat RAdam (radam.py:28-94).  Per-element group id selects (lr, weight_decay); the
@@ -153,11 +167,11 @@ using namespace eosvos;
 extern "C" int eosvos_meta_update_chunk_elems(void) { return MU_CHUNK; }
 
 extern "C" int eosvos_meta_update(const long long* table_dev, const int* chunks_dev, int num_chunks, int use_log,
-                                  eosvos_stream_t stream_) {
+                                  int* nonfinite_flag, eosvos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (num_chunks == 0) return 0;
   EOSVOS_REQUIRE(table_dev && chunks_dev && num_chunks > 0, "meta_update: null table");
-  meta_update_kernel<<<num_chunks, MU_THREADS, 0, stream>>>(table_dev, chunks_dev, use_log);
+  meta_update_kernel<<<num_chunks, MU_THREADS, 0, stream>>>(table_dev, chunks_dev, use_log, nonfinite_flag);
   return check_launch("meta_update_kernel");
 }
 

@@ -695,8 +695,10 @@ class MetaUpdatePlan:
         self.table = stager.put(rows, dev)
 
 
-def meta_update(plan, use_log=False):
-    call("eosvos_meta_update", _ptr(plan.table), _ptr(plan.chunks), plan.num_chunks, 1 if use_log else 0, _stream())
+def meta_update(plan, use_log=False, nonfinite=None):
+    """nonfinite: optional int32 device tensor, OR-ed with 1 when an updated parameter is Inf / NaN."""
+    call("eosvos_meta_update", _ptr(plan.table), _ptr(plan.chunks), plan.num_chunks, 1 if use_log else 0, _ptr(nonfinite),
+         _stream())
 
 
 def radam_step(p, g, m, v, *, gscale, clip, beta1, beta2, eps, lr, wd, step_size, rectified, clamp=None):

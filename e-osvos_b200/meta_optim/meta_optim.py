@@ -231,6 +231,26 @@ class MetaOptimizer(nn.Module):
             train_loss = train_loss.detach()
         self._train_loss = train_loss
 
+    def _nonfinite_flag(self, device):
+        f = getattr(self, "_nonfinite", None)
+        if f is None or f.device != device:
+            f = self._nonfinite = torch.zeros(1, dtype=torch.int32, device=device)
+        return f
+
+    def check_finite(self):
+        """Raises FloatingPointError when a fused update since the last check produced Inf / NaN parameters -- the
+        backward runs in 16-bit storage under the static loss scale `ops.GRAD_SCALE` (fp16: 1024), so an activation
+        gradient above 65504 / scale overflows.  One small device->host read: call it where the host synchronises
+        anyway (evaluate_sequence does after every fine-tuning round).  Lower `ops.GRAD_SCALE` (or build the bf16
+        variant, EOSVOS_ACT=bf16) if it fires."""
+        f = getattr(self, "_nonfinite", None)
+        if f is not None and int(f.item()) != 0:
+            f.zero_()
+            from .. import ops
+            raise FloatingPointError(
+                f"non-finite parameters after the fused MetaOptimizer update: the 16-bit backward overflowed under "
+                f"loss scale {ops.GRAD_SCALE}")
+
     def _step_eval(self, train_loss):
         """Evaluation-time step (no graph is kept through the update): theta <- theta - lr (.) grad in ONE kernel,
         in place in the model's parameter arena, without the autograd Function and with the pointer table cached
@@ -268,7 +288,7 @@ class MetaOptimizer(nn.Module):
                 if len(self._plan_cache) > 8:
                     self._plan_cache.clear()
                 self._plan_cache[key] = plan
-        K.meta_update(plan, bool(self._use_log_init_lr))
+        K.meta_update(plan, bool(self._use_log_init_lr), self._nonfinite_flag(dev))
         if params[0] is not outs[0]:
             for (m, n), o in zip(slots, outs):
                 m._parameters[n] = o

@@ -251,6 +251,8 @@ def evaluate_sequence(model, meta_optim, meta_optim_state_dict, frames, first_la
             loss = finetune(model, meta_optim, batch_fn, iters, seed, k, reset_model_mode,
                             early_stopping_cfg=early_stopping_cfg)
             torch.cuda.synchronize(device)
+            if hasattr(meta_optim, "check_finite"):
+                meta_optim.check_finite()         # loud failure if the scaled 16-bit backward overflowed
             timers["finetune_s"] += time.perf_counter() - t0
             timers["finetune_iters"] += iters
             train_loss_seq.append(loss)                                   # read back after the sequence

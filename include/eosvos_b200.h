@@ -160,10 +160,12 @@ int eosvos_roi_encode(const float* all_boxes, const long long* labels, const lon
 /* ---- K9: MetaOptimizer update (reference: meta_optim.py:177-214, meta_model.py:78-80) */
 /* table_dev: int64 [T][8] = (p, g, lr, out, numel, elements per lr row, g_taps, g_cin); g_taps > 1 means the gradient
  * of a [Cout][Cin][taps] filter is stored [Cout][taps][Cin] (channels_last, eosvos_conv2d_wgrad dw_layout 1);
- * chunks_dev: int32 [n][2] = (tensor, chunk index), chunk = eosvos_meta_update_chunk_elems() elements.  out may alias p. */
+ * chunks_dev: int32 [n][2] = (tensor, chunk index), chunk = eosvos_meta_update_chunk_elems() elements.  out may alias p.
+ * nonfinite_flag (optional, device int): OR-ed with 1 when an updated value is Inf / NaN (overflow of the scaled
+ * 16-bit backward); never reset by the library. */
 int eosvos_meta_update_chunk_elems(void);
 int eosvos_meta_update(const long long* table_dev, const int* chunks_dev, int num_chunks, int use_log,
-                       eosvos_stream_t stream);
+                       int* nonfinite_flag, eosvos_stream_t stream);
 /* ---- K10: outer RAdam step of meta-training (reference: radam.py:28-94, train_meta.py:361-373) */
 int eosvos_radam_step(float* p, const float* g, float* m, float* v, long long n, float gscale, float clip, float beta1,
                       float beta2, float one_minus_beta1, float one_minus_beta2, float eps, float lr, float wd,

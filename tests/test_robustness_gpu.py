@@ -1,0 +1,113 @@
+"""Precision robustness of the 16-bit path and cache-coherence regressions ("weak" items 7-8 and the
+advisor's stale-operand finding)."""
+from unittest import mock
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.test_model_gpu import build_pair, det_randperm, frame, nchw, rel  # noqa: E402
+
+
+def test_overflow_of_scaled_backward_is_detected(monkeypatch):
+    """The backward runs in fp16 storage under a static loss scale; an overflow must not pass silently: the fused
+    update flags non-finite results and MetaOptimizer.check_finite raises (evaluate_sequence calls it per round)."""
+    from eosvos_b200 import kernels, ops
+    if kernels.ACT_DTYPE != torch.float16:
+        pytest.skip("bf16 build: no loss scale")
+    model, opt, _, _, dev, _ = build_pair()
+    img, tgt = frame()
+    model.train_without_dropout()
+    loss, _ = model(img.to(dev), tgt.to(dev))
+    opt.set_train_loss(loss)
+    opt.step(loss)
+    opt.meta_model.detach_param_groups()
+    opt.check_finite()                                   # regular scale: fine
+    monkeypatch.setattr(ops, "GRAD_SCALE", 2.0 ** 30)    # every activation gradient overflows fp16
+    loss, _ = model(img.to(dev), tgt.to(dev))
+    opt.set_train_loss(loss)
+    opt.step(loss)
+    opt.meta_model.detach_param_groups()
+    with pytest.raises(FloatingPointError):
+        opt.check_finite()
+    opt.check_finite()                                   # the flag is cleared by the check
+
+
+def test_large_pre_norm_magnitudes():
+    """Trained checkpoints have pre-GroupNorm activations far above the unit scale of a fresh initialisation: scale
+    every normalised conv's weights by 64 (GroupNorm removes the factor again, so the fp32 result is unchanged up to
+    eps) and require the same stage parity as at unit scale -- fp16 storage of the conv outputs must not lose it --
+    and a finite backward."""
+    model, opt, oracle, oopt, dev, tol = build_pair()
+    img, tgt = frame()
+    with torch.no_grad():
+        for net in (model, oracle):
+            body = net.backbone.body
+            for name, m in body.named_modules():
+                if isinstance(m, torch.nn.Conv2d):
+                    m.weight.mul_(64.0)
+    from eosvos_b200 import ops
+    ops.clear_prep_cache()
+    oracle.train_without_dropout()
+    model.train_without_dropout()
+    with mock.patch("torch.randperm", det_randperm(5)):
+        torch.manual_seed(21)
+        oloss, olosses = oracle(img, tgt)
+    model.capture = {}
+    model.fixed_proposals = oracle.last_proposals
+    with mock.patch("torch.randperm", det_randperm(5)):
+        torch.manual_seed(21)
+        loss, losses = model(img.to(dev), tgt.to(dev))
+    cap = model.capture
+    model.capture, model.fixed_proposals = None, None
+    for a, b in zip(cap["feats"], oracle.last_features.values()):
+        assert torch.isfinite(a.float()).all()
+        assert rel(nchw(a), b) < tol
+    for k in olosses:
+        assert abs(losses[k].item() - olosses[k].item()) <= 2e-2 * abs(olosses[k].item()) + 1e-4, k
+    opt.set_train_loss(loss)
+    opt.step(loss)
+    opt.meta_model.detach_param_groups()
+    opt.check_finite()
+    assert all(bool(torch.isfinite(p).all()) for *_, p in opt.meta_model.param_groups())
+
+
+def test_operand_cache_follows_out_of_band_parameter_writes():
+    """Regression (advisor, round 1): the fused RAdam step and MetaModel's `.data` writers change parameter values
+    without bumping autograd's version counter; the cached 16-bit operand layouts of the eager modules must be rebuilt.
+    Two outer steps: the first inner forward of the second meta-iteration must see the updated theta_0 -- its loss
+    equals the loss of a freshly built forward on the same parameters (cache cleared by hand)."""
+    from eosvos_b200 import ops
+    from eosvos_b200.util import meta_train
+    model, opt, _, _, dev, _ = build_pair("BCE")
+    img, tgt = frame()
+    img2, tgt2 = frame(seed=12)
+    tb, mb = (img.to(dev), tgt.to(dev)), (img2.to(dev), tgt2.to(dev))
+    radam = meta_train.FusedRAdam(opt, model_init_lr=1e-2, log_init_lr_lr=1e-5)      # a visible outer step
+    for it in range(2):
+        with mock.patch("torch.randperm", det_randperm(5)):
+            meta_train.meta_iteration(model, opt, radam, [(tb, mb)], 1, num_epochs=1, bptt_epochs=1, seed=1, meta_iter=it)
+    opt.eval()
+    opt.reset()
+    model.train_without_dropout()
+
+    def first_loss():
+        with mock.patch("torch.randperm", det_randperm(7)):
+            torch.manual_seed(5)
+            return model(*tb)[0].item()
+    cached = first_loss()
+    ops.clear_prep_cache()
+    model._graphs.clear()
+    fresh = first_loss()
+    assert abs(cached - fresh) <= 2e-3 * abs(fresh), (cached, fresh)
+    # MetaModel writers
+    other = torch.nn.ParameterList([torch.nn.Parameter(p.detach() * 1.02) for p in model.parameters()])
+    first_loss()
+    opt.meta_model.copy_params_from(other)
+    a = first_loss()
+    ops.clear_prep_cache()
+    model._graphs.clear()
+    b = first_loss()
+    assert np.isfinite(a) and abs(a - b) <= 2e-3 * abs(b) and abs(a - cached) > 1e-4 * abs(cached), (a, b, cached)
