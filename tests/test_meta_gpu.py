@@ -155,3 +155,51 @@ def test_meta_gradients_vs_oracle():
     radam.step(flat, offs, gscale=1.0, grad_clip=None, lr_clamp=(0.0, float("inf")))
     assert any(not torch.equal(a, p.detach()) for a, (_, p) in zip(before, opt.named_parameters()))
     assert all(float(p.min()) >= 0.0 for n, p in opt.named_parameters() if n.startswith("log_init_lr"))
+
+
+def test_meta_run_worker_follows_reference_worker():
+    """`eosvos_b200.util.meta_run.meta_run` (reference signature and shared-memory protocol) on the synthetic DAVIS
+    train tree of tests/golden/meta_run.pt, with the configuration the UNMODIFIED reference worker ran under: the
+    worker must select the same task and feed the model the very same batches (same seeds => same frames: bit-equal
+    tensors), produce losses close to the reference's (its samplers use the CUDA generator, the golden run the CPU
+    one: 20 %), and hand back finite meta-gradients for all 402 tensors through `shared_meta_optim_grads`."""
+    import os
+    import tempfile
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200.meta_optim.meta_optim import MetaOptimizer
+    from eosvos_b200.util import helper_func, meta_run as MR
+    from eosvos_b200.util.evaluate import set_random_seeds
+    from oracle import ref_harness as RH
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meta_run.pt"), weights_only=False)
+    cfg = g["config"]
+    seen = []
+    real_init = helper_func.init_parent_model
+
+    def small_init(**kw):
+        model, states = real_init(**kw)
+        model.transform.min_size, model.transform.max_size = (g["min_size"],), g["max_size"]
+        model.register_forward_pre_hook(lambda m, a: seen.append((a[0].detach().cpu().clone(), a[1].detach().cpu().clone())))
+        return model, states
+
+    with tempfile.TemporaryDirectory() as wd, RH._cwd(wd):
+        RH.make_davis_tree(wd, [("synth_t", 9, 4, 1)], split="train_seqs", height=96, width=170)
+        set_random_seeds(cfg["seed"])
+        model, _ = real_init(**cfg["parent_model"])
+        opt = MetaOptimizer(model, **cfg["meta_optim_cfg"])
+        sd = {k: v.detach().clone() for k, v in opt.state_dict().items()}
+        grads = {n: torch.zeros_like(p) for n, p in opt.named_parameters()}
+        shared = {"sub_iter_done": False, "meta_epoch_done": False}
+        from unittest import mock
+        with mock.patch.object(MR, "init_parent_model", small_init):
+            MR.meta_run(0, model.state_dict(), sd, torch.get_rng_state(), cfg, cfg["datasets"]["train"], shared,
+                        {"meta_iter": 0, "meta_epoch": 0}, grads, None, 1, once=True)
+    assert shared["sub_iter_done"] is True
+    assert len(seen) == len(g["batches"]) == cfg["num_epochs"]["train"] + 1
+    for (x, y), (gx, gy, _) in zip(seen, g["batches"]):
+        assert torch.equal(x, gx.float() / 255.0) and torch.equal(y, gy.float())
+    tl, ml = shared["seqs_metrics"]["train_loss"]["synth_t"][0], shared["seqs_metrics"]["meta_loss"]["synth_t"][0]
+    rtl, rml = g["train_loss"]["synth_t"][0], g["meta_loss"]["synth_t"][0]
+    print("train loss", tl, "reference", rtl, "meta loss", ml, "reference", rml)
+    assert abs(tl - rtl) <= 0.2 * rtl and abs(ml - rml) <= 0.2 * rml
+    assert len(grads) == 402 and all(bool(torch.isfinite(v).all()) for v in grads.values())
+    assert sum(float(v.abs().sum()) > 0 for v in grads.values()) > 350
