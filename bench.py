@@ -231,7 +231,7 @@ def run_block(model, meta_optim, state_first, get_batch, get_frame, start_target
     if counts is not None:
         counts["n_det"] += [int(b.abs().sum().item() > 0) for b in rows]
     if read_back:
-        sink += float(probs.cpu().sum())     # evaluate.py:302 probs_frame_range.cpu()  (synchronises)
+        sink += float(E.to_host(probs).sum())     # evaluate.py:302 probs_frame_range.cpu()  (synchronises)
         sink += float(loss_host.sum())
     if ev is not None:
         ev[2].record()

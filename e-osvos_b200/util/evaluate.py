@@ -23,6 +23,23 @@ from . import augment
 from .helper_func import early_stopping
 
 
+_pinned = {}
+
+
+def to_host(t):
+    """Device -> host through a reused PINNED buffer (a plain `.cpu()` lands in pageable memory: a staged, several
+    times slower copy).  The returned tensor is overwritten by the next call with the same shape / dtype."""
+    key = (tuple(t.shape), t.dtype)
+    buf = _pinned.get(key)
+    if buf is None:
+        if len(_pinned) > 16:
+            _pinned.clear()
+        buf = _pinned[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return buf
+
+
 def set_random_seeds(seed):
     """helper_func.py:515-518"""
     random.seed(seed)
@@ -270,7 +287,7 @@ def evaluate_sequence(model, meta_optim, meta_optim_state_dict, frames, first_la
             fr = (to_dev(frames[f:f + 1]) for f in frame_ids)
             on_frame = (lambda i, t, p, b, k=k: hooks["on_frame"](obj, k, i, t, p, b)) if "on_frame" in hooks else None
             probs, bxs = run_frames(model, fr, to_dev(start_target), on_frame)
-            probs, bxs = probs.cpu(), bxs.cpu()
+            probs, bxs = to_host(probs), bxs.cpu()
             timers["infer_s"] += time.perf_counter() - t0
             timers["infer_frames"] += range_max - range_min
             for f, p, b in zip(frame_ids, probs, bxs):
