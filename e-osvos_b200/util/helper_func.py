@@ -39,3 +39,37 @@ def early_stopping(loss_hist, patience, min_loss_improv):
     best = min(float(v) for v in loss_hist)
     best_before = min(float(v) for v in loss_hist[:-patience])
     return not abs(best - best_before) > min_loss_improv
+
+
+NAMED_CONFIGS = {"DAVIS-2017": "meta_davis-2017.yaml", "YouTube-VOS": "meta_youtube-vos.yaml",
+                 "e-OSVOS": "eval_e-osvos.yaml", "e-OSVOS-OnA": "eval_e-osvos-OnA.yaml"}
+
+
+def compose_config(cfg_dir, named=(), overrides=None):
+    """The reference's Sacred configuration without Sacred (src/train_meta.py:21-31): `cfgs/meta.yaml` <-
+    `cfgs/torch.yaml` <- the named configs in the order given on the command line (`DAVIS-2017`, `YouTube-VOS`,
+    `e-OSVOS`, `e-OSVOS-OnA`) <- `key.sub=value` overrides as {"key.sub": value}.  `cfg_dir` = the reference's cfgs/
+    directory.  The result is the `_config` dict the `evaluate` / `meta_run` workers take."""
+    import copy
+    import os
+    import yaml
+
+    def merge(d, u):
+        for k, v in u.items():
+            if isinstance(v, dict) and isinstance(d.get(k), dict):
+                merge(d[k], v)
+            else:
+                d[k] = copy.deepcopy(v)
+        return d
+
+    cfg = {}
+    for f in ("meta.yaml", "torch.yaml") + tuple(NAMED_CONFIGS[n] for n in named):
+        with open(os.path.join(cfg_dir, f)) as fh:
+            merge(cfg, yaml.safe_load(fh) or {})
+    for key, val in (overrides or {}).items():
+        node = cfg
+        parts = key.split(".")
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+        node[parts[-1]] = val
+    return cfg

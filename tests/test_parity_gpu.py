@@ -536,3 +536,43 @@ def test_sparse_rpn_backward_matches_dense(monkeypatch):
     for k, (d, floor) in groups.items():
         print(f"{k:12s} sparse-vs-dense {d:.4f}   dense-vs-dense (noise floor) {floor:.4f}")
         assert d <= (2e-2 if k == "rpn" else 3 * floor + 2e-2), (k, d, floor)
+
+
+def test_youtube_vos_shaped_sequence_with_late_object():
+    """BASELINE configs[3] semantics on the GPU: a 1280x720 YouTube-VOS-shaped sequence (-> 1333x749, padded to
+    1344x768: the trunk shapes of the DAVIS case) with a second object whose first annotation is a LATER frame
+    (src/data/youtube.py:131-185; evaluate.py:143-146,156-170).  The product's evaluate_sequence runs free; the oracle
+    is replayed in lock-step per round / frame.  Checks the per-object schedules (the late object is fine-tuned on its
+    own first frame and only predicted after it) and the reference's quirk that the late object's propagation starts
+    without a target (the test loader's label file is the sequence's first one: empty for that object)."""
+    from eosvos_b200.util import davis_io
+    from eosvos_b200.util import evaluate as E
+    from oracle import ref_harness as RH
+    model, opt, oracle, _, dev, _ = build_pair(min_size=None)
+    model.roi_heads.score_thresh = oracle.roi_heads.score_thresh = 0.05
+    oracle.roi_heads.detections_per_img = 1
+    T, appear = 6, [0, 2]
+    frames, labels = RH.synthetic_video(21, T, 720, 1280, 2, appear=appear)
+    fr = torch.from_numpy(frames).permute(0, 3, 1, 2).float().div(255.0).contiguous()
+    lab = torch.from_numpy(labels)
+    annotated = [i in set(appear) for i in range(T)]
+    seq = davis_io.VideoSequence(fr, lab * torch.tensor(annotated)[:, None, None].to(lab.dtype), annotated=annotated,
+                                 objects=[(1, 0), (2, 2)], test_mode=True)
+    assert seq.num_objects == 2 and seq.gt_frame_id(1) == (2, 1)
+    assert float(seq.label(2, 1, None).sum()) == 0 and float(seq.label(2, 1, 1).sum()) > 0
+    state = copy.deepcopy(opt.state_dict())
+    ls = LockStep(model, opt, oracle, dev)
+    timers = {}
+    pred, stats = E.evaluate_sequence(model, opt, state, seq, num_epochs_eval=10, online_adapt_step=2, online_adapt_epochs=3,
+                                      batch_size=3, seed=1, random_train_transform=True, hooks=ls.hooks(), timers=timers)
+    # object 0: rounds over frames [1,3), [3,5), [5,6); object 1 (first annotated at 2): [3,5), [5,6)
+    rounds = sorted((o, k, tuple(r["frame_ids"])) for (o, k), r in ls.rounds.items())
+    assert rounds == [(0, 0, (1, 2)), (0, 1, (3, 4)), (0, 2, (5,)), (1, 0, (3, 4)), (1, 1, (5,))], rounds
+    assert timers["finetune_iters"] == (10 + 3 + 3) + (10 + 3) and timers["infer_frames"] == 5 + 3
+    assert ls.rounds[(1, 0)]["frames"][0]["target"] is None            # no start target for the late object
+    # the late object is never predicted before its first annotation -- and, as in the reference, not ON it either:
+    # `masks[frame][obj] = 2 * train_frame_gt` uses the test loader's (empty) label (evaluate.py:156-168)
+    assert (pred[:3] == 2).sum() == 0
+    infos = ls.replay(fr, lab)
+    _check_lockstep(infos, require_det=False)
+    assert pred.shape == (T, 720, 1280)
