@@ -62,6 +62,7 @@ SIGNATURES = {
     "eosvos_roi_encode": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "eosvos_meta_update_chunk_elems": [],
     "eosvos_meta_update": [_P, _P, _I, _I, _P, _P],
+    "eosvos_lr_grad": [_P, _P, _I, _I, _P],
     "eosvos_radam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
     "eosvos_permute_cast": [_P, _P, _P, _P, _P, _I, _I, _P],
     "eosvos_permute_cast_multi_chunk_elems": [],

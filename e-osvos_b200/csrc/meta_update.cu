@@ -133,6 +133,68 @@ meta_update_kernel(const long long* __restrict__ table, const int* __restrict__ 
   if (bad && nonfinite) atomicOr(nonfinite, 1);
 }
 
+// Meta-gradient of the learning rates through one fused update (first-order BPTT, reference
+// src/util/meta_run.py:124-214 via autograd of meta_model.py:78-80):  theta' = theta - lr (.) g  =>
+//     d L / d lr[row] = - sum_{j in row} d[j] * g[j]      (x exp(log_lr[row]) in log mode),
+// d = d L / d theta'.  One launch over all 201 tensors instead of 201 x (mul, sum, neg).
+// table: int64 [T][10] = (d, g, lr, dl, numel, row_len, g_taps, g_cin, d_taps, d_cin): *_taps > 1 marks a K x K filter
+// stored channels-last ([Cout][taps][Cin], what the wgrad epilogue emits) instead of [Cout][Cin][taps].
+// work: int32 [n][3] = (tensor, first row, kind): kind 0 = one CTA reduces ONE row (row_len >= 256), kind 1 = 256
+// consecutive rows, one thread each (short rows).  Deterministic: no atomics.
+__global__ void __launch_bounds__(MU_THREADS)
+lr_grad_kernel(const long long* __restrict__ table, const int* __restrict__ work, int use_log) {
+  const int t = work[blockIdx.x * 3], row0 = work[blockIdx.x * 3 + 1], kind = work[blockIdx.x * 3 + 2];
+  const long long* e = table + (size_t)t * 10;
+  const float* __restrict__ d = reinterpret_cast<const float*>(e[0]);
+  const float* __restrict__ g = reinterpret_cast<const float*>(e[1]);
+  const float* __restrict__ lr = reinterpret_cast<const float*>(e[2]);
+  float* __restrict__ dl = reinterpret_cast<float*>(e[3]);
+  const long long numel = e[4], row_len = e[5];
+  const int g_taps = (int)e[6], g_cin = (int)e[7], d_taps = (int)e[8], d_cin = (int)e[9];
+  const long long rows = numel / row_len;
+  // offset inside a filter (logical element j = ci * taps + tp) for a channels-last operand
+  auto off = [](long long j, int taps, int cin) -> long long {
+    if (taps <= 1) return j;
+    const long long ci = j / taps, tp = j - ci * taps;
+    return tp * cin + ci;
+  };
+  if (kind == 0) {
+    const long long base = (long long)row0 * row_len;
+    float acc = 0.f;
+    if (g_taps <= 1 && d_taps <= 1) {
+      for (long long j = threadIdx.x; j < row_len; j += MU_THREADS) acc += __ldcs(d + base + j) * __ldcs(g + base + j);
+    } else {
+      // a row of a K x K filter tensor is one filter (NEURON level) or the whole tensor: permute inside each filter
+      const long long filt = (long long)(g_taps > 1 ? g_taps : d_taps) * (g_taps > 1 ? g_cin : d_cin);
+      for (long long j = threadIdx.x; j < row_len; j += MU_THREADS) {
+        const long long f = j / filt, r = j - f * filt;
+        acc += d[base + f * filt + off(r, d_taps, d_cin)] * g[base + f * filt + off(r, g_taps, g_cin)];
+      }
+    }
+    __shared__ float s_w[MU_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < MU_THREADS / 32; ++w) tot += s_w[w];
+      dl[row0] = -tot * (use_log ? expf(lr[row0]) : 1.f);
+    }
+    return;
+  }
+  const long long row = (long long)row0 + threadIdx.x;
+  if (row >= rows) return;
+  const long long base = row * row_len;
+  float acc = 0.f;
+  if (g_taps <= 1 && d_taps <= 1) {
+    for (long long j = 0; j < row_len; ++j) acc += d[base + j] * g[base + j];
+  } else {
+    for (long long j = 0; j < row_len; ++j) acc += d[base + off(j, d_taps, d_cin)] * g[base + off(j, g_taps, g_cin)];
+  }
+  dl[row] = -acc * (use_log ? expf(lr[row]) : 1.f);
+}
+
 // Flat RAdam (radam.py:28-94).  Per-element group id selects (lr, weight_decay); the
 // rectification terms depend only on the step count and are computed on the host.
 //   g' = clamp(g * gscale, -clip, clip) ; m = b1 m + (1-b1) g' ; v = b2 v + (1-b2) g'^2
@@ -173,6 +235,15 @@ extern "C" int eosvos_meta_update(const long long* table_dev, const int* chunks_
   EOSVOS_REQUIRE(table_dev && chunks_dev && num_chunks > 0, "meta_update: null table");
   meta_update_kernel<<<num_chunks, MU_THREADS, 0, stream>>>(table_dev, chunks_dev, use_log, nonfinite_flag);
   return check_launch("meta_update_kernel");
+}
+
+extern "C" int eosvos_lr_grad(const long long* table_dev, const int* work_dev, int num_work, int use_log,
+                              eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (num_work == 0) return 0;
+  EOSVOS_REQUIRE(table_dev && work_dev && num_work > 0, "lr_grad: null table");
+  lr_grad_kernel<<<num_work, MU_THREADS, 0, stream>>>(table_dev, work_dev, use_log);
+  return check_launch("lr_grad_kernel");
 }
 
 extern "C" int eosvos_radam_step(float* p, const float* g, float* m, float* v, long long n, float gscale, float clip,

@@ -701,6 +701,56 @@ def meta_update(plan, use_log=False, nonfinite=None):
          _stream())
 
 
+_lr_work_cache = {}
+
+
+def lr_grad(douts, grads, lrs, use_log=False):
+    """d L / d lr_i = -rowsum(dout_i (.) grad_i) (x exp(lr_i) in log mode) for all tensors in ONE launch.
+    douts / grads: fp32, contiguous or (4-D) channels_last; lrs: fp32, numel divides the tensor's numel.
+    -> list of tensors shaped like lrs."""
+    import numpy as np
+    dev = douts[0].device
+    T = len(douts)
+    tab = np.empty((T, 10), dtype=np.int64)
+    total = sum(l.numel() for l in lrs)
+    flat = torch.empty((total,), device=dev, dtype=torch.float32)
+    outs, o = [], 0
+
+    def layout(x):
+        if x.is_contiguous():
+            return 1, 1
+        if x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last):
+            return x.shape[2] * x.shape[3], x.shape[1]
+        raise _lib.EosvosError("lr_grad: operands must be contiguous or channels_last")
+    sig = []
+    for t, (d, g, l) in enumerate(zip(douts, grads, lrs)):
+        n = d.numel()
+        if g.numel() != n or n % l.numel() != 0 or d.dtype != torch.float32 or g.dtype != torch.float32:
+            raise _lib.EosvosError("lr_grad: sizes / dtypes do not match")
+        gt, gc = layout(g)
+        dt, dc = layout(d)
+        out = flat[o:o + l.numel()]
+        tab[t] = (d.data_ptr(), g.data_ptr(), l.data_ptr(), out.data_ptr(), n, n // l.numel(), gt, gc, dt, dc)
+        outs.append(out.view(l.shape))
+        o += l.numel()
+        sig.append((n, l.numel()))
+    key = (str(dev), tuple(sig))
+    hit = _lr_work_cache.get(key)
+    if hit is None:
+        work = []
+        for t, (n, rows) in enumerate(sig):
+            if n // rows >= 256:
+                work += [(t, r, 0) for r in range(rows)]
+            else:
+                work += [(t, r, 1) for r in range(0, rows, 256)]
+        hit = (torch.tensor(work, dtype=torch.int32).to(dev), len(work))
+        _lr_work_cache.clear()
+        _lr_work_cache[key] = hit
+    table = stager.put(tab, dev) if tab.nbytes <= stager.slot_bytes else torch.from_numpy(tab).to(dev)
+    call("eosvos_lr_grad", _ptr(table), _ptr(hit[0]), hit[1], 1 if use_log else 0, _stream())
+    return outs
+
+
 def radam_step(p, g, m, v, *, gscale, clip, beta1, beta2, eps, lr, wd, step_size, rectified, clamp=None):
     for t in (p, g, m, v):
         _chk(t, torch.float32, "radam operand")

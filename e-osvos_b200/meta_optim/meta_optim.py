@@ -56,27 +56,17 @@ class _FusedUpdateFn(torch.autograd.Function):
         n = ctx.n
         saved = ctx.saved_tensors
         gs, ls = saved[:n], saved[n:]
-        dps, dls = [], []
-        for i in range(n):
-            d = douts[i]
-            if d is None:
-                dps.append(None)
-                dls.append(None)
-                continue
-            dps.append(d)
-            if ctx.needs_input_grad[4 + 2 * n + i]:
-                prod = -(d * gs[i])
-                red = [k for k in range(prod.dim()) if ls[i].shape[k] == 1 and prod.shape[k] != 1] \
-                    if ls[i].dim() == prod.dim() else None
-                if red is None:
-                    dl = prod.sum().reshape(ls[i].shape) if ls[i].numel() == 1 else prod.reshape(ls[i].shape)
-                else:
-                    dl = prod.sum(dim=red, keepdim=True) if red else prod
-                if ctx.use_log:
-                    dl = dl * ls[i].exp()
-                dls.append(dl)
-            else:
-                dls.append(None)
+        live = [i for i in range(n) if douts[i] is not None]
+        dls = [None] * n
+        want = [i for i in live if ctx.needs_input_grad[4 + 2 * n + i]]
+        if want:
+            # d L / d lr = -rowsum(upstream (.) grad) for every tensor in one launch (meta_update.cu::lr_grad_kernel)
+            ds = [douts[i] if (douts[i].is_contiguous() or (douts[i].dim() == 4 and douts[i].is_contiguous(
+                memory_format=torch.channels_last))) else douts[i].contiguous() for i in want]
+            res = K.lr_grad(ds, [gs[i] for i in want], [ls[i] for i in want], ctx.use_log)
+            for i, r in zip(want, res):
+                dls[i] = r
+        dps = [douts[i] for i in range(n)]
         return (None, None, None, None, *dps, *([None] * n), *dls)
 
 

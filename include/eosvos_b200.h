@@ -166,6 +166,9 @@ int eosvos_roi_encode(const float* all_boxes, const long long* labels, const lon
 int eosvos_meta_update_chunk_elems(void);
 int eosvos_meta_update(const long long* table_dev, const int* chunks_dev, int num_chunks, int use_log,
                        int* nonfinite_flag, eosvos_stream_t stream);
+/* d loss / d learning rate through one fused update (first-order BPTT of meta_run.py:124-214): see csrc/meta_update.cu
+ * for the table ([T][10] int64) and work-list ([n][3] int32) layouts */
+int eosvos_lr_grad(const long long* table_dev, const int* work_dev, int num_work, int use_log, eosvos_stream_t stream);
 /* ---- K10: outer RAdam step of meta-training (reference: radam.py:28-94, train_meta.py:361-373) */
 int eosvos_radam_step(float* p, const float* g, float* m, float* v, long long n, float gscale, float clip, float beta1,
                       float beta2, float one_minus_beta1, float one_minus_beta2, float eps, float lr, float wd,

@@ -26,7 +26,8 @@ def test_fused_update_autograd_matches_torch():
         got = torch.autograd.grad(sum((o * w).sum() for o, w in zip(outs, ws)), ps + ls)
         exp = torch.autograd.grad(sum((o * w).sum() for o, w in zip(ref, ws)), ps + ls)
         for a, b in zip(got, exp):
-            assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+            # d / d lambda is a row sum of up to 27 products of O(1) terms: the fused kernel sums in another order
+            assert torch.allclose(a, b, rtol=1e-5, atol=5e-6)
 
 
 def test_fused_radam_matches_reference():
@@ -203,3 +204,30 @@ def test_meta_run_worker_follows_reference_worker():
     assert abs(tl - rtl) <= 0.2 * rtl and abs(ml - rml) <= 0.2 * rml
     assert len(grads) == 402 and all(bool(torch.isfinite(v).all()) for v in grads.values())
     assert sum(float(v.abs().sum()) > 0 for v in grads.values()) > 350
+
+
+def test_lr_grad_kernel_on_real_tensor_set():
+    """lr_grad_kernel (d L / d lambda through the fused update) on the model's 201 tensors with NEURON-level rates,
+    K x K filter gradients in channels-last memory order as the wgrad epilogue emits them, lin and log mode."""
+    import eosvos_b200  # noqa: F401
+    from eosvos_b200 import kernels as K
+    from tests.test_model_gpu import build_pair
+    model, opt, _, _, dev, _ = build_pair()
+    params = [p.detach() for *_, p in opt.meta_model.param_groups()]
+    g = torch.Generator(device="cpu").manual_seed(0)
+    grads = [torch.randn(p.shape, generator=g).to(dev) for p in params]
+    grads = [x.contiguous(memory_format=torch.channels_last) if (x.dim() == 4 and x.shape[-1] > 1) else x for x in grads]
+    douts = [torch.randn(p.shape, generator=g).to(dev) for p in params]
+    douts = [x.contiguous(memory_format=torch.channels_last) if (x.dim() == 4 and x.shape[-1] > 1 and i % 2) else x
+             for i, x in enumerate(douts)]
+    for use_log in (False, True):
+        lrs = [(l.detach().log() if use_log else l.detach()) for l in opt.log_init_lr]
+        got = K.lr_grad(douts, grads, lrs, use_log)
+        for d, gg, l, r in zip(douts, grads, lrs, got):
+            red = [k for k in range(d.dim()) if l.shape[k] == 1 and d.shape[k] != 1]
+            want = -(d.double() * gg.double())
+            want = want.sum(dim=red, keepdim=True) if red else want
+            if use_log:
+                want = want * l.double().exp()
+            assert r.shape == l.shape
+            assert torch.allclose(r.double(), want, rtol=1e-4, atol=1e-4 * float(want.abs().max() + 1e-12))
