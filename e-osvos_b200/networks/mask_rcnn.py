@@ -373,6 +373,9 @@ class MaskRCNN(_MaskRCNN):
         through the host-side section.  Two alternating graph instances keep frame f's features intact."""
         if self.training or not self.use_cuda_graphs or self.capture is not None:
             return
+        if (os.environ.get("EOSVOS_FRAME_GRAPH", "1") != "0" and self._fast_ok() and self.num_classes == 2
+                and self.roi_heads.detections_per_img == 1):
+            return            # the whole frame replays as one graph: nothing to run ahead
         x8, _, sizes, padded = self._transform(inputs, None)
         slot = self._pf_slot
         self._pf_slot ^= 1
@@ -1318,6 +1321,125 @@ class MaskRCNN(_MaskRCNN):
                                          self._mask_slots_eval, mask_kinds, False, alias_inputs=4)
         return det, mask_logits
 
+    def _frame_functional(self, img, stats, fallback, rnd, *theta):
+        """A whole inference frame as a pure function of tensors with static shapes -- what the frame graph captures:
+        transform, trunk, RPN head, proposal kernels, EXTEND / REPLACE boxes, box branch, arg-max detection, mask
+        branch on the one RoI, paste / threshold / next-target tail.  Configuration (mode, thresholds, sizes) is read
+        from self._frame_cfg and is part of the graph key."""
+        slots = self._frame_slots
+        saved = [m._parameters[n] for m, n in slots]
+        for (m, n), t in zip(slots, theta):
+            m._parameters[n] = t
+        if self._active_plan is not None:
+            self._active_plan.launch()
+            for k in [k for k in ops._scope if isinstance(k[1], tuple) and k[1][0] == "head"]:
+                del ops._scope[k]
+        try:
+            cfg = self._frame_cfg
+            rpn, rh, tr = self.rpn, self.roi_heads, self.transform
+            B, _, h, w = img.shape
+            oh, ow, Hp, Wp = cfg["oh"], cfg["ow"], cfg["Hp"], cfg["Wp"]
+            x8 = K.transform(img, oh, ow, Hp, Wp, tr.image_mean, tr.image_std, Cs=8)
+            feats = self._backbone_eager(x8)
+            head_outs = self._rpn_head(feats)
+            image_sizes, image_shape = [(oh, ow)] * B, (B, 3, Hp, Wp)
+            post, mode, Kc = cfg["post"], cfg["mode"], self.num_classes - 1
+            if cfg["has_target"] and mode is not None:
+                n_aug = post // 2 if mode == 'EXTEND' else post
+                n_front = post // 2 if mode == 'EXTEND' else 0
+                padded = torch.empty((B, n_front + n_aug * Kc, 4), device=img.device, dtype=torch.float32)
+                count = torch.zeros((B,), device=img.device, dtype=torch.int32)
+                if n_front:
+                    _, count = self._rpn_fast(feats, image_shape, image_sizes, head_outs, n_front, padded, 0)
+                rw = float(torch.tensor(ow, dtype=torch.float32) / torch.tensor(w, dtype=torch.float32))
+                rh_ = float(torch.tensor(oh, dtype=torch.float32) / torch.tensor(h, dtype=torch.float32))
+                K.extend_boxes(stats, fallback, rnd, n_aug, rw, rh_, float(Wp), float(Hp), 0.1, padded, n_front)
+            else:
+                padded, count = self._rpn_fast(feats, image_shape, image_sizes, head_outs, post)
+            R = padded.shape[1]
+            rois5 = torch.cat([self._image_index(B, R, img.device), padded], dim=2).view(B * R, 5)
+            head = self._box_branch(feats[:4], rois5)
+            back_h = float(torch.tensor(h, dtype=torch.float32) / torch.tensor(oh, dtype=torch.float32))
+            back_w = float(torch.tensor(w, dtype=torch.float32) / torch.tensor(ow, dtype=torch.float32))
+            nc = rh.box_predictor.cls_score.weight.shape[0]
+            det = K.det_top1(head, padded.view(B * R, 4), B, R, nc, rh.box_coder.weights, rh.box_coder.bbox_xform_clip,
+                             cfg["score_thresh"], 1e-2, float(ow), float(oh), back_w, back_h)
+            mask_logits = self._mask_branch_rois(feats[:4], det["roi"])
+            probs, tgt, stats_out = K.mask_paste_threshold(mask_logits, det["chan"], det["label"], det["box"], B, Kc, h, w,
+                                                           0.5, want_target=True)
+            return probs, det["box"], tgt, stats_out, padded, count, det["row"]
+        finally:
+            for (m, n), t in zip(slots, saved):
+                m._parameters[n] = t
+
+    def _image_index(self, B, R, device):
+        img_idx = getattr(self, "_img_idx_cache", None)
+        if img_idx is None or img_idx.shape != (B, R, 1) or img_idx.device != device:
+            img_idx = torch.arange(B, device=device, dtype=torch.float32).view(B, 1, 1).expand(B, R, 1).contiguous()
+            self._img_idx_cache = img_idx
+        return img_idx
+
+    def _forward_eval_frame_graph(self, inputs, targets, dev_stats):
+        """Inference frame as ONE CUDA-graph replay (everything is shape-static at inference: see _frame_functional).
+        Host work per frame: the reference's CPU random numbers for the jittered boxes (uploaded), three small input
+        copies, one replay."""
+        device = inputs.device
+        B, _, h, w = inputs.shape
+        rpn, rh = self.rpn, self.roi_heads
+        oh, ow = self._resized_size(h, w)
+        div = int(self.transform.size_divisible)
+        Hp, Wp = (oh + div - 1) // div * div, (ow + div - 1) // div * div
+        mode = rpn._eval_augment_proposals_mode
+        has_target = targets is not None and mode is not None
+        post = rpn.post_nms_top_n()
+        Kc = self.num_classes - 1
+        cfg = dict(oh=oh, ow=ow, Hp=Hp, Wp=Wp, mode=mode, has_target=has_target, post=post,
+                   score_thresh=float(rh.score_thresh))
+        if getattr(self, "_frame_slots", None) is None:
+            mods = (self.backbone, rpn.head, rh.box_head, rh.box_predictor, rh.mask_head, rh.mask_predictor)
+            self._frame_slots = [(m, n) for mod in mods for _, m in mod.named_modules()
+                                 for n, p in m._parameters.items() if p is not None]
+        conv1, fc6, C = self.backbone.body.conv1, rh.box_head.fc6, self.backbone.out_channels
+
+        def kinds(m, n, t):
+            if n != "weight":
+                return ()
+            if m is conv1:
+                return ("stem",)
+            if isinstance(m, nn.ConvTranspose2d):
+                return ("dc",)
+            if isinstance(m, nn.Conv2d) and t.shape[0] >= 64:
+                return ("f",)
+            if isinstance(m, nn.Linear) and t.shape[0] >= 64:
+                return (("lf", C if m is fc6 else 0),)
+            return ()
+        if has_target:
+            stats, fallback = dev_stats
+            n_aug = post // 2 if mode == 'EXTEND' else post
+            rnd = self._extend_rands(B, Kc, n_aug, device)
+            fallback = stats if fallback is None else fallback
+        else:
+            dummy = getattr(self, "_frame_dummy", None)
+            if dummy is None or dummy[0].device != device:
+                dummy = self._frame_dummy = (torch.zeros((B, Kc, 5), dtype=torch.int32, device=device),
+                                             torch.zeros((1,), device=device))
+            stats = fallback = dummy[0]
+            rnd = dummy[1]
+        key = ("frame", (B, h, w), mode, has_target, post, rpn.pre_nms_top_n(), float(rh.score_thresh), float(rpn.nms_thresh),
+               device.index)
+        self._frame_cfg = cfg
+        K.zero_pool.reset()
+        probs, box, tgt, stats_out, padded, count, row = self._graphed_call(
+            key, self._frame_functional, [inputs.to(torch.float32).contiguous(), stats, fallback, rnd], self._frame_slots,
+            kinds, False)
+        n_front = (post // 2 if mode == 'EXTEND' else 0) if has_target else post
+        self._last_padded = (padded, count if n_front else None, n_front)
+        self._last_det = {"row": row}
+        # the graph's output buffers are rewritten by the next frame: hand out copies of what the caller keeps
+        self.last_propagated_target = tgt.clone()
+        self.last_target_stats = stats_out.clone()
+        return probs.clone(), box.clone().view(B, Kc, 4)
+
     def _forward_eval_fast(self, inputs, targets, dev_stats):
         """Inference frame without a host synchronisation (helper_func.py:100-126 body): transform, trunk graph,
         proposal kernels, EXTEND / REPLACE boxes from the device-resident target box, box graph, arg-max detection,
@@ -1542,6 +1664,8 @@ class MaskRCNN(_MaskRCNN):
                     # reference asserts here that the target holds at least one object (mask_rcnn.py:623); without
                     # the read-back an empty target yields degenerate boxes and no detection instead of raising.
                     dev_stats = (K.mask_to_bbox(targets.to(torch.float32).contiguous(), self.num_classes - 1), None)
+            if os.environ.get("EOSVOS_FRAME_GRAPH", "1") != "0":
+                return self._forward_eval_frame_graph(inputs, targets, dev_stats)
             return self._forward_eval_fast(inputs, targets, dev_stats)
         self._last_padded, self._last_det = None, None
         if targets is not None:
