@@ -70,10 +70,15 @@ static int pick_bn(int n_cols, long long m_tiles, int bn_hint) {
   if (bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return bn_hint;
   if (bn_hint == 512) return 256;   // CTA-pair kernel forced
   if (n_cols <= 64) return 64;
+  const long long sms = num_sms();
+  // launches that cannot fill the chip even with 128-column tiles are latency-bound (one tile per CTA): the narrowest
+  // tile gives the most CTAs and the deepest ring (conv_fprop.cu FpropCfg<BN, DEEP>); measured 1.1-1.25x on layer3/4,
+  // the mask head and the coarse pyramid levels, more at batch 1
+  if (m_tiles * ((n_cols + 127) / 128) <= sms && m_tiles * ((n_cols + 63) / 64) <= 2 * sms) return 64;
   if (n_cols <= 128) return 128;
   // wide outputs: 256-column tiles halve A re-reads, but only when the grid still fills the chip
   const long long ctas256 = m_tiles * ((n_cols + 255) / 256);
-  if (n_cols % 256 == 0 && ctas256 >= (long long)num_sms()) return 256;
+  if (n_cols % 256 == 0 && ctas256 >= sms) return 256;
   return 128;
 }
 

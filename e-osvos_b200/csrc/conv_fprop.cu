@@ -15,10 +15,14 @@
 
 namespace eosvos {
 
-template <int BN>
+// DEEP: launches whose tiles fit in ONE wave of one CTA per SM (most layers at batch 1, layer3/4 + the small pyramid
+// levels at batch 3).  A CTA then sees a single tile, so nothing overlaps its K loop except its own ring: measured, a
+// 36-block K loop takes ~18 us whatever the tile (0.5 us per 64-wide K block = load latency / ring depth).  These
+// launches get the whole shared memory of the SM as ONE deep ring (8 / 6 / 4 stages) instead of two CTAs with 4 / 3.
+template <int BN, bool DEEP = false>
 struct FpropCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 3 : 4);
-  static constexpr int CTAS_PER_SM = BN == 256 ? 1 : 2;
+  static constexpr int STAGES = DEEP ? (BN == 256 ? 4 : (BN == 128 ? 6 : 8)) : (BN == 256 ? 4 : (BN == 128 ? 3 : 4));
+  static constexpr int CTAS_PER_SM = (DEEP || BN == 256) ? 1 : 2;
   static constexpr uint32_t TMEM_COLS = 2 * BN;      // two accumulators: 128, 256 or 512 columns
   static constexpr int SMEM = 1024 + STAGES * (128 * 128 + BN * 128) + 256;
 };
@@ -217,14 +221,14 @@ __device__ __forceinline__ void fprop_epilogue_tile(const FpropParams& p, const 
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(192, FpropCfg<BN>::CTAS_PER_SM)
+template <int BN, bool DEEP>
+__global__ void __launch_bounds__(192, FpropCfg<BN, DEEP>::CTAS_PER_SM)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const FpropParams p) {
-  constexpr int STAGES = FpropCfg<BN>::STAGES;
+  constexpr int STAGES = FpropCfg<BN, DEEP>::STAGES;
   constexpr int A_STAGE = 128 * 128;
   constexpr int B_STAGE = BN * 128;
-  constexpr uint32_t TMEM_COLS = FpropCfg<BN>::TMEM_COLS;
+  constexpr uint32_t TMEM_COLS = FpropCfg<BN, DEEP>::TMEM_COLS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -531,20 +535,31 @@ static int launch_fprop_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   return check_launch("conv_fprop_pair_kernel");
 }
 
-template <int BN>
-static int launch_fprop_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t stream) {
-  constexpr int SMEM = FpropCfg<BN>::SMEM;
+template <int BN, bool DEEP>
+static int launch_fprop_td(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t stream) {
+  constexpr int SMEM = FpropCfg<BN, DEEP>::SMEM;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_fprop)");
     attr_done = true;
   }
   const long long total = (long long)p.m_tiles * p.n_tiles_n;
-  const long long slots = (long long)num_sms() * FpropCfg<BN>::CTAS_PER_SM;
+  const long long slots = (long long)num_sms() * FpropCfg<BN, DEEP>::CTAS_PER_SM;
   dim3 grid((unsigned)(total < slots ? total : slots));
-  conv_fprop_kernel<BN><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
+  conv_fprop_kernel<BN, DEEP><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
   return check_launch("conv_fprop_kernel");
+}
+
+template <int BN>
+static int launch_fprop_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, cudaStream_t stream) {
+  static const bool deep_ok = [] {
+    const char* e = getenv("EOSVOS_FPROP_DEEP");
+    return !(e && e[0] == '0');
+  }();
+  const long long total = (long long)p.m_tiles * p.n_tiles_n;
+  if (deep_ok && BN != 256 && total <= (long long)num_sms()) return launch_fprop_td<BN, true>(tmA, tmB, p, stream);
+  return launch_fprop_td<BN, false>(tmA, tmB, p, stream);
 }
 
 int launch_fprop(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const FpropParams& p, int m_tiles,
