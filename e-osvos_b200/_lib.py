@@ -43,6 +43,7 @@ SIGNATURES = {
     "eosvos_mask_loss_bce": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "eosvos_mask_paste_threshold": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "eosvos_mask_to_bbox": [_P, _P, _I, _I, _I, _I, _P],
+    "eosvos_jf_counts": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "eosvos_nms_scratch_bytes": [_I, _I],
     "eosvos_nms_segments": [_P, _P, _I, _I, _F, _P, _P, _P],
     "eosvos_rpn_scratch_bytes": [_I, _P, _I, _I],

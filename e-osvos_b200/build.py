@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeosvos_b200.so")
-SOURCES = ["common.cu", "conv_gemm.cu", "conv_fprop.cu", "conv_api.cu", "gn.cu", "roi_align.cu", "mask_loss.cu", "mask_tail.cu",
+SOURCES = ["common.cu", "conv_gemm.cu", "conv_fprop.cu", "conv_api.cu", "gn.cu", "roi_align.cu", "mask_loss.cu", "mask_tail.cu", "jf_measure.cu",
            "meta_update.cu", "misc.cu", "nms.cu", "rpn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]

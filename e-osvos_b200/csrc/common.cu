@@ -1,5 +1,6 @@
 // Error state, device checks and library identification for libeosvos_b200.so.
 #include "common.h"
+#include <stdlib.h>
 #include "../../include/eosvos_b200.h"
 #include <string.h>
 #include <cuda.h>
@@ -33,6 +34,14 @@ int num_sms() {
       n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("EOSVOS_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 }  // namespace eosvos

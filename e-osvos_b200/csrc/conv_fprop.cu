@@ -13,6 +13,12 @@
 #include "ptx.cuh"
 #include "common.h"
 
+// Timing-only diagnostic builds (tools/diag_kblock.py; never the product library): bit 0 drops the A-operand TMA loads,
+// bit 1 the B-operand loads, bit 2 the MMAs of the single-CTA kernel, to see which of them bounds a K block.
+#ifndef EOSVOS_DIAG
+#define EOSVOS_DIAG 0
+#endif
+
 namespace eosvos {
 
 // DEEP: launches whose tiles fit in ONE wave of one CTA per SM (most layers at batch 1, layer3/4 + the small pyramid
@@ -267,11 +273,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is private to the CTA: it overlaps the tail of the previous kernel; from here on global memory
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)p.a_bytes + (uint32_t)B_STAGE;
+      const uint32_t tx = ((EOSVOS_DIAG & 1) ? 0u : (uint32_t)p.a_bytes) + ((EOSVOS_DIAG & 2) ? 0u : (uint32_t)B_STAGE);
       int gi = 0;  // global k-block counter across tiles -> ring stage / phase
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles_n) * BN;
@@ -289,9 +298,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_arrive_expect_tx(&full[s], tx);
           const int tap = it / p.kchunks;
           const int kc = it - tap * p.kchunks;
-          tma_load_5d(sA + s * A_STAGE, &tmA, &full[s], p.tap_delta[tap][0] + kc * 64, base[0] + p.tap_delta[tap][1],
-                      base[1] + p.tap_delta[tap][2], base[2] + p.tap_delta[tap][3], base[3] + p.tap_delta[tap][4]);
-          tma_load_2d(sB + s * B_STAGE, &tmB, &full[s], p.tap_bk[tap] + kc * 64, n0);
+          if (!(EOSVOS_DIAG & 1))
+            tma_load_5d(sA + s * A_STAGE, &tmA, &full[s], p.tap_delta[tap][0] + kc * 64, base[0] + p.tap_delta[tap][1],
+                        base[1] + p.tap_delta[tap][2], base[2] + p.tap_delta[tap][3], base[3] + p.tap_delta[tap][4]);
+          if (!(EOSVOS_DIAG & 2)) tma_load_2d(sB + s * B_STAGE, &tmB, &full[s], p.tap_bk[tap] + kc * 64, n0);
         }
       }
     }
@@ -313,7 +323,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
           const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < ((EOSVOS_DIAG & 4) ? 0 : 4); ++k) {
             const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
             const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
             umma_f16kind(acc, ad, bd, idesc, (uint32_t)((it | k) != 0));
@@ -547,7 +557,8 @@ static int launch_fprop_td(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   const long long total = (long long)p.m_tiles * p.n_tiles_n;
   const long long slots = (long long)num_sms() * FpropCfg<BN, DEEP>::CTAS_PER_SM;
   dim3 grid((unsigned)(total < slots ? total : slots));
-  conv_fprop_kernel<BN, DEEP><<<grid, 192, SMEM, stream>>>(tmA, tmB, p);
+  cudaError_t le = launch_pdl(conv_fprop_kernel<BN, DEEP>, grid, dim3(192), SMEM, stream, tmA, tmB, p);
+  if (le != cudaSuccess) return set_cuda_error(le, "conv_fprop_kernel launch");
   return check_launch("conv_fprop_kernel");
 }
 

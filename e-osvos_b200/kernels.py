@@ -450,6 +450,24 @@ def mask_to_bbox(target, K):
     return stats
 
 
+def jf_counts(pred, gt, num_objects, radius):
+    """pred, gt [T,H,W] uint8 object ids -> counts [T,num_objects,6] int32 (intersection, union, |boundary pred|,
+    |boundary gt|, matched pred boundary, matched gt boundary).  Eight objects per launch pair."""
+    _chk(pred, torch.uint8, "pred")
+    _chk(gt, torch.uint8, "gt")
+    if pred.shape != gt.shape or pred.dim() != 3:
+        raise ValueError("jf_counts: pred and gt must both be [T,H,W]")
+    T, H, W = pred.shape
+    bmap = torch.empty((T, 2, H, W), device=pred.device, dtype=torch.uint8)
+    parts = []
+    for id0 in range(0, num_objects, 8):
+        k = min(8, num_objects - id0)
+        counts = torch.empty((T, k, 6), device=pred.device, dtype=torch.int32)
+        call("eosvos_jf_counts", _ptr(pred), _ptr(gt), _ptr(bmap), _ptr(counts), T, id0, k, H, W, int(radius), _stream())
+        parts.append(counts)
+    return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+
+
 # ------------------------------------------------------------------------------------------- K5
 def nms_segments(boxes_sorted, seg_offsets, num_segments, max_seg, thresh):
     """boxes [n,4] fp32 sorted by descending score inside each segment; seg_offsets int32 [S+1] (device).

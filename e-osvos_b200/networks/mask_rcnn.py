@@ -113,6 +113,7 @@ class MaskRCNN(_MaskRCNN):
         self._trunk_slots = None
         self._side_stream = None
         self._prefetched = {}
+        self._lookahead = None
         self._pf_slot = 0
         self._theta_home = None
         self._active_plan = None
@@ -145,6 +146,8 @@ class MaskRCNN(_MaskRCNN):
         super(MaskRCNN, self).train(mode)
         if mode and getattr(self, "_prefetched", None):
             self._prefetched.clear()            # look-ahead features are only valid for the weights they ran on
+        if mode:
+            self._lookahead = None
         if not self._train_encoder:
             self.backbone.eval()
         if not self._accum_batch_norm_stats:
@@ -486,7 +489,7 @@ class MaskRCNN(_MaskRCNN):
             # never continue in a zero block it touched
             K.zero_pool.reset()
             ent = (graphed, per_call, plan, vals)
-            if len(self._graphs) >= 24:         # bounded: graphs pin their activation pools
+            if len(self._graphs) >= 40:         # bounded: graphs pin their activation pools
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = ent
         from .. import _lib
@@ -532,7 +535,7 @@ class MaskRCNN(_MaskRCNN):
             fms = [torch.empty((image_shape[0], 1, h, w), device=device, dtype=torch.float32) for h, w in feat_shapes]
             hit = [a.detach() for a in self.rpn.anchor_generator(il, fms)]
             torch.cuda.current_stream(device).synchronize()     # once per signature
-            if len(self._anchor_cache) >= 8:
+            if len(self._anchor_cache) >= 64:     # (well above the graph cache: captured graphs read these in place)
                 self._anchor_cache.pop(next(iter(self._anchor_cache)))
             self._anchor_cache[key] = hit
         return hit
@@ -615,15 +618,17 @@ class MaskRCNN(_MaskRCNN):
         return {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
 
     def _segment_offsets(self, N, sizes, device):
+        # kept per signature for the life of the model: captured graphs hold the address of the entry they saw
         key = (N, tuple(sizes), str(device))
-        if getattr(self, "_seg_cache_key", None) != key:
+        cache = self.__dict__.setdefault("_seg_cache", {})
+        hit = cache.get(key)
+        if hit is None:
             offs = [0]
             for _ in range(N):
                 for k in sizes:
                     offs.append(offs[-1] + k)
-            self._seg_cache = torch.tensor(offs, dtype=torch.int32, device=device)
-            self._seg_cache_key = key
-        return self._seg_cache
+            hit = cache[key] = torch.tensor(offs, dtype=torch.int32, device=device)
+        return hit
 
     def _rpn_fast(self, feats, image_shape, image_sizes, head_outs, post_n, out=None, out_offset=0):
         """tv rpn.py filter_proposals on statically shaped buffers (csrc/rpn.cu): per-level top-k + decode of the
@@ -1279,11 +1284,7 @@ class MaskRCNN(_MaskRCNN):
         rh = self.roi_heads
         device = feats[0].device
         B, R = padded.shape[0], padded.shape[1]
-        img_idx = getattr(self, "_img_idx_cache", None)
-        if img_idx is None or img_idx.shape != (B, R, 1) or img_idx.device != device:
-            img_idx = torch.arange(B, device=device, dtype=torch.float32).view(B, 1, 1).expand(B, R, 1).contiguous()
-            self._img_idx_cache = img_idx
-        rois5 = torch.cat([img_idx, padded], dim=2).view(B * R, 5)
+        rois5 = torch.cat([self._image_index(B, R, device), padded], dim=2).view(B * R, 5)
         C = feats[0].shape[-1]
         fc6 = rh.box_head.fc6
         if getattr(self, "_box_slots_eval", None) is None:
@@ -1372,11 +1373,199 @@ class MaskRCNN(_MaskRCNN):
             for (m, n), t in zip(slots, saved):
                 m._parameters[n] = t
 
+    # ---- look-ahead over several frames: everything of a frame that does not depend on the previous frame's result
+    #      (transform, trunk, RPN head, proposal selection + NMS) runs for a whole run of frames in ONE batched graph;
+    #      the per-frame remainder (jittered boxes from the propagated target, box branch, detection, mask branch,
+    #      paste / threshold) replays per frame on that graph's outputs (reference loop: helper_func.py:100-126).
+    def _frame_geometry(self, h, w):
+        oh, ow = self._resized_size(h, w)
+        div = int(self.transform.size_divisible)
+        return oh, ow, (oh + div - 1) // div * div, (ow + div - 1) // div * div
+
+    def _frame_kinds(self):
+        conv1, fc6, C = self.backbone.body.conv1, self.roi_heads.box_head.fc6, self.backbone.out_channels
+
+        def kinds(m, n, t):
+            if n != "weight":
+                return ()
+            if m is conv1:
+                return ("stem",)
+            if isinstance(m, nn.ConvTranspose2d):
+                return ("dc",)
+            if isinstance(m, nn.Conv2d) and t.shape[0] >= 64:
+                return ("f",)
+            if isinstance(m, nn.Linear) and t.shape[0] >= 64:
+                return (("lf", C if m is fc6 else 0),)
+            return ()
+        return kinds
+
+    def _with_theta(self, slots, theta):
+        saved = [m._parameters[n] for m, n in slots]
+        for (m, n), t in zip(slots, theta):
+            m._parameters[n] = t
+        if self._active_plan is not None:
+            self._active_plan.launch()
+            for k in [k for k in ops._scope if isinstance(k[1], tuple) and k[1][0] == "head"]:
+                del ops._scope[k]
+        return saved
+
+    def _frames_pre_functional(self, imgs, *theta):
+        """Target-independent part of F frames at once: features of the four RoI levels, and the padded proposal rows
+        [F, R, 4] with the first n_front rows (post-NMS RPN proposals) filled in."""
+        slots = self._pre_slots
+        saved = self._with_theta(slots, theta)
+        try:
+            cfg = self._frame_cfg
+            tr = self.transform
+            F_ = imgs.shape[0]
+            oh, ow, Hp, Wp = cfg["oh"], cfg["ow"], cfg["Hp"], cfg["Wp"]
+            x8 = K.transform(imgs, oh, ow, Hp, Wp, tr.image_mean, tr.image_std, Cs=8)
+            feats = self._backbone_eager(x8)
+            head_outs = self._rpn_head(feats)
+            padded = torch.zeros((F_, cfg["R"], 4), device=imgs.device, dtype=torch.float32)
+            count = torch.zeros((F_,), device=imgs.device, dtype=torch.int32)
+            if cfg["n_front"]:
+                _, count = self._rpn_fast(feats, (F_, 3, Hp, Wp), [(oh, ow)] * F_, head_outs, cfg["n_front"], padded, 0)
+            return feats[0], feats[1], feats[2], feats[3], padded, count
+        finally:
+            for (m, n), t in zip(slots, saved):
+                m._parameters[n] = t
+
+    def _frame_tail_functional(self, f0, f1, f2, f3, padded, stats, fallback, rnd, *theta):
+        """Per-frame remainder on one frame's slice of the batched features / proposal rows (all static shapes)."""
+        slots = self._tail_slots
+        saved = self._with_theta(slots, theta)
+        try:
+            cfg = self._frame_cfg
+            rh = self.roi_heads
+            h, w, oh, ow, Hp, Wp = cfg["h"], cfg["w"], cfg["oh"], cfg["ow"], cfg["Hp"], cfg["Wp"]
+            Kc = self.num_classes - 1
+            if cfg["has_target"]:
+                rw = float(torch.tensor(ow, dtype=torch.float32) / torch.tensor(w, dtype=torch.float32))
+                rh_ = float(torch.tensor(oh, dtype=torch.float32) / torch.tensor(h, dtype=torch.float32))
+                K.extend_boxes(stats, fallback, rnd, cfg["n_aug"], rw, rh_, float(Wp), float(Hp), 0.1, padded,
+                               cfg["n_front"])
+            R = padded.shape[1]
+            feats = [f0, f1, f2, f3]
+            rois5 = torch.cat([self._image_index(1, R, f0.device), padded], dim=2).view(R, 5)
+            head = self._box_branch(feats, rois5)
+            back_h = float(torch.tensor(h, dtype=torch.float32) / torch.tensor(oh, dtype=torch.float32))
+            back_w = float(torch.tensor(w, dtype=torch.float32) / torch.tensor(ow, dtype=torch.float32))
+            nc = rh.box_predictor.cls_score.weight.shape[0]
+            det = K.det_top1(head, padded.view(R, 4), 1, R, nc, rh.box_coder.weights, rh.box_coder.bbox_xform_clip,
+                             cfg["score_thresh"], 1e-2, float(ow), float(oh), back_w, back_h)
+            mask_logits = self._mask_branch_rois(feats, det["roi"])
+            probs, tgt, stats_out = K.mask_paste_threshold(mask_logits, det["chan"], det["label"], det["box"], 1, Kc, h, w,
+                                                           0.5, want_target=True)
+            return probs, det["box"], tgt, stats_out, det["row"]
+        finally:
+            for (m, n), t in zip(slots, saved):
+                m._parameters[n] = t
+
+    def _lookahead_cfg(self, h, w, has_target):
+        rpn, rh = self.rpn, self.roi_heads
+        oh, ow, Hp, Wp = self._frame_geometry(h, w)
+        mode = rpn._eval_augment_proposals_mode
+        post = rpn.post_nms_top_n()
+        Kc = self.num_classes - 1
+        if has_target:
+            n_aug = post // 2 if mode == 'EXTEND' else post
+            n_front = post // 2 if mode == 'EXTEND' else 0
+        else:
+            n_aug, n_front = 0, post
+        return dict(h=h, w=w, oh=oh, ow=ow, Hp=Hp, Wp=Wp, mode=mode, has_target=has_target, post=post, n_aug=n_aug,
+                    n_front=n_front, R=n_front + n_aug * Kc, score_thresh=float(rh.score_thresh),
+                    pre=rpn.pre_nms_top_n(), nms=float(rpn.nms_thresh))
+
+    def lookahead_ok(self):
+        return (not self.training and self.use_cuda_graphs and self.capture is None and self._fast_ok()
+                and self.num_classes == 2 and self.roi_heads.detections_per_img == 1
+                and self.fixed_proposals is None and os.environ.get("EOSVOS_FRAME_GRAPH", "1") != "0"
+                and int(os.environ.get("EOSVOS_FRAME_BATCH", "8")) > 1)
+
+    def prefetch_frames(self, frames, has_target):
+        """frames: the next F >= 2 inputs ([1,3,h,w] device tensors) that `forward` will be called with, in order, while
+        the parameters stay as they are; has_target: whether those calls carry a target with proposal augmentation.
+        Runs the target-independent part of all F frames as one batched graph; the forward calls then only replay the
+        per-frame remainder.  A forward call with any other input simply does not use the look-ahead."""
+        self._lookahead = None
+        if len(frames) < 2 or not self.lookahead_ok():
+            return False
+        mode = self.rpn._eval_augment_proposals_mode
+        if has_target and mode not in ('EXTEND', 'REPLACE'):
+            return False
+        device = frames[0].device
+        shape = tuple(frames[0].shape)
+        if any(tuple(f.shape) != shape or f.shape[0] != 1 for f in frames):
+            return False
+        _, _, h, w = shape
+        cfg = self._lookahead_cfg(h, w, bool(has_target))
+        if getattr(self, "_pre_slots", None) is None:
+            rpn, rh = self.rpn, self.roi_heads
+            self._pre_slots = [(m, n) for mod in (self.backbone, rpn.head) for _, m in mod.named_modules()
+                               for n, p in m._parameters.items() if p is not None]
+            self._tail_slots = [(m, n) for mod in (rh.box_head, rh.box_predictor, rh.mask_head, rh.mask_predictor)
+                                for _, m in mod.named_modules() for n, p in m._parameters.items() if p is not None]
+        F_ = len(frames)
+        imgs = torch.cat([f.to(torch.float32) for f in frames])
+        key = ("frames_pre", F_, h, w, cfg["mode"], cfg["has_target"], cfg["post"], cfg["pre"], cfg["nms"], device.index)
+        self._frame_cfg = cfg
+        K.zero_pool.reset()
+        outs = self._graphed_call(key, self._frames_pre_functional, [imgs], self._pre_slots, self._frame_kinds(), False)
+        self._lookahead = dict(cfg=cfg, outs=outs, frames=list(frames), index={id(f): i for i, f in enumerate(frames)},
+                               versions=[f._version for f in frames], ptrs=[f.data_ptr() for f in frames])
+        return True
+
+    def _lookahead_slot(self, inputs, has_target):
+        la = getattr(self, "_lookahead", None)
+        if la is None:
+            return None
+        i = la["index"].get(id(inputs))
+        if (i is None or la["frames"][i] is not inputs or la["versions"][i] != inputs._version
+                or la["ptrs"][i] != inputs.data_ptr()):
+            return None
+        cfg = la["cfg"]
+        now = self._lookahead_cfg(cfg["h"], cfg["w"], has_target)
+        if now != cfg:          # mode / thresholds / proposal counts changed since the look-ahead ran
+            return None
+        return i
+
+    def _forward_eval_tail(self, i, inputs, dev_stats):
+        la = self._lookahead
+        cfg = la["cfg"]
+        device = inputs.device
+        f0, f1, f2, f3, padded, count = la["outs"]
+        Kc = self.num_classes - 1
+        if cfg["has_target"]:
+            stats, fallback = dev_stats
+            rnd = self._extend_rands(1, Kc, cfg["n_aug"], device)
+            fallback = stats if fallback is None else fallback
+        else:
+            dummy = getattr(self, "_frame_dummy", None)
+            if dummy is None or dummy[0].device != device:
+                dummy = self._frame_dummy = (torch.zeros((1, Kc, 5), dtype=torch.int32, device=device),
+                                             torch.zeros((1,), device=device))
+            stats = fallback = dummy[0]
+            rnd = dummy[1]
+        sl = [t[i:i + 1] for t in (f0, f1, f2, f3, padded)]
+        key = ("frame_tail", i, sl[0].data_ptr(), sl[4].data_ptr(), cfg["h"], cfg["w"], cfg["mode"], cfg["has_target"],
+               cfg["post"], cfg["score_thresh"], device.index)
+        self._frame_cfg = cfg
+        K.zero_pool.reset()
+        probs, box, tgt, stats_out, row = self._graphed_call(key, self._frame_tail_functional, sl + [stats, fallback, rnd],
+                                                             self._tail_slots, self._frame_kinds(), False, alias_inputs=5)
+        self._last_padded = (sl[4], count[i:i + 1] if cfg["n_front"] else None, cfg["n_front"])
+        self._last_det = {"row": row}
+        self.last_propagated_target = tgt.clone()
+        self.last_target_stats = stats_out.clone()
+        return probs.clone(), box.clone().view(1, Kc, 4)
+
     def _image_index(self, B, R, device):
-        img_idx = getattr(self, "_img_idx_cache", None)
-        if img_idx is None or img_idx.shape != (B, R, 1) or img_idx.device != device:
+        cache = self.__dict__.setdefault("_img_idx_cache", {})     # per signature, never freed (graphs bake addresses)
+        img_idx = cache.get((B, R, str(device)))
+        if img_idx is None:
             img_idx = torch.arange(B, device=device, dtype=torch.float32).view(B, 1, 1).expand(B, R, 1).contiguous()
-            self._img_idx_cache = img_idx
+            cache[(B, R, str(device))] = img_idx
         return img_idx
 
     def _forward_eval_frame_graph(self, inputs, targets, dev_stats):
@@ -1665,6 +1854,9 @@ class MaskRCNN(_MaskRCNN):
                     # the read-back an empty target yields degenerate boxes and no detection instead of raising.
                     dev_stats = (K.mask_to_bbox(targets.to(torch.float32).contiguous(), self.num_classes - 1), None)
             if os.environ.get("EOSVOS_FRAME_GRAPH", "1") != "0":
+                slot = self._lookahead_slot(inputs, dev_stats is not None)
+                if slot is not None:
+                    return self._forward_eval_tail(slot, inputs, dev_stats)
                 return self._forward_eval_frame_graph(inputs, targets, dev_stats)
             return self._forward_eval_fast(inputs, targets, dev_stats)
         self._last_padded, self._last_det = None, None

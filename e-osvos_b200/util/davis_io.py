@@ -227,6 +227,14 @@ def evaluate_dataset(model, meta_optim, meta_optim_state_dict, root, split, save
             metrics.save_predictions(pred_np, save_dir, s, names)
         K = int(lab[0].max())
         ann = np.where(has)[0]
-        jf = metrics.evaluate_sequence_jf(pred_np[ann], lab.numpy()[ann], K) if ann.size >= 3 else {"J": [], "F": []}
+        if ann.size >= 3:
+            dev = next((p.device for p in getattr(model, "parameters", lambda: [])()), torch.device("cpu"))
+            if dev.type == "cuda":
+                jf = metrics.evaluate_sequence_jf_device(torch.from_numpy(pred_np[ann]).to(torch.uint8).to(dev),
+                                                         lab[ann].to(torch.uint8).to(dev), K)
+            else:                                   # a host-only caller of the dataset driver (no model on a GPU)
+                jf = metrics.evaluate_sequence_jf(pred_np[ann], lab.numpy()[ann], K)
+        else:
+            jf = {"J": [], "F": []}
         results[s] = {"J": jf["J"], "F": jf["F"], "time_per_frame": stats.get("time_per_frame"), "num_objects": K}
     return results

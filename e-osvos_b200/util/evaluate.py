@@ -10,6 +10,7 @@ are the headline metric, and the reference's `evaluate` worker around it.
                            427-439): results are returned through `shared_dict`
 Frames live in memory (`davis_io.VideoSequence`) instead of the reference's dataset objects.  Wall-clock accounting
 follows evaluate.py:152,319-320,436."""
+import collections
 import copy
 import os
 import random
@@ -64,7 +65,6 @@ def run_frames(model, frames_dev, start_target, on_frame=None):
             targets = start_target.clone()
     probs_all, boxes_all = [], []
     it = iter(frames_dev)
-    nxt_inputs = next(it, None)
     prefetch = getattr(model, "prefetch_backbone", None)
     # Sync-free propagation (EXTEND mode): the next frame needs only the BOX of this frame's thresholded prediction
     # (mask_rcnn.py:251-285), which the fused tail kernel leaves on the device; an empty prediction falls back to the
@@ -77,14 +77,39 @@ def run_frames(model, frames_dev, start_target, on_frame=None):
         start_stats = K.mask_to_bbox(start_target.to(torch.float32).contiguous(), Kc)
         K.target_stats.put(targets, start_stats, None)
     i = 0
+    # Look-ahead over a run of frames: whatever of a frame does not depend on its predecessor's result (transform,
+    # trunk, RPN head, proposal selection) runs for up to `ahead` frames in one batched graph -- possible whenever every
+    # frame of the run takes the same branch: device-resident propagation (EXTEND) or no proposal augmentation at all.
+    ahead = 0
+    if (sync_free or mode is None) and getattr(model, "lookahead_ok", None) is not None:
+        model.eval()
+        ahead = int(os.environ.get("EOSVOS_FRAME_BATCH", "5")) if model.lookahead_ok() else 0
+    queue = collections.deque()
+
+    def pull():
+        if not queue:
+            for _ in range(max(ahead, 1)):
+                f = next(it, None)
+                if f is None:
+                    break
+                queue.append(f)
+            if ahead > 1 and len(queue) >= 2:
+                model.prefetch_frames(list(queue), targets is not None)
+        return queue.popleft() if queue else None
     with torch.no_grad():
         model.eval()
-        if nxt_inputs is not None and prefetch is not None:
+        nxt_inputs = pull()
+        if nxt_inputs is not None and prefetch is not None and ahead <= 1:
             prefetch(nxt_inputs)
         while nxt_inputs is not None:
-            inputs, nxt_inputs = nxt_inputs, next(it, None)
+            inputs = nxt_inputs
+            if ahead <= 1 or queue:
+                nxt_inputs = pull()
+                pulled = True
+            else:
+                pulled = False                # last frame of a batched run: fetch the next run after this frame ran
             model.eval()
-            if prefetch is not None and nxt_inputs is not None:
+            if prefetch is not None and nxt_inputs is not None and ahead <= 1:
                 # look-ahead: the trunk of the NEXT frame is independent of this frame's result; enqueue it behind
                 # this frame's trunk so the GPU stays busy while the host prepares the heads
                 prefetch(nxt_inputs)
@@ -114,6 +139,10 @@ def run_frames(model, frames_dev, start_target, on_frame=None):
             probs_all.append(probs)
             boxes_all.append(boxes)
             i += 1
+            if not pulled:
+                nxt_inputs = pull()
+    if ahead > 1:
+        model._lookahead = None           # batched features are only valid for the weights and frames they ran on
     return torch.cat(probs_all), torch.cat(boxes_all)
 
 
@@ -391,9 +420,9 @@ def evaluate(rank, dataset_key, shared_meta_optim_state_dict, shared_variables, 
                 else:
                     fr = (seq.frames[f:f + 1].to(device, non_blocking=True) for f in range(len(seq)))
                     probs, _ = run_frames(model, fr, None)
-                    init_pred = probs.cpu()[:, 0].ge(0.5).to(torch.uint8).numpy()
-                    jf = metrics.evaluate_sequence_jf(init_pred, (seq.labels != 0).to(torch.uint8).numpy(), 1,
-                                                      measures=("J",))
+                    init_pred = probs[:, 0].ge(0.5).to(torch.uint8)
+                    jf = metrics.evaluate_sequence_jf_device(
+                        init_pred, (seq.labels != 0).to(torch.uint8).to(device), 1, measures=("J",))
                     out['init_J_seq'].extend([s[0] for s in jf["J"]])
             pred, stats = evaluate_sequence(
                 model, meta_optim, meta_optim_state_dict, seq, num_epochs_eval=_config['num_epochs']['eval'],
@@ -414,8 +443,9 @@ def evaluate(rank, dataset_key, shared_meta_optim_state_dict, shared_variables, 
             else:
                 ann = np.where(seq.annotated)[0]
                 n_eval = seq.num_objects if data_cfg['multi_object'] else 1
-                lab = seq.labels.numpy() if data_cfg['multi_object'] else (seq.labels != 0).to(torch.uint8).numpy()
-                jf = metrics.evaluate_sequence_jf(pred_np[ann], lab[ann], n_eval)
+                lab = seq.labels if data_cfg['multi_object'] else (seq.labels != 0)
+                jf = metrics.evaluate_sequence_jf_device(pred[ann].to(torch.uint8).to(device),
+                                                         lab[ann].to(torch.uint8).to(device), n_eval)
             if evaluate_only and _log is not None:
                 _log.info(f"{dataset_key}: {seq_name} {[s[0] for s in jf['J']]}")
             for m in ("J", "F"):

@@ -94,6 +94,31 @@ def evaluate_sequence_jf(pred, labels, num_objects, measures=("J", "F")):
     return out
 
 
+def evaluate_sequence_jf_device(pred, labels, num_objects, measures=("J", "F"), bound_th=0.008):
+    """`evaluate_sequence_jf` with the per-pixel work on the GPU: pred, labels are [T,H,W] uint8 CUDA tensors of object
+    ids; two launches count, per (frame, object), the integers J and F are ratios of (csrc/jf_measure.cu), the ratios
+    and the sequence statistics are formed here in float64 exactly as on the host path."""
+    from .. import kernels as K
+    T, H, W = pred.shape
+    last = max(T - 1, 2)                       # frames 1 .. T-2, as the host path
+    radius = bound_th if bound_th >= 1 else math.ceil(bound_th * math.hypot(H, W))
+    counts = K.jf_counts(pred[1:last].contiguous(), labels[1:last].contiguous(), num_objects, int(radius))
+    c = counts.cpu().numpy().astype(np.float64)
+    out = {"J": [], "F": []}
+    for k in range(num_objects):
+        inter, union, n_fg, n_gt, m_fg, m_gt = (c[:, k, i] for i in range(6))
+        if "J" in measures:
+            j = np.where(union == 0, 1.0, inter / np.maximum(union, 1.0))
+            out["J"].append(sequence_statistics(j))
+        if "F" in measures:
+            prec = np.where(n_fg == 0, np.where(n_gt > 0, 1.0, 1.0), m_fg / np.maximum(n_fg, 1.0))
+            rec = np.where(n_gt == 0, 1.0, np.where(n_fg == 0, 0.0, m_gt / np.maximum(n_gt, 1.0)))
+            prec = np.where((n_fg > 0) & (n_gt == 0), 0.0, prec)
+            f = np.where(prec + rec == 0, 0.0, 2.0 * prec * rec / np.maximum(prec + rec, 1e-300))
+            out["F"].append(sequence_statistics(f))
+    return out
+
+
 def save_predictions(pred, save_dir, seq_name, frame_names=None):
     """pred [T,H,W] uint8 object ids -> {save_dir}/{seq_name}/{frame}.png (single-channel ids, evaluate.py:338-342)."""
     import cv2

@@ -103,6 +103,13 @@ int eosvos_mask_paste_threshold(const float* logits, const int* det_of_chan, con
                                 int W, int M, int Cc, float thresh, eosvos_stream_t stream);
 int eosvos_mask_to_bbox(const float* target, int* stats, int B, int K, int H, int W, eosvos_stream_t stream);
 
+/* ---- DAVIS J / F counts of a sequence (stage after the hot path; reference: db_eval_sequence of the external davis
+ *      package, called at src/util/helper_func.py:444-458).  pred, gt: [T,H,W] uint8 object ids; objects id0+1..id0+K
+ *      (K <= 8 per call); bmap: [T,2,H,W] uint8 scratch; counts: [T,K,6] int32 = intersection, union, boundary pixels
+ *      of pred / gt, pred boundary pixels matched within `radius` of a gt boundary pixel, and the converse. */
+int eosvos_jf_counts(const unsigned char* pred, const unsigned char* gt, unsigned char* bmap, int* counts, int T,
+                     int id0, int K, int H, int W, int radius, eosvos_stream_t stream);
+
 /* ---- K5: segmented NMS, one segment per (image, FPN level) or per image (reference: mask_rcnn.py:249 ->
  *      tv rpn.py filter_proposals; mask_rcnn.py:392 -> torchvision::nms) */
 long long eosvos_nms_scratch_bytes(int num_segments, int max_seg);

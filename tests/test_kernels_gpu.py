@@ -771,3 +771,46 @@ def test_rpn_anchor_match_sampler_and_loss_match_torchvision():
     assert torch.allclose(lo, ro, rtol=1e-5) and torch.allclose(lb, rb, rtol=1e-4)
     for a_, b_ in zip(got, ref_heads):
         assert torch.allclose(a_, b_.grad, rtol=1e-3, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------- J / F on the device
+def _blob_sequence(T, H, W, K, seed):
+    """Object-id maps made of drifting discs (some touching the frame border, one object absent in some frames)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[:H, :W]
+    seq = np.zeros((T, H, W), np.uint8)
+    cen = rng.rand(K, 2) * [H, W]
+    vel = rng.randn(K, 2) * 3
+    rad = rng.randint(6, max(7, min(H, W) // 4), K)
+    for t in range(T):
+        for k in range(K):
+            if k == 1 and t % 3 == 0:
+                continue
+            c = cen[k] + vel[k] * t
+            seq[t][(yy - c[0]) ** 2 + (xx - c[1]) ** 2 <= rad[k] ** 2] = k + 1
+    return seq
+
+
+@pytest.mark.parametrize("T,H,W,K", [(6, 120, 213, 3), (4, 97, 131, 10), (3, 480, 854, 2), (5, 64, 64, 1)])
+def test_jf_device_matches_host(T, H, W, K):
+    """DAVIS J / F with the pixel work on the device == util.metrics' host path (integer counts => exact)."""
+    import numpy as np
+    from eosvos_b200.util import metrics
+    gt = _blob_sequence(T, H, W, K, 1)
+    pred = _blob_sequence(T, H, W, K, 2)
+    pred[1] = gt[1]                                   # a perfect frame
+    pred[2][pred[2] == 1] = 0                         # object 1 missing from the prediction in one frame
+    host = metrics.evaluate_sequence_jf(pred, gt, K)
+    dev = metrics.evaluate_sequence_jf_device(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda(), K)
+    for m in ("J", "F"):
+        assert len(dev[m]) == K
+        np.testing.assert_allclose(np.asarray(dev[m]), np.asarray(host[m]), rtol=0, atol=1e-12, equal_nan=True)
+
+
+def test_jf_counts_rejects_bad_arguments():
+    p = torch.zeros((2, 8, 8), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        K().jf_counts(p, p[:1], 1, 2)
+    with pytest.raises(RuntimeError):
+        K().jf_counts(p, p, 1, 100)

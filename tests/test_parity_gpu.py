@@ -194,6 +194,10 @@ class LockStep:
                 o_rows = cand["rows"]
                 p_rows = rec["rows"][0]
                 info = dict(obj=obj, k=k, frame=f, n_det=(int(p_rows.numel()), int(o_rows.numel())), tie=False)
+                if p_rows.numel() != o_rows.numel() and cand["scores"].numel():
+                    # one side's best score fell on the other side of roi_heads.score_thresh: a tie against the
+                    # threshold when the oracle's best score is within `score_tie` of it
+                    info["thresh_tie"] = abs(float(cand["scores"].max()) - float(oracle.roi_heads.score_thresh)) <= score_tie
                 if p_rows.numel() and o_rows.numel():
                     # map the product's source row to the oracle's proposal list (EXTEND rows sit at the end of both)
                     o_props = oracle.last_proposals[0]
@@ -243,7 +247,10 @@ def _check_lockstep(infos, box_tol=0.5, require_det=True):
     flips = ties = 0
     for it in infos:
         print(it)
-        assert it["n_det"][0] == it["n_det"][1], it
+        if it["n_det"][0] != it["n_det"][1]:
+            assert it.get("thresh_tie"), f"detection on one side only and not a tie against the score threshold: {it}"
+            ties += 1
+            continue
         if it["n_det"][0] == 0:
             assert it["px"] == (0, 0)
             continue
@@ -274,12 +281,12 @@ def _video(seed, T, K=1, h=480, w=854):
 
 
 def test_run_frames_matches_oracle_run_loader():
-    """run_loader (helper_func.py:67-159) over 6 frames at 854x480 after 30 fine-tune iterations, hook-free (own
+    """run_loader (helper_func.py:67-159) over 7 frames at 854x480 after 30 fine-tune iterations, hook-free (own
     proposals, own detection), frame by frame from identical state; plus the two fallback branches: an all-zero start
     target (:90-93 -> EXTEND mode, no augmentation) and an empty prediction (:124-126 -> back to the start target)."""
     from eosvos_b200.util import evaluate as E
     model, opt, oracle, _, dev, _ = build_pair(min_size=None)
-    fr, labels = _video(5, 7)
+    fr, labels = _video(5, 8)
     gt0 = (labels[0] == 1).float()[None, None]
     model.roi_heads.detections_per_img = oracle.roi_heads.detections_per_img = 1
     inp, gts = fr[0:1].to(dev).repeat(3, 1, 1, 1), gt0.to(dev).repeat(3, 1, 1, 1)
@@ -288,10 +295,11 @@ def test_run_frames_matches_oracle_run_loader():
     ls = LockStep(model, opt, oracle, dev)
     ls.after_finetune(0, 0, model, opt)
     torch.manual_seed(77)
-    ls.before_frames(0, 0, list(range(1, 7)), gt0)
-    probs, boxes = E.run_frames(model, (fr[f:f + 1].to(dev) for f in range(1, 7)), gt0.to(dev),
+    ls.before_frames(0, 0, list(range(1, 8)), gt0)
+    # 7 frames: with the default look-ahead a batched run of 5 and one of 2
+    probs, boxes = E.run_frames(model, (fr[f:f + 1].to(dev) for f in range(1, 8)), gt0.to(dev),
                                 on_frame=lambda i, t, p, b: ls.on_frame(0, 0, i, t, p, b))
-    assert probs.shape == (6, 1, 480, 854)
+    assert probs.shape == (7, 1, 480, 854)
     _check_lockstep(ls.replay(fr, labels))
 
     # (b) empty prediction -> the next frame runs with the START target and EXTEND mode (helper_func.py:124-126)
