@@ -8,8 +8,8 @@ e-OSVOS-100-OnA").
 One STEP = one online-adaptation block of the e-OSVOS-100-OnA schedule on one 854x480 object (reference
 src/util/evaluate.py:140-317, reset_model_mode FIRST_STEP): restore the model state saved after the first fine-tuning
 round (`model.load_state_dict`, evaluate.py:200-205), ITERS_PER_STEP fine-tune iterations at batch 3 (forward +
-backward + fused MetaOptimizer update), FRAMES_PER_STEP inference frames with target propagation -- the 10:3
-iteration:frame ratio of a 70-frame video (230 iterations, 69 frames).  The first round (FIRST_ROUND_ITERS iterations
+backward + fused MetaOptimizer update), FRAMES_PER_STEP inference frames with target propagation -- 10 iterations
+and the 5 frames up to the next adaptation (cfgs/eval.yaml e-OSVOS-OnA: online_adapt step 5, num_epochs 10).  The first round (FIRST_ROUND_ITERS iterations
 from the random initialisation) runs once, untimed, so that the timed frames carry a real detection through the mask
 branch and the paste kernel (`n_det` in the output line).
 `value` = fine-tune iterations/s (device-resident inputs); `frames_per_s` = inference object-frames/s; `e2e` = the same
@@ -38,7 +38,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 ITERS_PER_STEP = 10
-FRAMES_PER_STEP = 3
+FRAMES_PER_STEP = 5
 FIRST_ROUND_ITERS = 40
 BATCH = 3
 H, W = 480, 854
@@ -49,7 +49,7 @@ SCORE_THRESH = float(os.environ.get("EOSVOS_BENCH_SCORE_THRESH", "0.05"))
 METRIC = "finetune_iters_per_s"
 UNIT = "iter/s (batch 3, 854x480)"
 WORKLOAD = ("e-OSVOS-100-OnA block on synthetic DAVIS-2017-val-shaped 854x480 video: state restore + 10 fine-tune iters "
-            "(batch 3, LOVASZ) + 3 inference frames per step, Mask R-CNN R50-GN-FPN random init")
+            "(batch 3, LOVASZ) + 5 inference frames per step, Mask R-CNN R50-GN-FPN random init")
 
 
 def load_peaks():
@@ -757,7 +757,7 @@ def reference_arm(args):
         fvals.append(base["frames_per_s"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
-    # ms_per_step of THIS arm's step definition (10 iterations + 3 frames), from the measured per-unit times
+    # ms_per_step of THIS arm's step definition (10 iterations + 5 frames), from the measured per-unit times
     ms_step = 1e3 * (ITERS_PER_STEP / v + FRAMES_PER_STEP / float(np.mean(fvals)))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

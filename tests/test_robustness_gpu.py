@@ -85,7 +85,7 @@ def test_operand_cache_follows_out_of_band_parameter_writes():
     img, tgt = frame()
     img2, tgt2 = frame(seed=12)
     tb, mb = (img.to(dev), tgt.to(dev)), (img2.to(dev), tgt2.to(dev))
-    radam = meta_train.FusedRAdam(opt, model_init_lr=1e-2, log_init_lr_lr=1e-5)      # a visible outer step
+    radam = meta_train.FusedRAdam(opt, model_init_lr=3e-3, log_init_lr_lr=1e-5)      # a visible outer step
     for it in range(2):
         with mock.patch("torch.randperm", det_randperm(5)):
             meta_train.meta_iteration(model, opt, radam, [(tb, mb)], 1, num_epochs=1, bptt_epochs=1, seed=1, meta_iter=it)
@@ -101,7 +101,9 @@ def test_operand_cache_follows_out_of_band_parameter_writes():
     ops.clear_prep_cache()
     model._graphs.clear()
     fresh = first_loss()
-    assert abs(cached - fresh) <= 2e-3 * abs(fresh), (cached, fresh)
+    # (two captures of the same forward differ by the fp32-atomics noise of the GroupNorm sums, amplified by the loss
+    # of a random-init network: a stale operand would show up at the 1e-1 level, the noise stays below 5e-3)
+    assert abs(cached - fresh) <= 5e-3 * abs(fresh), (cached, fresh)
     # MetaModel writers
     other = torch.nn.ParameterList([torch.nn.Parameter(p.detach() * 1.02) for p in model.parameters()])
     first_loss()
@@ -110,4 +112,4 @@ def test_operand_cache_follows_out_of_band_parameter_writes():
     ops.clear_prep_cache()
     model._graphs.clear()
     b = first_loss()
-    assert np.isfinite(a) and abs(a - b) <= 2e-3 * abs(b) and abs(a - cached) > 1e-4 * abs(cached), (a, b, cached)
+    assert np.isfinite(a) and abs(a - b) <= 5e-3 * abs(b) and abs(a - cached) > 2e-2 * abs(cached), (a, b, cached)
