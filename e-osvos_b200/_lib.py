@@ -71,6 +71,7 @@ SIGNATURES = {
     "eosvos_weight_prep_tile_elems": [],
     "eosvos_weight_prep_multi": [_P, _P, _I, _P],
     "eosvos_affine_warp_cubic": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "eosvos_label_warp_nearest": [_P, _P, _P, _P, _I, _I, _I, _P],
     "eosvos_transform": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "eosvos_mask_resize_nearest": [_P, _P, _I, _I, _I, _I, _I, _P],
     "eosvos_im2col_stem": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -691,7 +691,45 @@ affine_warp_cubic_kernel(const float* __restrict__ src, const float* __restrict_
 #pragma unroll
   for (int c = 0; c < 3; ++c) dst[((size_t)b * 3 + c) * H * W + po] = acc[c];
 }
+
+// cv2.warpAffine(label, M, flags=INTER_NEAREST) (+ an optional horizontal flip of the source first), bit for bit:
+// OpenCV walks the destination with 10-bit fixed-point source coordinates -- per column rint(m0*x*1024) and
+// rint(m3*x*1024), per row rint((m1*y + m2)*1024) + 512 and rint((m4*y + m5)*1024) + 512, summed and shifted right by
+// 10, saturated to int16 -- and copies the source pixel or writes 0 outside (imgwarp.cpp WarpAffineInvoker +
+// remapNearest, BORDER_CONSTANT).  minv is the INVERTED matrix in double, as OpenCV forms it.  Explicit
+// round-to-nearest multiplies / adds: no FMA contraction, the host code has none either.
+__global__ void __launch_bounds__(256)
+label_warp_nearest_kernel(const float* __restrict__ src, const double* __restrict__ minv, const int* __restrict__ flip,
+                          float* __restrict__ dst, int B, int H, int W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W) return;
+  const int x = (int)(idx % W);
+  const int y = (int)((idx / W) % H);
+  const int b = (int)(idx / ((long long)W * H));
+  const double* m = minv + b * 6;
+  const double xd = (double)x, yd = (double)y;
+  const int ad = __double2int_rn(__dmul_rn(__dmul_rn(m[0], xd), 1024.0));
+  const int bd = __double2int_rn(__dmul_rn(__dmul_rn(m[3], xd), 1024.0));
+  const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], yd), m[2]), 1024.0)) + 512;
+  const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], yd), m[5]), 1024.0)) + 512;
+  int X = (X0 + ad) >> 10, Y = (Y0 + bd) >> 10;
+  X = min(max(X, -32768), 32767);
+  Y = min(max(Y, -32768), 32767);
+  float v = 0.f;
+  if (X >= 0 && X < W && Y >= 0 && Y < H) v = src[(size_t)Y * W + (flip[b] ? W - 1 - X : X)];
+  dst[idx] = v;
+}
 }  // namespace eosvos
+
+extern "C" int eosvos_label_warp_nearest(const float* src, const double* minv, const int* flip, float* dst, int B, int H,
+                                         int W, eosvos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  EOSVOS_REQUIRE(src && minv && flip && dst && B > 0 && H > 0 && W > 0, "label_warp_nearest: bad arguments");
+  EOSVOS_REQUIRE(H <= 32767 && W <= 32767, "label_warp_nearest: image larger than OpenCV's int16 coordinate range");
+  const long long total = (long long)B * H * W;
+  eosvos::label_warp_nearest_kernel<<<eosvos::blocks_for(total), 256, 0, stream>>>(src, minv, flip, dst, B, H, W);
+  return eosvos::check_launch("label_warp_nearest_kernel");
+}
 
 extern "C" int eosvos_affine_warp_cubic(const float* src, const float* minv, const int* flip, float* dst, int B, int H,
                                         int W, eosvos_stream_t stream_) {

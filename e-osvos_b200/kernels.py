@@ -911,6 +911,20 @@ def affine_warp_cubic(src_chw, minv, flip, B):
     return out
 
 
+def label_warp_nearest(src_hw, minv64, flip, out=None):
+    """src [H,W] fp32 ids, minv64 [B,6] float64 (OpenCV's inverted matrix), flip [B] int32 -> [B,1,H,W] fp32 ==
+    cv2.warpAffine(flip(src), M, flags=cv2.INTER_NEAREST)."""
+    _chk(src_hw, torch.float32, "label")
+    _chk(minv64, torch.float64, "minv")
+    _chk(flip, torch.int32, "flip")
+    H, W = src_hw.shape
+    B = minv64.shape[0]
+    if out is None:
+        out = torch.empty((B, 1, H, W), device=src_hw.device, dtype=torch.float32)
+    call("eosvos_label_warp_nearest", _ptr(src_hw), _ptr(minv64), _ptr(flip), _ptr(out), B, H, W, _stream())
+    return out
+
+
 def nchw_to_nhwc_bf16(x):
     """fp32/bf16 [N,C,H,W] -> bf16 [N,H,W,C]."""
     N, C, H, W = x.shape

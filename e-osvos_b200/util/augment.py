@@ -1,6 +1,7 @@
 """First-frame augmentation used while fine-tuning (host side, as in the reference):
 RandomHorizontalFlip + RandomScaleNRotate(rots=(-30,30), scales=(.75,1.25)) -- reference
 src/data/custom_transforms.py:9-89,188-211, composed in src/util/helper_func.py:254-263."""
+import os
 import random
 
 import cv2
@@ -77,6 +78,62 @@ class DeviceAugmenter:
         return minv, flips, gts
 
     @staticmethod
+    def cv_inverse(M):
+        """The inverse cv2.warpAffine forms from a forward 2x3 matrix (imgwarp.cpp), float64, same operation order."""
+        M = np.array(M, dtype=np.float64).reshape(6).copy()
+        D = M[0] * M[4] - M[1] * M[3]
+        D = 1.0 / D if D != 0 else 0.0
+        A11, A22 = M[4] * D, M[0] * D
+        M[0] = A11
+        M[1] *= -D
+        M[3] *= -D
+        M[4] = A22
+        b1 = -M[0] * M[2] - M[1] * M[5]
+        b2 = -M[3] * M[2] - M[4] * M[5]
+        M[2], M[5] = b1, b2
+        return M
+
+    def device_labels(self, batch_size, rng=random, rots=(-30, 30), scales=(.75, 1.25)):
+        """host_part with the label work on the GPU (current stream): same random draws in the same order, the nearest
+        label warp by kernels.label_warp_nearest (== cv2.warpAffine INTER_NEAREST bit for bit), the rejection test
+        (`len(np.unique(aug_gt)) == num_labels`, custom_transforms.py:74-78) from the per-id pixel counts of the warped
+        label, which also are the boxes / counts MaskRCNN needs for its targets.  Only the counts (20 bytes per sample)
+        come back to the host.  Returns (minv [B,6] f32 numpy, flips [B] i32 numpy, gts [B,1,H,W] device, stats
+        int32 [B,K,5] host)."""
+        import torch
+        from .. import kernels as K
+        dev = self.src.device
+        h, w = self.h, self.w
+        if getattr(self, "gt_dev", None) is None:
+            self.gt_dev = torch.from_numpy(self.gt).to(dev)
+            self.num_ids = max(int(self.gt.max()), 1)
+            self.num_labels = int(np.count_nonzero(np.bincount(self.gt.astype(np.uint8).ravel(), minlength=256)))
+            self._flags = [torch.zeros(1, dtype=torch.int32, device=dev), torch.ones(1, dtype=torch.int32, device=dev)]
+            self._stager = K.PinnedStager(slot_bytes=256, slots=32)       # private: this runs on a worker thread
+        Kn = self.num_ids
+        minv = np.empty((batch_size, 6), np.float32)
+        flips = np.empty((batch_size,), np.int32)
+        gts = torch.empty((batch_size, 1, h, w), device=dev, dtype=torch.float32)
+        stats = torch.empty((batch_size, Kn, 5), dtype=torch.int32)
+        for b in range(batch_size):
+            do_flip = rng.random() < 0.5
+            while True:
+                rot = (rots[1] - rots[0]) * rng.random() - (rots[1] - rots[0]) / 2
+                sc = (scales[1] - scales[0]) * rng.random() - (scales[1] - scales[0]) / 2 + 1
+                M = cv2.getRotationMatrix2D((w / 2, h / 2), rot, sc)
+                m64 = self._stager.put(self.cv_inverse(M).reshape(1, 6), dev)
+                K.label_warp_nearest(self.gt_dev, m64, self._flags[int(do_flip)], out=gts[b:b + 1])
+                st = K.mask_to_bbox(gts[b:b + 1], Kn).cpu()                 # (waits for this sample's two kernels)
+                counts = st[0, :, 4]
+                present = int((counts > 0).sum()) + int(h * w - int(counts.sum()) > 0)
+                if not self.num_labels > 1 or present == self.num_labels:
+                    break
+            minv[b] = cv2.invertAffineTransform(M).reshape(6)
+            flips[b] = int(do_flip)
+            stats[b] = st[0]
+        return minv, flips, gts, stats
+
+    @staticmethod
     def target_stats(gts, num_ids=1):
         """Per-sample, per-id (xmin, ymin, xmax, ymax, count) of label maps [B,1,H,W] -- what
         MaskRCNN._build_targets would otherwise derive on the device and read back (a stream sync)."""
@@ -121,13 +178,26 @@ class PrefetchingAugmenter:
     # cudaHostAlloc of ~20 MB costs milliseconds, which would otherwise be paid at the start of every block
     _rings = {}
     _pool = None
+    _side = None
 
-    def __init__(self, frame0_chw_device, gt_hw, batch_size, seed_for_epoch, depth=3, first_epoch=None):
+    def __init__(self, frame0_chw_device, gt_hw, batch_size, seed_for_epoch, depth=3, first_epoch=None,
+                 device_labels=None):
         import torch
         from concurrent.futures import ThreadPoolExecutor
         self.aug = DeviceAugmenter(frame0_chw_device, gt_hw)
         self.batch_size, self.seed_for_epoch, self.depth = batch_size, seed_for_epoch, depth
         h, w = self.aug.h, self.aug.w
+        # label warp + rejection test + boxes on the GPU (default): the worker thread then only draws the random
+        # numbers and launches kernels on its own stream -- the host keeps no per-pixel work
+        if device_labels is None:
+            device_labels = os.environ.get("EOSVOS_DEVICE_LABELS", "1") != "0" and float(np.max(gt_hw)) <= 64
+        self.device_labels = bool(device_labels) and frame0_chw_device.is_cuda
+        if self.device_labels:
+            if PrefetchingAugmenter._side is None:
+                PrefetchingAugmenter._side = torch.cuda.Stream(device=frame0_chw_device.device)
+            self.side = PrefetchingAugmenter._side
+            self.ready = torch.cuda.Event()
+            self.ready.record(torch.cuda.current_stream(frame0_chw_device.device))   # frame 0 is on the device
         key = (batch_size, h, w, depth)
         rings = PrefetchingAugmenter._rings.setdefault(key, [])
         # two rings alternate, so an augmenter created while its predecessor still has copies in flight never
@@ -159,13 +229,38 @@ class PrefetchingAugmenter:
                                out=tuple(t.numpy() for t in slot))
             return slot + (self.aug.target_stats(slot[2].numpy()),)
 
-        self.futures[epoch] = self.pool.submit(work)
+        def work_device():
+            import torch
+            from .. import kernels as K
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.ready)
+                minv, flips, gts, stats = self.aug.device_labels(self.batch_size, random.Random(self.seed_for_epoch(epoch)))
+                slot[0].copy_(torch.from_numpy(minv))
+                slot[1].copy_(torch.from_numpy(flips))
+                dev = gts.device
+                imgs = K.affine_warp_cubic(self.aug.src, slot[0].to(dev, non_blocking=True),
+                                           slot[1].to(dev, non_blocking=True), self.batch_size)
+                done = torch.cuda.Event()
+                done.record(self.side)
+            return imgs, gts, stats, done
+
+        self.futures[epoch] = self.pool.submit(work_device if self.device_labels else work)
 
     def get(self, epoch):
         for e in range(epoch, epoch + self.depth):
             if e not in self.futures:
                 self._submit(e)
         slot = self.futures.pop(epoch).result()
+        if self.device_labels:
+            import torch
+            from .. import kernels as K
+            imgs, gts, stats, done = slot
+            cur = torch.cuda.current_stream(imgs.device)
+            cur.wait_event(done)
+            imgs.record_stream(cur)          # allocated on the worker's stream, consumed (and freed) on this one
+            gts.record_stream(cur)
+            K.target_stats.put(gts, stats, torch.zeros(stats.shape[0], dtype=torch.int32))
+            return imgs, gts
         return self.aug.device_part(*slot)
 
     def close(self):

@@ -198,6 +198,11 @@ int eosvos_weight_prep_multi(const long long* table_dev, const int* tiles_dev, i
 /* device half of the first-frame augmentation (reference: src/data/custom_transforms.py:40-51,188-211) */
 int eosvos_affine_warp_cubic(const float* src, const float* minv, const int* flip, float* dst, int B, int H, int W,
                              eosvos_stream_t stream);
+/* Label half of the same augmentation: cv2.warpAffine(gt, M, flags=INTER_NEAREST) after the optional flip, bit for bit
+ * (reference custom_transforms.py:57-89 warps the label with cv2 on the host).  src: [H,W] fp32 ids; minv: [B,6] DOUBLE,
+ * the inverted matrix as OpenCV forms it; dst: [B,1,H,W]. */
+int eosvos_label_warp_nearest(const float* src, const double* minv, const int* flip, float* dst, int B, int H, int W,
+                              eosvos_stream_t stream);
 int eosvos_transform(const float* img, void* out, int B, int h, int w, int oh, int ow, int Hp, int Wp, int Cs,
                      const float* mean3, const float* std3, eosvos_stream_t stream);
 int eosvos_mask_resize_nearest(const uint8_t* src, uint8_t* dst, int G, int h, int w, int oh, int ow,

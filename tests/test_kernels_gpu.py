@@ -511,6 +511,91 @@ def test_device_augmentation_matches_cv2_family():
         assert d.mean().item() < 2e-3 and d.max().item() < 0.25, (d.mean().item(), d.max().item())
 
 
+def _label_map(h, w, seed, ids=3):
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[:h, :w]
+    gt = np.zeros((h, w), np.float32)
+    for k in range(ids):
+        cy, cx, r = rng.randint(0, h), rng.randint(0, w), rng.randint(min(h, w) // 10, min(h, w) // 3)
+        gt[(yy - cy) ** 2 + (xx - cx) ** 2 < r * r] = k + 1
+    return gt
+
+
+@pytest.mark.parametrize("h,w", [(480, 854), (720, 1280), (97, 131)])
+def test_label_warp_nearest_equals_cv2(h, w):
+    """label_warp_nearest_kernel == cv2.warpAffine(flip(gt), M, flags=INTER_NEAREST) bit for bit (OpenCV's 10-bit
+    fixed-point coordinates, int16 saturation, zero border) on id maps and on a noise image, 24 random transforms."""
+    import random
+    import cv2
+    import numpy as np
+    from eosvos_b200.util import augment
+    rng = random.Random(h)
+    for src in (_label_map(h, w, 1), (np.random.RandomState(2).rand(h, w) * 5).astype(np.int32).astype(np.float32)):
+        src_d = torch.from_numpy(src).to(dev())
+        Ms, flips, refs = [], [], []
+        for _ in range(12):
+            rot, sc, fl = 60 * rng.random() - 30, 0.5 * rng.random() + 0.75, rng.random() < 0.5
+            M = cv2.getRotationMatrix2D((w / 2, h / 2), rot, sc)
+            refs.append(cv2.warpAffine(cv2.flip(src, 1) if fl else src, M, (w, h), flags=cv2.INTER_NEAREST))
+            Ms.append(augment.DeviceAugmenter.cv_inverse(M))
+            flips.append(int(fl))
+        out = K().label_warp_nearest(src_d, torch.from_numpy(np.stack(Ms)).to(dev()),
+                                     torch.tensor(flips, dtype=torch.int32, device=dev()))
+        for b, ref in enumerate(refs):
+            assert torch.equal(out[b, 0].cpu(), torch.from_numpy(ref)), b
+
+
+def test_device_label_augmentation_equals_host_path():
+    """DeviceAugmenter.device_labels (draws on the host, label warp / rejection test / boxes on the GPU) against
+    host_part + target_stats (cv2 + numpy): same flips, matrices, labels and boxes from the same random stream --
+    including a label whose small corner object is pushed out of the frame by some draws (rejection loop,
+    custom_transforms.py:74-78) -- and the prefetching augmenter's two modes hand out identical batches."""
+    import random
+    import numpy as np
+    from eosvos_b200.util import augment
+    h, w = 240, 427
+    gt = np.zeros((h, w), np.float32)
+    gt[4:22, 6:30] = 1                                   # leaves the frame under many rotations / scalings
+    img = np.random.RandomState(0).rand(h, w, 3).astype(np.float32)
+    src = torch.from_numpy(img.transpose(2, 0, 1).copy()).to(dev())
+    aug = augment.DeviceAugmenter(src, gt)
+    draws = []
+
+    class Counting(random.Random):
+        def random(self):
+            draws.append(1)
+            return super().random()
+    minv_h, flips_h, gts_h = aug.host_part(6, Counting(11))
+    n_host = len(draws)
+    del draws[:]
+    minv_d, flips_d, gts_d, stats_d = aug.device_labels(6, Counting(11))
+    assert len(draws) == n_host and n_host > 6 * 3       # the rejection loop ran, and ran equally often
+    assert np.array_equal(minv_h, minv_d) and np.array_equal(flips_h, flips_d)
+    assert torch.equal(gts_d.cpu(), torch.from_numpy(gts_h))
+    st_h, _ = aug.target_stats(gts_h)
+    assert torch.equal(stats_d, st_h)
+    # multi-id label map: every id must survive the warp
+    gt3 = _label_map(h, w, 5)
+    aug3 = augment.DeviceAugmenter(src, gt3)
+    a = aug3.host_part(4, random.Random(3))
+    b = aug3.device_labels(4, random.Random(3))
+    assert np.array_equal(a[0], b[0]) and torch.equal(b[2].cpu(), torch.from_numpy(a[2]))
+    assert torch.equal(b[3], aug3.target_stats(a[2], num_ids=3)[0])
+    # the prefetching augmenter (worker thread + its own stream) in both modes
+    pa = augment.PrefetchingAugmenter(src, gt, 3, lambda e: 100 + e, device_labels=True)
+    pb = augment.PrefetchingAugmenter(src, gt, 3, lambda e: 100 + e, device_labels=False)
+    for e in (1, 2, 3, 4, 5):
+        xa, ga = pa.get(e)
+        xb, gb = pb.get(e)
+        torch.cuda.synchronize()
+        assert torch.equal(ga, gb) and torch.equal(xa, xb)
+        sa, sb = K().target_stats.get_host(ga), K().target_stats.get_host(gb)
+        assert sa is not None and torch.equal(sa[0], sb[0])
+    pa.close()
+    pb.close()
+
+
 # ------------------------------------------------------------------------------------------------ K5/K6 (rpn.cu)
 def _rpn_case(N, feat_shapes, seed):
     from torchvision.models.detection.anchor_utils import AnchorGenerator
