@@ -14,8 +14,8 @@ from the random initialisation) runs once, untimed, so that the timed frames car
 branch and the paste kernel (`n_det` in the output line).
 `value` = fine-tune iterations/s (device-resident inputs); `frames_per_s` = inference object-frames/s; `e2e` = the same
 block driven from HOST buffers: first frame + every inference frame H2D from pinned memory, first-frame augmentation
-per iteration (random draws + label warp on the host, bicubic image warp on the GPU), every loss and probability map
-read back (D2H) inside the timed region.  With N > 1 every rank runs its own objects (weak scaling, no data-path
+per iteration (random draws on the host in the reference's order; label warp, rejection test and bicubic image warp on
+the GPU), every loss and probability map read back (D2H) inside the timed region.  With N > 1 every rank runs its own objects (weak scaling, no data-path
 collective); time = max over ranks.  Extra blocks in the same JSON line: `roofline_layers` (every distinct contraction
 of an iteration, timed alone with an L2 flush between launches), `roofline_update` / `roofline_loss` / `roofline_tail`
 (HBM-bound kernels), `gpu_eager_baseline` (the unmodified reference on the same GPU through cuDNN / ATen),
@@ -835,7 +835,7 @@ def main():
 
     def host_batch(i):
         # end to end: frame 0 goes H2D once per step (block); every iteration draws fresh random flips/rotations/
-        # scales (host, reference RNG order), warps the label on the host (nearest) and the image on the GPU (bicubic)
+        # scales (host, reference RNG order) and warps label (nearest, == cv2) and image (bicubic) on the GPU
         # (the host half of the NEXT block's first iterations is started while this block finishes, as a per-object
         # driver would do for the next object)
         if i % ITERS_PER_STEP == 1 or "aug" not in e2e_state:
@@ -906,9 +906,13 @@ def main():
     if rank == 0:
         n_it = args.steps * ITERS_PER_STEP * world
         n_fr = args.steps * FRAMES_PER_STEP * world
-        h2d = (fr[0].numel() * 4 + ITERS_PER_STEP * (batches[0][1].numel() * 4 + BATCH * 28)
-               + FRAMES_PER_STEP * fr[0:1].numel() * 4)
-        d2h = ITERS_PER_STEP * 4 + FRAMES_PER_STEP * H * W * 4
+        # per iteration: the three samples' warp matrices (fp32 for the image, fp64 for the label) and flip flags go
+        # up, the per-id pixel counts / boxes of the warped labels (rejection test, 20 B per sample) come back; with
+        # EOSVOS_DEVICE_LABELS=0 the host-warped labels go up instead
+        dev_labels = os.environ.get("EOSVOS_DEVICE_LABELS", "1") != "0"
+        per_iter_up = BATCH * (24 + 4 + 48) if dev_labels else batches[0][1].numel() * 4 + BATCH * 28
+        h2d = fr[0].numel() * 4 + ITERS_PER_STEP * per_iter_up + FRAMES_PER_STEP * fr[0:1].numel() * 4
+        d2h = ITERS_PER_STEP * (4 + (BATCH * 20 if dev_labels else 0)) + FRAMES_PER_STEP * H * W * 4
         line = {
             "metric": METRIC, "value": n_it / (ft_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
