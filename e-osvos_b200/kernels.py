@@ -44,6 +44,12 @@ def _chk(t, dtype=None, name="tensor"):
     return t
 
 
+# Held by whoever captures a CUDA graph and by the augmentation worker thread around its CUDA section: allocations,
+# synchronisations and frees issued by another thread while a capture is under way can invalidate it.
+import threading  # noqa: E402
+capture_lock = threading.RLock()
+
+
 class PinnedStager:
     """Small host->device uploads (pointer tables, boxes, ids) through a ring of PINNED staging buffers with
     non_blocking copies.  A plain `torch.tensor(..., device='cuda')` / `.to(device)` from pageable memory makes the

@@ -42,6 +42,26 @@ class _ImageListLike:
         self._device = device
 
 
+class _ThreadLocalCapture:
+    """While active, `torch.cuda.graph` (also the one `make_graphed_callables` opens) captures with
+    cudaStreamCaptureModeThreadLocal instead of the global mode."""
+
+    def __enter__(self):
+        orig = torch.cuda.graph
+
+        class graph(orig):
+            def __init__(self, *args, **kwargs):
+                kwargs.setdefault("capture_error_mode", "thread_local")
+                super().__init__(*args, **kwargs)
+        self.orig = orig
+        torch.cuda.graph = graph
+        return self
+
+    def __exit__(self, *exc):
+        torch.cuda.graph = self.orig
+        return False
+
+
 class MaskRCNN(_MaskRCNN):
 
     def __init__(self, backbone, num_classes, batch_norm=None, train_encoder=True,
@@ -474,16 +494,43 @@ class MaskRCNN(_MaskRCNN):
             self._active_plan = plan
             ops._scope = {(id(reqs[i][0]), kind): v for (i, kind), v in vals.items()}
             c0 = _lib.launch_count()
-            try:
-                if grad_mode:
-                    with torch.enable_grad():
-                        # (parameters whose gradient is produced outside the graph -- the RPN head under the sparse
-                        # backward -- are unused inside)
-                        graphed = torch.cuda.make_graphed_callables(fn, tuple(sample), allow_unused_input=True)
-                else:
-                    graphed = self._capture_inference_graph(fn, sample, nin)
-            finally:
-                self._active_plan, ops._scope = None, None
+            scope0 = dict(ops._scope)
+            import gc
+            gc_was_on = gc.isenabled()
+            for attempt in (0, 1):
+                try:
+                    # thread-local capture mode + the capture lock: nothing another thread does (the augmentation
+                    # worker allocates and synchronises on its own stream) may invalidate the capture; no cyclic
+                    # garbage collection in between either (torch collects right before the capture begins): a
+                    # collected model's graphs would release their memory pools in the middle of the capture
+                    gc.disable()
+                    with K.capture_lock, _ThreadLocalCapture():
+                        if grad_mode:
+                            with torch.enable_grad():
+                                # (parameters whose gradient is produced outside the graph -- the RPN head under the
+                                # sparse backward -- are unused inside)
+                                graphed = torch.cuda.make_graphed_callables(fn, tuple(sample), allow_unused_input=True)
+                        else:
+                            graphed = self._capture_inference_graph(fn, sample, nin)
+                    break
+                except Exception as e:      # noqa: BLE001
+                    # a capture invalidated from outside (e.g. the allocator releasing another graph's pool when the
+                    # garbage collector runs mid-capture) is not an error of this graph: start it over once
+                    if attempt or "capture" not in str(e).lower():
+                        self._active_plan, ops._scope = None, None
+                        raise
+                    import sys
+                    print(f"[eosvos] graph capture of {key[0]} restarted: {str(e).splitlines()[0][:160]}", file=sys.stderr)
+                    self.capture_restarts = getattr(self, "capture_restarts", 0) + 1
+                    torch.cuda.synchronize()
+                    K.zero_pool.cap_block = None        # (carved from the abandoned capture's pool)
+                    c0 = _lib.launch_count()
+                    ops._scope = dict(scope0)
+                    self._active_plan = plan
+                finally:
+                    if gc_was_on:
+                        gc.enable()
+            self._active_plan, ops._scope = None, None
             per_call = (_lib.launch_count() - c0) // 4      # 3 eager warm-up runs + 1 capture of the same kernels
             # the warm-up backward ran on uninitialised output gradients (torch's warm-up passes empty_like tensors):
             # never continue in a zero block it touched

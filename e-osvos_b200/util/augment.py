@@ -198,6 +198,7 @@ class PrefetchingAugmenter:
             self.side = PrefetchingAugmenter._side
             self.ready = torch.cuda.Event()
             self.ready.record(torch.cuda.current_stream(frame0_chw_device.device))   # frame 0 is on the device
+            frame0_chw_device.record_stream(self.side)     # read by the worker's kernels until the last one has run
         key = (batch_size, h, w, depth)
         rings = PrefetchingAugmenter._rings.setdefault(key, [])
         # two rings alternate, so an augmenter created while its predecessor still has copies in flight never
@@ -232,7 +233,7 @@ class PrefetchingAugmenter:
         def work_device():
             import torch
             from .. import kernels as K
-            with torch.cuda.stream(self.side):
+            with K.capture_lock, torch.cuda.stream(self.side):          # (never while the main thread captures a graph)
                 self.side.wait_event(self.ready)
                 minv, flips, gts, stats = self.aug.device_labels(self.batch_size, random.Random(self.seed_for_epoch(epoch)))
                 slot[0].copy_(torch.from_numpy(minv))

