@@ -1553,8 +1553,12 @@ class MaskRCNN(_MaskRCNN):
                                for n, p in m._parameters.items() if p is not None]
             self._tail_slots = [(m, n) for mod in (rh.box_head, rh.box_predictor, rh.mask_head, rh.mask_predictor)
                                 for _, m in mod.named_modules() for n, p in m._parameters.items() if p is not None]
-        F_ = len(frames)
-        imgs = torch.cat([f.to(torch.float32) for f in frames])
+        # a shorter run (the tail of a sequence) is padded with copies of its last frame up to the nominal run length:
+        # one batched graph and one set of per-frame graphs per model instead of one set per run length (a capture
+        # costs far more than the few wasted trunk passes)
+        nominal = max(int(os.environ.get("EOSVOS_FRAME_BATCH", "5")), len(frames))
+        F_ = nominal
+        imgs = torch.cat([f.to(torch.float32) for f in frames] + [frames[-1].to(torch.float32)] * (nominal - len(frames)))
         key = ("frames_pre", F_, h, w, cfg["mode"], cfg["has_target"], cfg["post"], cfg["pre"], cfg["nms"], device.index)
         self._frame_cfg = cfg
         K.zero_pool.reset()

@@ -400,6 +400,9 @@ def test_batched_lookahead_matches_per_frame_inference(mode, monkeypatch):
     monkeypatch.setattr(model, "prefetch_frames", lambda fs, ht: calls.append(len(fs)) or real(fs, ht))
     probs, boxes = E.run_frames(model, iter(dev_frames), start, on_frame=lambda i, t, p, b: seen.append(i))
     assert calls == [5, 2] and seen == list(range(7)) and model._lookahead is None
+    # the run of 2 is padded to the nominal length: one batched graph, at most 5 per-frame graphs
+    assert sum(1 for k in model._graphs if k[0] == "frames_pre") == 1
+    assert sum(1 for k in model._graphs if k[0] == "frame_tail") <= 5
     assert probs.shape == (7, 1, 240, 427) and torch.isfinite(probs).all() and 0 <= probs.min() and probs.max() <= 1
     # lock-step: both paths from the same target (the frame's predecessor ground truth), same uniforms
     same, ious = [], []
