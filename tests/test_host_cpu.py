@@ -296,6 +296,50 @@ def test_meta_optimizer_mirrors_reference_api():
         o.step(net(torch.ones(1, 3, 8, 8)).sum())
 
 
+def test_run_frames_lookahead_protocol(monkeypatch):
+    """Host logic of run_frames' look-ahead (no GPU: a stand-in model): frames are announced in runs of
+    EOSVOS_FRAME_BATCH before the first of them is run, the next run is announced only after the last frame of the
+    current one ran, every frame is run exactly once and in order, and the announcement is dropped at the end."""
+    from eosvos_b200.util import evaluate as E
+
+    class Rpn:
+        _eval_augment_proposals_mode = None
+
+    class Stub:
+        def __init__(self):
+            self.rpn, self.num_classes, self.events, self._lookahead = Rpn(), 2, [], None
+
+        def eval(self):
+            return self
+
+        def lookahead_ok(self):
+            return True
+
+        def prefetch_frames(self, frames, has_target):
+            self.events.append(("announce", [int(f[0, 0, 0, 0]) for f in frames], has_target))
+            self._lookahead = object()
+            return True
+
+        def __call__(self, inputs, targets):
+            self.events.append(("run", int(inputs[0, 0, 0, 0])))
+            self.last_propagated_target = self.last_target_stats = None
+            return torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 4)
+
+    for batch, want in (("3", [[0, 1, 2], [3, 4, 5], [6, 7]]), ("5", [[0, 1, 2, 3, 4], [5, 6, 7]]), ("1", [])):
+        monkeypatch.setenv("EOSVOS_FRAME_BATCH", batch)
+        m = Stub()
+        frames = (torch.full((1, 3, 4, 4), float(i)) for i in range(8))
+        seen = []
+        probs, boxes = E.run_frames(m, frames, None, on_frame=lambda i, t, p, b: seen.append(i))
+        assert probs.shape[0] == 8 and seen == list(range(8)) and m._lookahead is None
+        assert [e[1] for e in m.events if e[0] == "run"] == list(range(8))
+        assert [e[1] for e in m.events if e[0] == "announce"] == want
+        assert all(e[2] is False for e in m.events if e[0] == "announce")
+        for run in want:                       # announced before its first frame, after the previous run's last one
+            k = m.events.index(("announce", run, False))
+            assert m.events[k + 1] == ("run", run[0]) and (run[0] == 0 or m.events[k - 1] == ("run", run[0] - 1))
+
+
 def test_ona_schedule_and_sharding():
     import eosvos_b200  # noqa: F401
     from eosvos_b200.util import shard, synthetic
