@@ -316,7 +316,7 @@ class ConvGnFn(torch.autograd.Function):
         wf = prep_conv_w(w)
         N = x.shape[0]
         # statistics ride in the conv epilogue when the K loop is long enough to hide them: measured on every
-        # ResNet-50 shape (tools/bench_gn_fprop.py), the fused form wins whenever K >= 4 * Cout and loses or ties
+        # ResNet-50 shape (round-1 sweep), the fused form wins whenever K >= 4 * Cout and loses or ties
         # for the expanding 1x1 convs (K <= Cout / 2: the epilogue, whose length grows with Cout, is the bound there
         # and a separate pass over the mostly L2-resident output is cheaper)
         if w.shape[1] * w.shape[2] * w.shape[3] >= 2 * w.shape[0]:
