@@ -6,6 +6,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import model_oracle as MO  # noqa: E402
+from tests.conftest import statistical  # noqa: E402
 
 
 def test_fused_update_autograd_matches_torch():
@@ -103,6 +104,7 @@ def test_bptt_chain_exact_on_small_model():
         assert torch.allclose(a_, b_, rtol=1e-4, atol=1e-7)
 
 
+@statistical()
 def test_meta_gradients_vs_oracle():
     """First-order BPTT through 2 fine-tune steps + meta frame on the full model.  To keep the comparison about
     arithmetic (not about which RoIs a noisy NMS lets through), both sides get the same fixed proposal set in every
@@ -158,6 +160,7 @@ def test_meta_gradients_vs_oracle():
     assert all(float(p.min()) >= 0.0 for n, p in opt.named_parameters() if n.startswith("log_init_lr"))
 
 
+@statistical()
 def test_meta_run_worker_follows_reference_worker():
     """`eosvos_b200.util.meta_run.meta_run` (reference signature and shared-memory protocol) on the synthetic DAVIS
     train tree of tests/golden/meta_run.pt, with the configuration the UNMODIFIED reference worker ran under: the

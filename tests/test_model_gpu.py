@@ -26,6 +26,7 @@ from oracle import model_oracle as MO  # noqa: E402
 from oracle import ops_oracle as O  # noqa: E402
 
 _real_randperm = torch.randperm
+from tests.conftest import statistical  # noqa: E402
 
 
 def det_randperm(seed):
@@ -102,6 +103,7 @@ def test_api_surface_matches_reference():
 
 
 @pytest.mark.parametrize("kind", ["LOVASZ", "BCE"])
+@statistical()
 def test_train_step_parity(kind):
     model, opt, oracle, oopt, dev, tol = build_pair(kind)
     img, tgt = frame()
@@ -175,6 +177,7 @@ def _finetune_and_sync(model, opt, oracle, dev, img, tgt, iters):
     return hist
 
 
+@statistical()
 def test_finetune_then_inference_parity():
     """e-OSVOS-style: fine-tune on the first frame (CUDA), then propagate over frames.  Inference is compared
     from IDENTICAL state (fine-tuned weights copied into the oracle).  score_thresh is lowered to 0.05 on both
@@ -279,6 +282,7 @@ def test_full_size_properties():
     assert (p1 - p2).abs().mean().item() < 1e-3 and (iou >= 0.99 or (m1 | m2).sum().item() == 0)
 
 
+@statistical()
 def test_graphed_trunk_matches_eager():
     """The CUDA-graphed trunk (ResNet + FPN + RPN head, static parameter arena, in-place fused update) must follow the
     eager trunk over several fine-tune steps: same seeds -> losses within rounding noise, every gradient finite.
@@ -369,6 +373,7 @@ def test_evaluate_sequence_online_adaptation():
 
 
 @pytest.mark.parametrize("mode", ["EXTEND", None])
+@statistical()
 def test_batched_lookahead_matches_per_frame_inference(mode, monkeypatch):
     """The batched look-ahead (transform / trunk / RPN head / proposal selection of a run of frames in one graph, the
     per-frame remainder replayed on its slices) against one whole-frame graph per frame.  The only numerical difference

@@ -30,6 +30,7 @@ from oracle import evaluate_oracle as EO  # noqa: E402
 from oracle import model_oracle as MO  # noqa: E402
 from oracle import ops_oracle as O  # noqa: E402
 from tests.test_model_gpu import build_pair, det_randperm, frame, rel  # noqa: E402
+from tests.conftest import statistical  # noqa: E402
 
 
 def _sync_state(opt, oracle):
@@ -54,6 +55,7 @@ def _iou(a, b):
 
 # ---------------------------------------------------------------------------------------------- a4
 @pytest.mark.parametrize("full_size", [False, True])
+@statistical()
 def test_own_proposals_match_oracle(full_size):
     """rpn_forward (mask_rcnn.py:217-344 -> tv filter_proposals) WITHOUT the fixed_proposals hook, training and
     evaluation mode: decode, per-level top-k, clip, small-box / score filter, per-level NMS, post-NMS top-n, and the
@@ -301,6 +303,7 @@ def _video(seed, T, K=1, h=480, w=854):
     return fr, torch.from_numpy(labels)
 
 
+@statistical()
 def test_run_frames_matches_oracle_run_loader():
     """run_loader (helper_func.py:67-159) over 7 frames at 854x480 after 30 fine-tune iterations, hook-free (own
     proposals, own detection), frame by frame from identical state; plus the two fallback branches: an all-zero start
@@ -346,6 +349,7 @@ def test_run_frames_matches_oracle_run_loader():
 
 
 @pytest.mark.parametrize("case", ["cfg1", "ona"])
+@statistical()
 def test_evaluate_sequence_matches_oracle(case):
     """evaluate (evaluate.py:111-326) on BASELINE configs[0] -- e-OSVOS-10, batch 1, one 854x480 10-frame single-object
     video -- and on an online-adaptation schedule (e-OSVOS-12-OnA, step 3, 4 adaptation iterations, batch 3, 8 frames):
@@ -386,6 +390,7 @@ def _ref_available():
 
 
 @pytest.mark.skipif(not _ref_available(), reason="unmodified reference copy (oracle/_ref) not present")
+@statistical()
 def test_reference_call_sites_run_on_product_classes():
     """INTEGRATION.md's claim, executed: the reference's OWN `evaluate` worker (oracle/_ref, unmodified:
     src/util/evaluate.py:20-439 with its data loaders, run_loader and fine-tune loop) runs with
@@ -517,6 +522,7 @@ def test_static_shape_pipeline_matches_list_pipeline():
                 assert abs(float(det["score"][0]) - float(sl_[0][0])) <= 1e-6
 
 
+@statistical()
 def test_sparse_rpn_backward_matches_dense(monkeypatch):
     """The sparse backward of the RPN head (ops.RpnSparseFn: sampled anchors only) against the dense autograd path
     (conv dgrad / wgrad over every level) from the same weights, batch and sampler permutations.  The RPN losses must
@@ -567,6 +573,7 @@ def test_sparse_rpn_backward_matches_dense(monkeypatch):
         assert d <= (2e-2 if k == "rpn" else 3 * floor + 2e-2), (k, d, floor)
 
 
+@statistical()
 def test_youtube_vos_shaped_sequence_with_late_object():
     """BASELINE configs[3] semantics on the GPU: a 1280x720 YouTube-VOS-shaped sequence (-> 1333x749, padded to
     1344x768: the trunk shapes of the DAVIS case) with a second object whose first annotation is a LATER frame

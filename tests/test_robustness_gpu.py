@@ -9,6 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from tests.test_model_gpu import build_pair, det_randperm, frame, nchw, rel  # noqa: E402
+from tests.conftest import statistical  # noqa: E402
 
 
 def test_overflow_of_scaled_backward_is_detected(monkeypatch):
@@ -74,6 +75,7 @@ def test_large_pre_norm_magnitudes():
     assert all(bool(torch.isfinite(p).all()) for *_, p in opt.meta_model.param_groups())
 
 
+@statistical()
 def test_operand_cache_follows_out_of_band_parameter_writes():
     """Regression (advisor, round 1): the fused RAdam step and MetaModel's `.data` writers change parameter values
     without bumping autograd's version counter; the cached 16-bit operand layouts of the eager modules must be rebuilt.
