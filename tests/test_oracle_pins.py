@@ -161,3 +161,31 @@ def test_meta_gradients_match_reference():
             assert abs(got.norm().item() - ref_n) <= 2e-3 * max(ref_n, 1e-6) + 1e-9, (key, got.norm().item(), ref_n)
             if ref_n > 0:
                 assert torch.allclose(got.flatten()[:32], g["grad_samples"][key], rtol=5e-3, atol=1e-6 * max(ref_n, 1e-12) + 1e-10), key
+
+
+def test_label_warp_restatement_matches_opencv():
+    """The integer-arithmetic restatement of cv2.warpAffine(INTER_NEAREST) -- the specification of the label-warp
+    kernel -- against OpenCV itself: every pixel of 150 random flip / rotate / scale draws on id maps and on a noise
+    image at three sizes, plus the inverse the augmenter hands to the kernel."""
+    import random
+    import cv2
+    import numpy as np
+    from oracle import ops_oracle as O
+    from eosvos_b200.util import augment
+    rng = random.Random(3)
+    for h, w in ((480, 854), (720, 1280), (97, 131)):
+        yy, xx = np.mgrid[:h, :w]
+        ids = np.zeros((h, w), np.float32)
+        ids[(yy - h // 2) ** 2 + (xx - w // 3) ** 2 < (h // 4) ** 2] = 1
+        ids[h // 10:h // 4, w // 2:w - 5] = 2
+        noise = (np.random.RandomState(h).rand(h, w) * 6).astype(np.int32).astype(np.float32)
+        for src in (ids, noise):
+            for _ in range(25):
+                rot, sc, fl = 60 * rng.random() - 30, 0.5 * rng.random() + 0.75, rng.random() < 0.5
+                M = cv2.getRotationMatrix2D((w / 2, h / 2), rot, sc)
+                ref = cv2.warpAffine(cv2.flip(src, 1) if fl else src, M, (w, h), flags=cv2.INTER_NEAREST)
+                assert np.array_equal(O.label_warp_nearest(src, M, fl), ref)
+        # the augmenter's inverse == the one formed inside the restatement (same operations, same order)
+        M = cv2.getRotationMatrix2D((w / 2, h / 2), 17.3, 1.11)
+        inv = augment.DeviceAugmenter.cv_inverse(M)
+        assert np.allclose(inv.reshape(2, 3) @ np.vstack([M, [0, 0, 1]])[:, :], np.hstack([np.eye(2), np.zeros((2, 1))]), atol=1e-9)
