@@ -429,6 +429,26 @@ def layer_rooflines(device, calls, peaks, reps=5):
     return rows, agg
 
 
+def ncu_traffic(kernel_substr, path=os.path.join(ROOT, "profiles", "r02_top_kernels_raw.csv")):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the first kernel whose name contains
+    `kernel_substr` in the committed `ncu --set full` capture (tools/prof_final.py); None when the file or row is absent.
+    The capture is of the roofline layers (3x3 256->256 at 3x192x336; the 201-tensor update), not of this run."""
+    import csv
+    try:
+        with open(path, newline="") as f:
+            rows = list(csv.reader(f))
+        H, units = rows[0], rows[1]
+        ki, ri, wi = H.index("Kernel Name"), H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if kernel_substr in r[ki]:
+                return (float(r[ri].replace(",", "")) * scale.get(units[ri], 1.0)
+                        + float(r[wi].replace(",", "")) * scale.get(units[wi], 1.0))
+    except Exception:
+        pass
+    return None
+
+
 def update_roofline(device, meta_optim, model, peaks, peak_kind, reps=20):
     """HBM roofline of the fused MetaOptimizer update on the real 201-tensor parameter set (528.1 MB / step)."""
     from eosvos_b200 import kernels as K
@@ -454,7 +474,9 @@ def update_roofline(device, meta_optim, model, peaks, peak_kind, reps=20):
     return {"bound": "hbm", "kernel": "meta_update_kernel (201 tensors, 43,975,515 params)",
             "achieved": round(nbytes / dur / 1e9, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
             "frac": round(nbytes / dur / 1e9 / peak, 4), "bytes_per_launch": nbytes, "us_per_launch": round(dur * 1e6, 1),
-            "traffic": None, "note": "528 MB working set > 126 MB L2; back-to-back launches"}
+            "traffic": ncu_traffic("meta_update_kernel"),
+            "note": "528 MB working set > 126 MB L2; back-to-back launches; traffic = DRAM bytes of one launch in the "
+                    "committed ncu capture (profiles/r02_top_kernels_raw.csv)"}
 
 
 def small_kernel_rooflines(device, peaks, n_pos=32):
@@ -943,7 +965,11 @@ def main():
                                 "achieved": a["tflops"], "peak": float(peaks.get("bf16_tflops", 1590.0)),
                                 "peak_kind": f"{peak_kind} burst (kernels timed alone)", "unit": "TFLOP/s",
                                 "frac": a["frac_of_tensor_peak"], "frac_of_layer_bounds": a["frac_of_layer_bounds"],
-                                "flops_per_iteration": a["gflop"] * 1e9, "us_per_iteration": a["us"], "traffic": None}
+                                "flops_per_iteration": a["gflop"] * 1e9, "us_per_iteration": a["us"],
+                                # DRAM bytes of ONE launch of the family's largest layer (3x3 256->256 at 3x192x336:
+                                # 198 MB algorithmic in + out) in the committed ncu capture
+                                "traffic": ncu_traffic("conv_fprop_kernel<256"),
+                                "traffic_of": "conv_fprop_kernel<256>, 3x3 256->256 @3x192x336, one launch (ncu --set full)"}
         else:
             line["roofline"] = line["roofline_update"]
         if world == 1 and not args.no_cpu_baseline:
