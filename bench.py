@@ -785,7 +785,7 @@ def reference_arm(args):
             "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_s": float(np.mean(fvals)),
             "config": {"workload": WORKLOAD, "sampled": "each step = 2 iterations + 2 frames; ms_per_step extrapolates "
-                                                        "the measured per-iteration / per-frame time to 10 + 3"},
+                                                        "the measured per-iteration / per-frame time to 10 + 5"},
             "gpu_launches": 0, "wall_s": wall,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": base["cores"], "kind": base["kind"],
                              "sample": base["sample"]},
