@@ -436,13 +436,22 @@ static int run_wgrad(const AView& a_view, const AView& b_view, const int extent[
   p.n_tiles_n = (n_valid + bn - 1) / bn;
   const int m_tiles = (m_valid + 127) / 128;
   const long long base_ctas = (long long)m_tiles * p.n_tiles_n * num_taps;
+  // narrow (64-column) tiles run three shallow-ring CTAs per SM (conv_gemm.cu::launch_wgrad case 63)
+  static const bool light_ok = [] {
+    const char* e = getenv("EOSVOS_WGRAD_LIGHT");
+    return !(e && e[0] == '0');
+  }();
+  // (only where every CTA keeps a long K loop: >= 32 pixel tiles per CTA slot; short launches lose to the extra
+  // prologues and RED epilogues -- 1x1 64->256 at 3x192x336: 34.8 us deep vs 45.1 us light; 3x3 64->64: 100 vs 47)
+  const bool light = light_ok && bn == 64 && tiles * base_ctas >= 32LL * 3 * num_sms();
+  const long long per_sm = light ? 3 : 1;
   // split the pixel reduction so that the grid is a whole number of waves (1 CTA / SM, long-running CTAs: a
   // partial trailing wave costs a full wave of time); prefer the fewest waves among near-equal efficiencies
   long long split = 1;
   if (split_hint > 0) {
     split = split_hint;
   } else {
-    const long long sms = num_sms();
+    const long long sms = num_sms() * per_sm;
     double best_eff = -1.0;
     for (int k = 1; k <= 4; ++k) {
       long long sp = (k * sms) / base_ctas;
@@ -474,7 +483,7 @@ static int run_wgrad(const AView& a_view, const AView& b_view, const int extent[
   EOSVOS_TRY(make_tensor_map_act(&tmA, a_view.base, 5, a_view.dims, a_view.strides, boxa, a_view.estride));
   EOSVOS_TRY(make_tensor_map_act(&tmB, b_view.base, 5, b_view.dims, b_view.strides, boxb, b_view.estride));
   dim3 grid((unsigned)split, (unsigned)(m_tiles * p.n_tiles_n), (unsigned)num_taps);
-  return launch_wgrad(bn, tmA, tmB, p, grid, stream);
+  return launch_wgrad(light ? 63 : bn, tmA, tmB, p, grid, stream);
 }
 }  // namespace eosvos
 

@@ -237,6 +237,9 @@ static int launch_wgrad_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 int launch_wgrad(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, dim3 grid,
                  cudaStream_t stream) {
   switch (bn) {
+    // 64-channel inputs: a 64-pixel K step carries a quarter of the MMA work of the wide tiles, so the CTA is bound by
+    // the latency of its own load -> MMA -> commit chain; three shallow CTAs per SM (3 stages, 75 KB) hide it
+    case 63: return launch_wgrad_t<64, 3>(tmA, tmB, p, grid, stream);
     case 64: return launch_wgrad_t<64, 6>(tmA, tmB, p, grid, stream);
     case 128: return launch_wgrad_t<128, 5>(tmA, tmB, p, grid, stream);
     case 256: return launch_wgrad_t<256, 4>(tmA, tmB, p, grid, stream);
